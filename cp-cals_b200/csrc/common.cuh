@@ -1,0 +1,62 @@
+// Shared device/host structures of the B200 CP-CALS engine.
+//
+// Device-resident state replaces the reference's host-side MultiKtensor registry (include/multi_ktensor.h:12-47):
+// every queued model owns a ModelDesc; the scheduler kernel (sched.cuh) admits / evicts / compacts without a host
+// round trip and every compute kernel reads the live set from SchedState.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CALS_MAX_MODES 8
+#define CALS_MAX_OUTER (CALS_MAX_MODES - 2)
+
+enum ModelState : int { MODEL_QUEUED = 0, MODEL_LIVE = 1, MODEL_EVICT = 2, MODEL_DONE = 3 };
+
+// One CP model (reference: Ktensor + RegistryEntry).  Factors of a queued / finished model live in the per-mode
+// "home" matrices at columns [home_col, home_col+rank); while live they occupy buffer columns [col, col+rank).
+struct ModelDesc {
+  int rank;
+  int home_col;
+  int jk_mode; // -1: regular
+  int jk_fiber;
+  long long gram_off; // doubles; n_modes matrices of rank*rank, mode-major
+  int state;
+  int col;
+  int iters;
+  int chol_info;
+  double error, fit, old_fit;
+};
+
+struct SchedState {
+  int n_models;
+  int next;   // queue head (FIFO)
+  int n_live;
+  int C;      // active buffer columns
+  int cur;    // which of the two factor buffers is current
+  int changed; // set by the scheduler when columns have to move this iteration
+  int done;
+  int flags;  // CALS_B200_FORCE_MAX_ITER | CALS_B200_ALWAYS_EVICT_FIRST
+  int max_iter;
+  int buffer_cols;
+  int n_evict; // models flagged for eviction by the last fit step
+  int pad_;
+  double tol;
+  double x_norm;
+  unsigned long long global_iter;
+  unsigned long long n_admitted;
+  unsigned long long comp_sum;
+};
+
+// Geometry shared by all kernels: extents and leading dimensions.
+struct Geom {
+  int n_modes;
+  int dims[CALS_MAX_MODES];
+  int ldF[CALS_MAX_MODES]; // leading dimension of factor buffers / home matrices / G (dims rounded up to even)
+};
+
+struct FactorPtrs {
+  double *buf[2][CALS_MAX_MODES]; // ping-pong multi-factor buffers, ldF[n] x buffer_cols
+  double *home[CALS_MAX_MODES];   // ldF[n] x total_cols
+};
+
+static inline int round_up_int(int x, int m) { return (x + m - 1) / m * m; }

@@ -1,0 +1,1022 @@
+// Host side of the C ABI (include/cals_b200.h): context, device memory, tensor maps and the iteration loop that replaces
+// the do/while of cals::cp_cals (reference src/cals.cpp:174-382).  No cuBLAS, no CPU fallback: every entry point fails
+// with an error string when the device or the sm_100a kernels are unavailable.
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/cals_b200.h"
+#include "common.cuh"
+#include "mttkrp.cuh"
+#include "prep.cuh"
+#include "sched.cuh"
+#include "update.cuh"
+
+using namespace calsb200;
+
+namespace {
+
+std::string g_create_error;
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct HostModel {
+  int rank, jk_mode, jk_fiber;
+  std::vector<double> factors; // concatenated I_n x rank blocks (dense, ld = I_n)
+};
+
+// Everything whose size depends on the number of buffer columns.
+struct Buffers {
+  int cols = 0;
+  FactorPtrs fac{};
+  double *G = nullptr;
+  double *ws = nullptr;
+  size_t ws_tiles = 0;
+  MttkrpMaps maps[CALS_MAX_MODES];
+  MttkrpGeom mg[CALS_MAX_MODES];
+  int wm[CALS_MAX_MODES];
+  std::vector<void *> allocs;
+};
+
+} // namespace
+
+struct cals_b200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  PFN_encodeTiled encode = nullptr;
+
+  // tensor
+  Geom geo{};
+  long long nX = 0;
+  double *Xp = nullptr; // original order, pitch ldX0
+  double *Xt = nullptr; // modes 0 and 1 swapped, pitch ldX1
+  int ldX0 = 0, ldX1 = 0;
+  double *jk_norms = nullptr; // dims[0]
+  double *d_norm = nullptr;
+  double x_norm = 0.0;
+  bool have_tensor = false;
+
+  // params
+  int buffer_cols = 4200;
+  int max_iter = 200;
+  double tol = 1e-7;
+  unsigned flags = 0;
+  int timing = 0;
+  int variant = CALS_B200_MTTKRP_DMMA;
+
+  // models
+  std::vector<HostModel> hmodels;
+  std::vector<ModelDesc> hdesc;
+  int total_cols = 0, max_rank = 0;
+  long long gram_doubles = 0;
+  bool uploaded = false;
+  bool results_fresh = false;
+
+  // run-time device state
+  Buffers bufs;
+  double *home0[CALS_MAX_MODES] = {}; // pristine copy of the initial home matrices (for rerun)
+  ModelDesc *d_models = nullptr;
+  SchedState *d_st = nullptr;
+  int *d_live = nullptr, *d_live_tmp = nullptr, *d_gather = nullptr, *d_evict = nullptr;
+  double *d_gram = nullptr, *d_lambda = nullptr;
+  int *h_flags = nullptr, *d_flags = nullptr;
+  std::vector<void *> run_allocs;
+  int run_cols = 0, run_total_cols = 0, run_models = 0;
+
+  // host mirrors of results
+  std::vector<double> h_home[CALS_MAX_MODES];
+  std::vector<double> h_lambda;
+
+  std::vector<cudaEvent_t> ev_pool;
+  bool dmma_attr_done[16] = {};
+  size_t update_attr_smem = 0;
+};
+
+namespace {
+
+int fail(cals_b200_ctx *c, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = buf;
+  else
+    g_create_error = buf;
+  return 1;
+}
+
+#define CU_TRY(c, expr)                                                                                               \
+  do {                                                                                                                \
+    cudaError_t e__ = (expr);                                                                                         \
+    if (e__ != cudaSuccess)                                                                                           \
+      return fail((c), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);                  \
+  } while (0)
+
+template <typename T> int dev_alloc(cals_b200_ctx *c, T **p, size_t n, std::vector<void *> &track) {
+  void *q = nullptr;
+  CU_TRY(c, cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+  track.push_back(q);
+  *p = (T *)q;
+  return 0;
+}
+
+void free_all(std::vector<void *> &v) {
+  for (void *p : v)
+    cudaFree(p);
+  v.clear();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tile configuration
+constexpr int WN_FIXED = 4;
+
+int pick_wm(int In) {
+  // All consumer warps share the M range of the CTA tile.  m8 sub-tiles that fall completely outside G are skipped
+  // by the kernel, so the cost of a choice is the number of m8 sub-tiles computed plus a per-tile overhead; prefer
+  // the larger tile on ties.  (WM = 7, 8 exceed the 168-register budget of a 288-thread CTA and spill.)
+  int best = 6;
+  double best_cost = 1e30;
+  for (int wm = 6; wm >= 4; wm--) {
+    const int mt = 8 * wm, tiles = (In + mt - 1) / mt;
+    const double cost = (double)((In + 7) / 8) + 0.25 * tiles;
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = wm;
+    }
+  }
+  return best;
+}
+
+template <int WM> int smem_bytes() { return TileCfg<WM, WN_FIXED>::SMEM_BYTES; }
+
+int tile_m(int wm) { return 8 * wm; }
+constexpr int TILE_N = TileCfg<4, WN_FIXED>::N_TILE;
+
+int encode_map(cals_b200_ctx *c, CUtensorMap *map, void *base, int rank, const cuuint64_t *dims,
+               const cuuint64_t *strides_bytes, const cuuint32_t *box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(c, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu %llu ..)", (int)r, rank,
+                (unsigned long long)dims[0], (unsigned long long)dims[1]);
+  return 0;
+}
+
+// Build per-mode geometry and TMA descriptors for a set of buffers.
+int build_mode_plans(cals_b200_ctx *c, Buffers &b) {
+  const Geom &geo = c->geo;
+  const int N = geo.n_modes;
+  for (int n = 0; n < N; n++) {
+    MttkrpGeom g{};
+    g.mode = n;
+    g.In = geo.dims[n];
+    g.p_mode = (n == 0) ? 1 : 0;
+    g.Ip = geo.dims[g.p_mode];
+    g.ldG = geo.ldF[n];
+    for (int k = 0; k < N; k++)
+      g.ldF[k] = geo.ldF[k];
+    int no = 0;
+    long long lmul = 1, umul = 1;
+    for (int k = 0; k < N; k++) {
+      if (k == n || k == g.p_mode)
+        continue;
+      g.outer_mode[no] = k;
+      g.outer_dim[no] = geo.dims[k];
+      if (n != 0 && k < n) {
+        g.outer_lmul[no] = (int)lmul;
+        g.outer_umul[no] = 0;
+        lmul *= geo.dims[k];
+      } else {
+        g.outer_lmul[no] = 0;
+        g.outer_umul[no] = (int)umul;
+        umul *= geo.dims[k];
+      }
+      no++;
+    }
+    g.n_outer = no;
+    if (no < 1)
+      return fail(c, "tensors need at least 3 modes (reference asserts the same, src/cals.cpp:52)");
+    g.P_tiles = (g.Ip + KT - 1) / KT;
+    g.QC = (g.outer_dim[0] + OC - 1) / OC;
+    long long S = 1;
+    for (int k = 1; k < no; k++)
+      S *= g.outer_dim[k];
+    if (S > 0x7fffffff / std::max(1, g.QC * g.P_tiles))
+      return fail(c, "tensor too large for 32-bit chunk indices");
+    g.S = (int)S;
+    const int wm = pick_wm(g.In);
+    b.wm[n] = wm;
+    g.m_tiles = (g.In + tile_m(wm) - 1) / tile_m(wm);
+    b.mg[n] = g;
+
+    // X view (P, L', M, U)
+    const long long Lp = lmul, U = umul;
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4] = {(cuuint32_t)KT, 1, (cuuint32_t)tile_m(wm), 1};
+    void *base;
+    if (n == 0) {
+      base = c->Xt;
+      dims[0] = geo.dims[1];
+      dims[1] = 1;
+      dims[2] = geo.dims[0];
+      dims[3] = (cuuint64_t)U;
+      strides[0] = (cuuint64_t)c->ldX1 * 8;
+      strides[1] = (cuuint64_t)c->ldX1 * 8;
+      strides[2] = (cuuint64_t)c->ldX1 * geo.dims[0] * 8;
+    } else {
+      base = c->Xp;
+      dims[0] = geo.dims[0];
+      dims[1] = (cuuint64_t)Lp;
+      dims[2] = geo.dims[n];
+      dims[3] = (cuuint64_t)U;
+      strides[0] = (cuuint64_t)c->ldX0 * 8;
+      strides[1] = (cuuint64_t)c->ldX0 * Lp * 8;
+      strides[2] = (cuuint64_t)c->ldX0 * Lp * geo.dims[n] * 8;
+    }
+    if (encode_map(c, &b.maps[n].X, base, 4, dims, strides, box))
+      return 1;
+    for (int cu = 0; cu < 2; cu++) {
+      cuuint64_t d2[2] = {(cuuint64_t)g.Ip, (cuuint64_t)b.cols};
+      cuuint64_t s2[1] = {(cuuint64_t)geo.ldF[g.p_mode] * 8};
+      cuuint32_t bx[2] = {(cuuint32_t)KT, (cuuint32_t)TILE_N};
+      if (encode_map(c, &b.maps[n].B[cu], b.fac.buf[cu][g.p_mode], 2, d2, s2, bx))
+        return 1;
+      const int q = g.outer_mode[0];
+      cuuint64_t d3[2] = {(cuuint64_t)geo.dims[q], (cuuint64_t)b.cols};
+      cuuint64_t s3[1] = {(cuuint64_t)geo.ldF[q] * 8};
+      cuuint32_t bw[2] = {(cuuint32_t)OC, (cuuint32_t)TILE_N};
+      if (encode_map(c, &b.maps[n].W[cu], b.fac.buf[cu][q], 2, d3, s3, bw))
+        return 1;
+    }
+  }
+  return 0;
+}
+
+int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, int home_cols) {
+  const Geom &geo = c->geo;
+  b.cols = cols;
+  int max_ld = 0;
+  for (int n = 0; n < geo.n_modes; n++) {
+    max_ld = std::max(max_ld, geo.ldF[n]);
+    for (int cu = 0; cu < 2; cu++) {
+      if (dev_alloc(c, &b.fac.buf[cu][n], (size_t)geo.ldF[n] * cols, b.allocs))
+        return 1;
+      CU_TRY(c, cudaMemsetAsync(b.fac.buf[cu][n], 0, (size_t)geo.ldF[n] * cols * 8, c->stream));
+    }
+    if (with_home_cols) {
+      if (dev_alloc(c, &b.fac.home[n], (size_t)geo.ldF[n] * home_cols, b.allocs))
+        return 1;
+      CU_TRY(c, cudaMemsetAsync(b.fac.home[n], 0, (size_t)geo.ldF[n] * home_cols * 8, c->stream));
+    }
+  }
+  if (dev_alloc(c, &b.G, (size_t)max_ld * cols, b.allocs))
+    return 1;
+  if (build_mode_plans(c, b))
+    return 1;
+  size_t tiles = 0, tile_elems = 0;
+  const int n_tiles_max = (cols + TILE_N - 1) / TILE_N;
+  for (int n = 0; n < geo.n_modes; n++) {
+    tiles = std::max(tiles, (size_t)(2 * c->sm_count + 2 * b.mg[n].m_tiles * n_tiles_max + 8));
+    tile_elems = std::max(tile_elems, (size_t)tile_m(b.wm[n]) * TILE_N);
+  }
+  b.ws_tiles = tiles;
+  if (dev_alloc(c, &b.ws, tiles * tile_elems, b.allocs))
+    return 1;
+  return 0;
+}
+
+template <int WM>
+int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override) {
+  auto kern = mttkrp_dmma_kernel<WM, WN_FIXED>;
+  if (!c->dmma_attr_done[WM]) {
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<WM>()));
+    c->dmma_attr_done[WM] = true;
+  }
+  const int G = c->sm_count;
+  kern<<<G, MTTKRP_THREADS, smem_bytes<WM>(), c->stream>>>(b.maps[n], b.mg[n], c->d_st, b.fac, b.ws, C_override);
+  const int cols = C_override > 0 ? C_override : b.cols;
+  dim3 rg((cols + 31) / 32, (b.mg[n].In + 31) / 32);
+  mttkrp_reduce_kernel<8 * WM, TILE_N><<<rg, 256, 0, c->stream>>>(b.mg[n], c->d_st, b.ws, b.G, G, C_override);
+  return 0;
+}
+
+int launch_mttkrp(cals_b200_ctx *c, Buffers &b, int n, int C_override, int variant) {
+  if (variant == CALS_B200_MTTKRP_NAIVE) {
+    NaiveGeom ng{};
+    ng.n_modes = c->geo.n_modes;
+    ng.mode = n;
+    long long stride = 1;
+    for (int k = 0; k < ng.n_modes; k++) {
+      ng.dims[k] = c->geo.dims[k];
+      ng.ldF[k] = c->geo.ldF[k];
+      ng.xstride[k] = stride;
+      stride *= (k == 0) ? c->ldX0 : c->geo.dims[k];
+    }
+    ng.ldG = c->geo.ldF[n];
+    const int cols = C_override > 0 ? C_override : b.cols;
+    const long long total = (long long)ng.dims[n] * cols;
+    mttkrp_naive_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(ng, c->d_st, c->Xp, b.fac, b.G,
+                                                                                 C_override);
+    return 0;
+  }
+  switch (b.wm[n]) {
+  case 4:
+    return launch_dmma<4>(c, b, n, C_override);
+  case 5:
+    return launch_dmma<5>(c, b, n, C_override);
+  default:
+    return launch_dmma<6>(c, b, n, C_override);
+  }
+}
+
+int ensure_dummy_state(cals_b200_ctx *c) {
+  if (!c->d_st) {
+    CU_TRY(c, cudaMalloc((void **)&c->d_st, sizeof(SchedState)));
+    CU_TRY(c, cudaMemset(c->d_st, 0, sizeof(SchedState)));
+  }
+  return 0;
+}
+
+void release_run(cals_b200_ctx *c) {
+  free_all(c->bufs.allocs);
+  free_all(c->run_allocs);
+  c->bufs = Buffers();
+  for (auto &p : c->home0)
+    p = nullptr;
+  c->d_models = nullptr;
+  c->d_live = c->d_live_tmp = c->d_gather = c->d_evict = nullptr;
+  c->d_gram = c->d_lambda = nullptr;
+  c->uploaded = false;
+}
+
+void release_tensor(cals_b200_ctx *c) {
+  release_run(c);
+  if (c->Xt && c->Xt != c->Xp)
+    cudaFree(c->Xt);
+  if (c->Xp)
+    cudaFree(c->Xp);
+  if (c->jk_norms)
+    cudaFree(c->jk_norms);
+  c->Xp = c->Xt = c->jk_norms = nullptr;
+  c->have_tensor = false;
+}
+
+int install_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const double *src, bool src_on_device) {
+  if (n_modes < 3 || n_modes > CALS_MAX_MODES)
+    return fail(c, "n_modes must be in [3, %d], got %d", CALS_MAX_MODES, n_modes);
+  release_tensor(c);
+  long long nX = 1;
+  for (int n = 0; n < n_modes; n++) {
+    if (modes[n] < 1 || modes[n] > (1u << 30))
+      return fail(c, "mode %d has unsupported extent %llu", n, (unsigned long long)modes[n]);
+    c->geo.dims[n] = (int)modes[n];
+    c->geo.ldF[n] = round_up_int((int)modes[n], 2);
+    nX *= (long long)modes[n];
+  }
+  c->geo.n_modes = n_modes;
+  c->nX = nX;
+  const int I0 = c->geo.dims[0], I1 = c->geo.dims[1];
+  c->ldX0 = round_up_int(I0, 2);
+  c->ldX1 = round_up_int(I1, 2);
+  const long long rest0 = nX / I0, rest2 = nX / ((long long)I0 * I1);
+
+  double *dense = nullptr;
+  bool dense_owned = false;
+  if (src_on_device) {
+    dense = const_cast<double *>(src);
+  } else if (c->ldX0 == I0) {
+    // the upload lands directly in Xp
+  } else {
+    CU_TRY(c, cudaMalloc((void **)&dense, (size_t)nX * 8));
+    dense_owned = true;
+    CU_TRY(c, cudaMemcpyAsync(dense, src, (size_t)nX * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU_TRY(c, cudaMalloc((void **)&c->Xp, (size_t)c->ldX0 * rest0 * 8));
+  if (!src_on_device && c->ldX0 == I0) {
+    CU_TRY(c, cudaMemcpyAsync(c->Xp, src, (size_t)nX * 8, cudaMemcpyHostToDevice, c->stream));
+    dense = c->Xp;
+  } else if (c->ldX0 == I0) {
+    CU_TRY(c, cudaMemcpyAsync(c->Xp, dense, (size_t)nX * 8, cudaMemcpyDeviceToDevice, c->stream));
+  } else {
+    pad_copy_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(dense, c->Xp, I0, c->ldX0, rest0);
+  }
+  CU_TRY(c, cudaMalloc((void **)&c->Xt, (size_t)c->ldX1 * I0 * rest2 * 8));
+  {
+    dim3 grid((I0 + 31) / 32, (I1 + 31) / 32, (unsigned)std::min<long long>(rest2, 65535));
+    swap01_copy_kernel<<<grid, 256, 0, c->stream>>>(dense, c->Xt, I0, I1, c->ldX1, rest2);
+  }
+  // norms: one pass over Xp
+  CU_TRY(c, cudaMalloc((void **)&c->jk_norms, (size_t)(I0 + 1) * 8));
+  c->d_norm = c->jk_norms + I0;
+  {
+    const int ctas = (int)std::min<long long>(std::max<long long>(rest0 / 4, 1), (long long)c->sm_count * 4);
+    double *partial = nullptr;
+    CU_TRY(c, cudaMalloc((void **)&partial, (size_t)ctas * I0 * 8));
+    rowsumsq_partial_kernel<<<ctas, 256, 256 * 8, c->stream>>>(c->Xp, I0, c->ldX0, rest0, partial);
+    rowsumsq_final_kernel<<<1, 256, 0, c->stream>>>(partial, ctas, I0, c->jk_norms, c->d_norm);
+    CU_TRY(c, cudaMemcpyAsync(&c->x_norm, c->d_norm, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaFree(partial);
+  }
+  if (dense_owned)
+    cudaFree(dense);
+  CU_TRY(c, cudaGetLastError());
+  c->have_tensor = true;
+  return 0;
+}
+
+// Upload the queued models and allocate every run-time structure.
+int prepare_run(cals_b200_ctx *c) {
+  if (!c->have_tensor)
+    return fail(c, "no tensor set");
+  if (c->hmodels.empty())
+    return fail(c, "model queue is empty");
+  const Geom &geo = c->geo;
+  const int N = geo.n_modes, M = (int)c->hmodels.size();
+  release_run(c);
+
+  c->hdesc.assign(M, ModelDesc{});
+  int col = 0, max_rank = 0;
+  long long goff = 0;
+  for (int m = 0; m < M; m++) {
+    const HostModel &hm = c->hmodels[m];
+    if (hm.rank > c->buffer_cols)
+      return fail(c, "model %d has rank %d > buffer_size %d: it can never be admitted", m, hm.rank, c->buffer_cols);
+    ModelDesc &d = c->hdesc[m];
+    d.rank = hm.rank;
+    d.home_col = col;
+    d.jk_mode = hm.jk_mode;
+    d.jk_fiber = hm.jk_fiber;
+    d.gram_off = goff;
+    d.state = MODEL_QUEUED;
+    col += hm.rank;
+    goff += (long long)N * hm.rank * hm.rank;
+    max_rank = std::max(max_rank, hm.rank);
+  }
+  c->total_cols = col;
+  c->max_rank = max_rank;
+  c->gram_doubles = goff;
+
+  if (alloc_buffers(c, c->bufs, c->buffer_cols, true, c->total_cols))
+    return 1;
+  if (dev_alloc(c, &c->d_models, (size_t)M, c->run_allocs) || dev_alloc(c, &c->d_live, (size_t)M, c->run_allocs) ||
+      dev_alloc(c, &c->d_live_tmp, (size_t)M, c->run_allocs) ||
+      dev_alloc(c, &c->d_gather, (size_t)c->buffer_cols, c->run_allocs) ||
+      dev_alloc(c, &c->d_evict, (size_t)c->buffer_cols, c->run_allocs) ||
+      dev_alloc(c, &c->d_gram, (size_t)goff, c->run_allocs) ||
+      dev_alloc(c, &c->d_lambda, (size_t)c->total_cols, c->run_allocs))
+    return 1;
+  if (ensure_dummy_state(c))
+    return 1;
+
+  // pack and upload the home matrices (pitch ldF)
+  for (int n = 0; n < N; n++) {
+    const int rows = geo.dims[n], ld = geo.ldF[n];
+    std::vector<double> &h = c->h_home[n];
+    h.assign((size_t)ld * c->total_cols, 0.0);
+    for (int m = 0; m < M; m++) {
+      const HostModel &hm = c->hmodels[m];
+      size_t off = 0;
+      for (int k = 0; k < n; k++)
+        off += (size_t)geo.dims[k] * hm.rank;
+      for (int j = 0; j < hm.rank; j++)
+        memcpy(&h[(size_t)(c->hdesc[m].home_col + j) * ld], &hm.factors[off + (size_t)j * rows], (size_t)rows * 8);
+    }
+    CU_TRY(c, cudaMemcpyAsync(c->bufs.fac.home[n], h.data(), h.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    if (dev_alloc(c, &c->home0[n], h.size(), c->run_allocs))
+      return 1;
+    CU_TRY(c, cudaMemcpyAsync(c->home0[n], c->bufs.fac.home[n], h.size() * 8, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  c->h_lambda.assign((size_t)c->total_cols, 0.0);
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  c->uploaded = true;
+  c->run_cols = c->buffer_cols;
+  return 0;
+}
+
+cudaEvent_t get_event(cals_b200_ctx *c, size_t i) {
+  while (c->ev_pool.size() <= i) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->ev_pool.push_back(e);
+  }
+  return c->ev_pool[i];
+}
+
+int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
+  const Geom &geo = c->geo;
+  const int N = geo.n_modes, M = (int)c->hmodels.size();
+  Buffers &b = c->bufs;
+  cudaStream_t s = c->stream;
+
+  // reset device state
+  if (restore_home)
+    for (int n = 0; n < N; n++)
+      CU_TRY(c, cudaMemcpyAsync(b.fac.home[n], c->home0[n], (size_t)geo.ldF[n] * c->total_cols * 8,
+                                cudaMemcpyDeviceToDevice, s));
+  for (auto &d : c->hdesc) {
+    d.state = MODEL_QUEUED;
+    d.col = 0;
+    d.iters = 0;
+    d.chol_info = 0;
+    d.error = d.fit = d.old_fit = 0.0;
+  }
+  CU_TRY(c, cudaMemcpyAsync(c->d_models, c->hdesc.data(), (size_t)M * sizeof(ModelDesc), cudaMemcpyHostToDevice, s));
+  SchedState st{};
+  st.n_models = M;
+  st.flags = (int)c->flags;
+  st.max_iter = c->max_iter;
+  st.buffer_cols = c->buffer_cols;
+  st.tol = c->tol;
+  st.x_norm = c->x_norm;
+  CU_TRY(c, cudaMemcpyAsync(c->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s));
+  c->h_flags[0] = c->h_flags[1] = c->h_flags[2] = 0;
+
+  init_grams_kernel<<<dim3(M, N), 256, 0, s>>>(geo, b.fac, c->d_models, c->d_gram);
+
+  SchedParams sp{c->d_st, c->d_models, c->d_live, c->d_live_tmp, c->d_gather, c->d_evict, c->d_flags};
+  const int max_live = std::min(M, c->buffer_cols);
+  const dim3 move_grid((c->buffer_cols + MOVE_COLS - 1) / MOVE_COLS, N, 2);
+
+  // shared memory of the update kernel
+  UpdateParams up[CALS_MAX_MODES];
+  size_t up_smem[CALS_MAX_MODES];
+  for (int n = 0; n < N; n++) {
+    UpdateParams &u = up[n];
+    u.mode = n;
+    u.n_modes = N;
+    u.rows = geo.dims[n];
+    u.ld = geo.ldF[n];
+    const int R = c->max_rank;
+    const size_t fixed = ((size_t)2 * R * R + 2 * R + 32) * 8;
+    const size_t budget = 200 * 1024;
+    if (fixed + (size_t)33 * R * 8 > budget)
+      return fail(c, "rank %d too large for the shared-memory update kernel", R);
+    int cr = round_up_int(u.rows, 32);
+    while (fixed + (size_t)(cr + 1) * R * 8 > budget)
+      cr -= 32;
+    u.chunk_rows = cr;
+    u.chunk_pitch = cr + 1;
+    u.max_rank = R;
+    u.G = b.G;
+    u.F[0] = b.fac.buf[0][n];
+    u.F[1] = b.fac.buf[1][n];
+    u.gram_pool = c->d_gram;
+    u.lambda_home = c->d_lambda;
+    u.x_norms_jk = c->jk_norms;
+    u.models = c->d_models;
+    u.live = c->d_live;
+    u.st = c->d_st;
+    up_smem[n] = fixed + (size_t)(cr + 1) * R * 8;
+  }
+  {
+    size_t mx = 0;
+    for (int n = 0; n < N; n++)
+      mx = std::max(mx, up_smem[n]);
+    if (mx > c->update_attr_smem) {
+      CU_TRY(c, cudaFuncSetAttribute(model_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+      c->update_attr_smem = mx;
+    }
+  }
+
+  const int RA = 4; // host run-ahead in CALS iterations
+  cudaEvent_t ring[RA];
+  for (int i = 0; i < RA; i++)
+    ring[i] = get_event(c, i);
+  cudaEvent_t ev_begin = get_event(c, RA), ev_end = get_event(c, RA + 1);
+  size_t ev_next = RA + 2;
+  std::vector<std::pair<size_t, int>> timed; // (first event index, kind 0 = mttkrp, 1 = update)
+
+  uint64_t launches = 1, mttkrp_launches = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  CU_TRY(c, cudaEventRecord(ev_begin, s));
+  long long it = 0;
+  for (;; it++) {
+    sched_kernel<<<1, 32, 0, s>>>(sp);
+    move_kernel<<<move_grid, 256, 0, s>>>(geo, b.fac, c->d_st, c->d_gather, c->d_evict);
+    launches += 2;
+    for (int n = 0; n < N; n++) {
+      if (c->timing) {
+        timed.push_back({ev_next, 0});
+        cudaEventRecord(get_event(c, ev_next), s);
+      }
+      if (launch_mttkrp(c, b, n, 0, c->variant))
+        return 1;
+      mttkrp_launches++;
+      launches += (c->variant == CALS_B200_MTTKRP_NAIVE) ? 1 : 2;
+      if (c->timing) {
+        cudaEventRecord(get_event(c, ev_next + 1), s);
+        timed.push_back({ev_next + 1, 1});
+        ev_next += 2;
+      }
+      model_update_kernel<<<max_live, UPDATE_THREADS, up_smem[n], s>>>(up[n]);
+      launches++;
+      if (c->timing) {
+        cudaEventRecord(get_event(c, ev_next), s);
+        ev_next += 1;
+      }
+    }
+    CU_TRY(c, cudaEventRecord(ring[it % RA], s));
+    if (it >= RA - 1)
+      CU_TRY(c, cudaEventSynchronize(ring[(it + 1) % RA]));
+    if (*(volatile int *)&c->h_flags[0])
+      break;
+    if (c->timing && ev_next > 60000) {
+      return fail(c, "timing level 1 supports at most ~6000 iterations per run");
+    }
+  }
+  CU_TRY(c, cudaEventRecord(ev_end, s));
+  CU_TRY(c, cudaStreamSynchronize(s));
+  CU_TRY(c, cudaGetLastError());
+  auto t1 = std::chrono::steady_clock::now();
+
+  // scalars back
+  CU_TRY(c, cudaMemcpy(&st, c->d_st, sizeof st, cudaMemcpyDeviceToHost));
+  if (rep) {
+    memset(rep, 0, sizeof *rep);
+    rep->iter = st.global_iter;
+    rep->n_ktensors = st.n_admitted;
+    rep->ktensor_comp_sum = st.comp_sum;
+    rep->x_norm = c->x_norm;
+    rep->total_time = std::chrono::duration<double>(t1 - t0).count();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_begin, ev_end);
+    rep->device_ms = ms;
+    rep->mttkrp_launches = mttkrp_launches;
+    rep->kernel_launches = launches;
+    if (c->timing) {
+      double mt = 0, ut = 0;
+      for (auto &t : timed) {
+        float e = 0;
+        cudaEventElapsedTime(&e, get_event(c, t.first), get_event(c, t.first + 1));
+        (t.second == 0 ? mt : ut) += e;
+      }
+      rep->mttkrp_ms = mt;
+      rep->update_ms = ut;
+    }
+  }
+  c->results_fresh = false;
+  return 0;
+}
+
+int download_results(cals_b200_ctx *c) {
+  if (c->results_fresh)
+    return 0;
+  if (!c->uploaded)
+    return fail(c, "no run to fetch results from");
+  const Geom &geo = c->geo;
+  for (int n = 0; n < geo.n_modes; n++)
+    CU_TRY(c, cudaMemcpyAsync(c->h_home[n].data(), c->bufs.fac.home[n], c->h_home[n].size() * 8,
+                              cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->h_lambda.data(), c->d_lambda, c->h_lambda.size() * 8, cudaMemcpyDeviceToHost,
+                            c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->hdesc.data(), c->d_models, c->hdesc.size() * sizeof(ModelDesc), cudaMemcpyDeviceToHost,
+                            c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  c->results_fresh = true;
+  return 0;
+}
+
+void copy_model_out(cals_b200_ctx *c, int m, double *const *factors_out, double *lambda_out,
+                    cals_b200_model_stats *stats) {
+  const Geom &geo = c->geo;
+  const ModelDesc &d = c->hdesc[m];
+  if (factors_out)
+    for (int n = 0; n < geo.n_modes; n++) {
+      if (!factors_out[n])
+        continue;
+      const int rows = geo.dims[n], ld = geo.ldF[n];
+      for (int j = 0; j < d.rank; j++)
+        memcpy(factors_out[n] + (size_t)j * rows, &c->h_home[n][(size_t)(d.home_col + j) * ld], (size_t)rows * 8);
+    }
+  if (lambda_out)
+    memcpy(lambda_out, &c->h_lambda[d.home_col], (size_t)d.rank * 8);
+  if (stats) {
+    stats->iters = (uint64_t)d.iters;
+    stats->error = d.error;
+    stats->fit = d.fit;
+    stats->old_fit = d.old_fit;
+    stats->chol_info = d.chol_info;
+  }
+}
+
+} // namespace
+
+// =================================================================================================================
+extern "C" {
+
+const char *cals_b200_version(void) { return "cals_b200 0.1 (sm_100a)"; }
+
+const char *cals_b200_last_error(const cals_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int cals_b200_create(cals_b200_ctx **out, int device) {
+  if (!out)
+    return fail(nullptr, "null ctx pointer");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, "no CUDA device available (%s): the B200 path has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev)
+    return fail(nullptr, "device %d out of range (have %d)", device, ndev);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
+                prop.minor);
+  cals_b200_ctx *c = new cals_b200_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreate(&c->stream)) != cudaSuccess) {
+    fail(nullptr, "cudaSetDevice/cudaStreamCreate: %s", cudaGetErrorString(e));
+    delete c;
+    return 1;
+  }
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    fail(nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    delete c;
+    return 1;
+  }
+  c->encode = (PFN_encodeTiled)fn;
+  if (cudaHostAlloc((void **)&c->h_flags, 64, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void **)&c->d_flags, c->h_flags, 0) != cudaSuccess) {
+    fail(nullptr, "cannot allocate mapped host flags");
+    delete c;
+    return 1;
+  }
+  memset(c->h_flags, 0, 64);
+  *out = c;
+  return 0;
+}
+
+int cals_b200_destroy(cals_b200_ctx *c) {
+  if (!c)
+    return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  release_tensor(c);
+  if (c->d_st)
+    cudaFree(c->d_st);
+  if (c->h_flags)
+    cudaFreeHost(c->h_flags);
+  for (auto e : c->ev_pool)
+    cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int cals_b200_set_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const double *host_X) {
+  if (!c || !modes || !host_X)
+    return fail(c, "null argument");
+  cudaSetDevice(c->device);
+  return install_tensor(c, n_modes, modes, host_X, false);
+}
+
+int cals_b200_set_tensor_dev(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const double *X_dev) {
+  if (!c || !modes || !X_dev)
+    return fail(c, "null argument");
+  cudaSetDevice(c->device);
+  return install_tensor(c, n_modes, modes, X_dev, true);
+}
+
+int cals_b200_configure(cals_b200_ctx *c, uint64_t buffer_cols, uint64_t max_iterations, double tol, unsigned flags) {
+  if (!c)
+    return 1;
+  if (buffer_cols < 1 || buffer_cols > (1u << 24))
+    return fail(c, "buffer_cols out of range");
+  if (max_iterations < 1 || max_iterations > 0x7fffffffull)
+    return fail(c, "max_iterations out of range");
+  if ((int)buffer_cols != c->buffer_cols)
+    c->uploaded = false;
+  c->buffer_cols = (int)buffer_cols;
+  c->max_iter = (int)max_iterations;
+  c->tol = tol;
+  c->flags = flags;
+  return 0;
+}
+
+int cals_b200_set_timing(cals_b200_ctx *c, int level) {
+  if (!c)
+    return 1;
+  c->timing = level;
+  return 0;
+}
+
+int cals_b200_set_mttkrp_variant(cals_b200_ctx *c, int variant) {
+  if (!c)
+    return 1;
+  if (variant != CALS_B200_MTTKRP_DMMA && variant != CALS_B200_MTTKRP_NAIVE)
+    return fail(c, "unknown MTTKRP variant %d", variant);
+  c->variant = variant;
+  return 0;
+}
+
+int cals_b200_clear_models(cals_b200_ctx *c) {
+  if (!c)
+    return 1;
+  c->hmodels.clear();
+  c->hdesc.clear();
+  c->uploaded = false;
+  c->results_fresh = false;
+  return 0;
+}
+
+int cals_b200_enqueue_model(cals_b200_ctx *c, uint64_t rank, const double *const *host_factors, int jk_mode,
+                            int64_t jk_fiber, int *model_id) {
+  if (!c || !host_factors)
+    return fail(c, "null argument");
+  if (!c->have_tensor)
+    return fail(c, "set the tensor before enqueueing models");
+  if (rank < 1 || rank > 4096)
+    return fail(c, "rank %llu out of range", (unsigned long long)rank);
+  const Geom &geo = c->geo;
+  if (jk_mode >= geo.n_modes)
+    return fail(c, "jk_mode %d out of range", jk_mode);
+  if (jk_mode >= 0 && (jk_fiber < 0 || jk_fiber >= geo.dims[jk_mode]))
+    return fail(c, "jk_fiber %lld out of range", (long long)jk_fiber);
+  HostModel hm;
+  hm.rank = (int)rank;
+  hm.jk_mode = jk_mode < 0 ? -1 : jk_mode;
+  hm.jk_fiber = jk_mode < 0 ? 0 : (int)jk_fiber;
+  size_t total = 0;
+  for (int n = 0; n < geo.n_modes; n++)
+    total += (size_t)geo.dims[n] * rank;
+  hm.factors.resize(total);
+  size_t off = 0;
+  for (int n = 0; n < geo.n_modes; n++) {
+    if (!host_factors[n])
+      return fail(c, "factor %d is null", n);
+    memcpy(&hm.factors[off], host_factors[n], (size_t)geo.dims[n] * rank * 8);
+    off += (size_t)geo.dims[n] * rank;
+  }
+  c->hmodels.push_back(std::move(hm));
+  c->uploaded = false;
+  if (model_id)
+    *model_id = (int)c->hmodels.size() - 1;
+  return 0;
+}
+
+int cals_b200_run(cals_b200_ctx *c, cals_b200_report *rep) {
+  if (!c)
+    return 1;
+  cudaSetDevice(c->device);
+  if (prepare_run(c))
+    return 1;
+  if (run_loop(c, rep, false))
+    return 1;
+  return download_results(c);
+}
+
+int cals_b200_rerun(cals_b200_ctx *c, cals_b200_report *rep) {
+  if (!c)
+    return 1;
+  cudaSetDevice(c->device);
+  if (!c->uploaded)
+    return fail(c, "rerun needs a previous cals_b200_run with the same queue and buffer size");
+  return run_loop(c, rep, true);
+}
+
+int cals_b200_fetch_model(cals_b200_ctx *c, int model_id, double *const *factors_out, double *lambda_out,
+                          cals_b200_model_stats *stats) {
+  if (!c)
+    return 1;
+  cudaSetDevice(c->device);
+  if (model_id < 0 || model_id >= (int)c->hdesc.size())
+    return fail(c, "model id %d out of range", model_id);
+  if (download_results(c))
+    return 1;
+  copy_model_out(c, model_id, factors_out, lambda_out, stats);
+  return 0;
+}
+
+int cals_b200_fetch_all(cals_b200_ctx *c, double *const *factors_out, double *const *lambda_out,
+                        cals_b200_model_stats *stats) {
+  if (!c)
+    return 1;
+  cudaSetDevice(c->device);
+  if (download_results(c))
+    return 1;
+  const int N = c->geo.n_modes;
+  for (int m = 0; m < (int)c->hdesc.size(); m++)
+    copy_model_out(c, m, factors_out ? factors_out + (size_t)m * N : nullptr, lambda_out ? lambda_out[m] : nullptr,
+                   stats ? stats + m : nullptr);
+  return 0;
+}
+
+int cals_b200_tensor_norm(cals_b200_ctx *c, double *norm_out) {
+  if (!c || !norm_out)
+    return fail(c, "null argument");
+  if (!c->have_tensor)
+    return fail(c, "no tensor set");
+  *norm_out = c->x_norm;
+  return 0;
+}
+
+int cals_b200_jk_norms(cals_b200_ctx *c, double *out) {
+  if (!c || !out)
+    return fail(c, "null argument");
+  if (!c->have_tensor)
+    return fail(c, "no tensor set");
+  cudaSetDevice(c->device);
+  CU_TRY(c, cudaMemcpy(out, c->jk_norms, (size_t)c->geo.dims[0] * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int cals_b200_mttkrp(cals_b200_ctx *c, int mode, uint64_t cols, const double *const *host_factors, double *host_G,
+                     int variant, int repeats, double *ms_out) {
+  if (!c || !host_factors || !host_G)
+    return fail(c, "null argument");
+  if (!c->have_tensor)
+    return fail(c, "no tensor set");
+  cudaSetDevice(c->device);
+  const Geom &geo = c->geo;
+  if (mode < 0 || mode >= geo.n_modes)
+    return fail(c, "mode out of range");
+  if (cols < 1 || cols > (1u << 24))
+    return fail(c, "cols out of range");
+  if (ensure_dummy_state(c))
+    return 1;
+  Buffers b;
+  int rc = alloc_buffers(c, b, (int)cols, false, 0);
+  if (!rc) {
+    for (int k = 0; k < geo.n_modes && !rc; k++) {
+      if (k == mode)
+        continue;
+      if (!host_factors[k]) {
+        rc = fail(c, "factor %d is null", k);
+        break;
+      }
+      cudaError_t e = cudaMemcpy2DAsync(b.fac.buf[0][k], (size_t)geo.ldF[k] * 8, host_factors[k],
+                                        (size_t)geo.dims[k] * 8, (size_t)geo.dims[k] * 8, cols,
+                                        cudaMemcpyHostToDevice, c->stream);
+      if (e != cudaSuccess)
+        rc = fail(c, "upload of factor %d failed: %s", k, cudaGetErrorString(e));
+    }
+  }
+  if (!rc) {
+    cudaEvent_t e0 = get_event(c, 0), e1 = get_event(c, 1);
+    if (repeats < 1)
+      repeats = 1;
+    rc = launch_mttkrp(c, b, mode, (int)cols, variant); // warm-up + result
+    cudaEventRecord(e0, c->stream);
+    for (int r = 1; r < repeats && !rc; r++)
+      rc = launch_mttkrp(c, b, mode, (int)cols, variant);
+    cudaEventRecord(e1, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess)
+      e = cudaGetLastError();
+    if (e != cudaSuccess)
+      rc = fail(c, "MTTKRP kernel failed: %s", cudaGetErrorString(e));
+    if (!rc && ms_out) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      *ms_out = repeats > 1 ? ms / (repeats - 1) : 0.0;
+    }
+    if (!rc) {
+      e = cudaMemcpy2D(host_G, (size_t)geo.dims[mode] * 8, b.G, (size_t)geo.ldF[mode] * 8,
+                       (size_t)geo.dims[mode] * 8, cols, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess)
+        rc = fail(c, "download of G failed: %s", cudaGetErrorString(e));
+    }
+  }
+  free_all(b.allocs);
+  return rc;
+}
+
+int cals_b200_device_info(cals_b200_ctx *c, int *sm_count, size_t *free_bytes, size_t *total_bytes) {
+  if (!c)
+    return 1;
+  cudaSetDevice(c->device);
+  if (sm_count)
+    *sm_count = c->sm_count;
+  size_t f = 0, t = 0;
+  CU_TRY(c, cudaMemGetInfo(&f, &t));
+  if (free_bytes)
+    *free_bytes = f;
+  if (total_bytes)
+    *total_bytes = t;
+  return 0;
+}
+
+} // extern "C"

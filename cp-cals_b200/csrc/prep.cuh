@@ -1,0 +1,104 @@
+// Streaming (HBM-bound) kernels that run once per tensor: device layouts and norms.
+//
+//   pad_copy_kernel        X (dense, mode 0 fastest)  ->  Xp with the fastest dimension padded to an even pitch
+//   swap01_copy_kernel     X -> Xt with modes 0 and 1 swapped (mode 1 fastest), pitch padded to even
+//   rowsumsq_*             per mode-0 index sums of squares in ONE pass over X, from which both
+//                            ||X||          Tensor::norm                       reference include/tensor.h:196
+//                            ||X||_jk[i]    utils::calculate_jackknifing_norms reference src/utils/utils.cpp:103-152
+//                          follow.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace calsb200 {
+
+__global__ void pad_copy_kernel(const double *__restrict__ X, double *__restrict__ Xp, int I0, int ld0,
+                                long long rest) {
+  const long long total = (long long)ld0 * rest;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % ld0);
+    const long long r = e / ld0;
+    Xp[e] = i < I0 ? X[r * I0 + i] : 0.0;
+  }
+}
+
+// Xt[i1 + ld1 * (i0 + I0 * r)] = X[i0 + I0 * (i1 + I1 * r)],  grid = (ceil(I0/32), ceil(I1/32), rest2 chunks)
+__global__ void swap01_copy_kernel(const double *__restrict__ X, double *__restrict__ Xt, int I0, int I1, int ld1,
+                                   long long rest2) {
+  __shared__ double t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 256 threads
+  const int a0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  for (long long r = blockIdx.z; r < rest2; r += gridDim.z) {
+    const double *Xs = X + r * (long long)I0 * I1;
+    double *Xd = Xt + r * (long long)ld1 * I0;
+    __syncthreads();
+    for (int bb = ty; bb < 32; bb += 8) {
+      const int i0 = a0 + tx, i1 = b0 + bb;
+      t[bb][tx] = (i0 < I0 && i1 < I1) ? Xs[(long long)i1 * I0 + i0] : 0.0;
+    }
+    __syncthreads();
+    for (int aa = ty; aa < 32; aa += 8) {
+      const int i0 = a0 + aa, i1 = b0 + tx;
+      if (i0 < I0 && i1 < ld1)
+        Xd[(long long)i0 * ld1 + i1] = (i1 < I1) ? t[tx][aa] : 0.0;
+    }
+  }
+}
+
+// partial[cta][i] = sum over this CTA's column range of X(i, j)^2.   X viewed I0 x cols with pitch ld0.
+__global__ void __launch_bounds__(256)
+rowsumsq_partial_kernel(const double *__restrict__ Xp, int I0, int ld0, long long cols, double *__restrict__ partial) {
+  extern __shared__ double sh[]; // 256 doubles
+  const int rpp = min(256, (I0 + 31) / 32 * 32); // rows per pass
+  const int lanes = 256 / rpp;                   // column lanes
+  const int r = threadIdx.x % rpp, cl = threadIdx.x / rpp;
+  const long long per = (cols + gridDim.x - 1) / gridDim.x;
+  const long long j0 = per * blockIdx.x, j1 = min(cols, j0 + per);
+  for (int rb = 0; rb < I0; rb += rpp) {
+    const int i = rb + r;
+    double acc = 0.0;
+    if (i < I0 && cl < lanes)
+      for (long long j = j0 + cl; j < j1; j += lanes) {
+        const double v = Xp[j * ld0 + i];
+        acc += v * v;
+      }
+    __syncthreads();
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (cl == 0 && i < I0) {
+      double s = 0.0;
+      for (int l = 0; l < lanes; l++)
+        s += sh[l * rpp + r];
+      partial[(long long)blockIdx.x * I0 + i] = s;
+    }
+  }
+}
+
+// rowsum[i] = sum_cta partial[cta][i] (fixed order); out[0] = ||X||, jk[i] = sqrt(total - rowsum[i]).  One CTA.
+__global__ void __launch_bounds__(256)
+rowsumsq_final_kernel(const double *__restrict__ partial, int n_ctas, int I0, double *__restrict__ jk,
+                      double *__restrict__ out_norm) {
+  __shared__ double sh[256];
+  double local = 0.0;
+  for (int i = threadIdx.x; i < I0; i += 256) {
+    double s = 0.0;
+    for (int c = 0; c < n_ctas; c++)
+      s += partial[(long long)c * I0 + i];
+    jk[i] = s;
+    local += s;
+  }
+  sh[threadIdx.x] = local;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double total = sh[0];
+  for (int i = threadIdx.x; i < I0; i += 256)
+    jk[i] = sqrt(total - jk[i]);
+  if (threadIdx.x == 0)
+    out_norm[0] = sqrt(total);
+}
+
+} // namespace calsb200

@@ -1,0 +1,321 @@
+// Per-model small operations, one CTA per live model, fused into a single kernel per mode:
+//
+//   H = hadamard of the other modes' Gramians     ops::hadamard_but_one      reference src/utils/utils.cpp:161-172
+//   L = chol_lower(H)                               dpotrf('L')                reference src/utils/update.cpp:183-185
+//   F = G * L^-T * L^-1 (row-wise two solves)       2 x dtrsm                  reference src/utils/update.cpp:187-190
+//   jackknife row := 0                              Ktensor::set_jk_fiber(0)   reference include/ktensor.h:316-325
+//   lambda, column scaling                          Ktensor::normalize(n, it)  reference src/ktensor.cpp:66-83
+//   Gram_n = F^T F                                  ops::update_gramian        reference src/utils/utils.cpp:174-178
+// and, after the last mode,
+//   P = hadamard of all Gramians, fast error, fit   ops::hadamard_all, error::compute_fast_error,
+//                                                   Ktensor::calculate_new_fit reference src/utils/utils.cpp:156,
+//                                                   src/utils/error.cpp:64-89, include/ktensor.h:178-183
+//   eviction predicate / iters++                    reference src/cals.cpp:336-347
+//
+// The MTTKRP result G is read from its own buffer and the updated factor is written to the multi-factor buffer, so the
+// last mode's G is still intact for the error term (the reference keeps a copy: G_last, src/cals.cpp:75,230-234).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace calsb200 {
+
+constexpr int UPDATE_THREADS = 256;
+
+struct UpdateParams {
+  int mode;
+  int n_modes;
+  int rows;      // I_n
+  int ld;        // ldF[n] == ldG
+  int chunk_rows; // rows staged in shared memory at a time (multiple of 32)
+  int chunk_pitch; // odd pitch (in doubles) of the staged chunk
+  int max_rank;
+  const double *G;         // MTTKRP result, ld x C
+  double *F[2];            // multi-factor buffers for this mode
+  double *gram_pool;
+  double *lambda_home;     // per home column
+  const double *x_norms_jk; // modes[0] entries or nullptr
+  ModelDesc *models;
+  const int *live;
+  SchedState *st;
+};
+
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+  // scratch: >= 32 doubles of shared memory
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0)
+    scratch[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (warp == 0) {
+    t = lane < (blockDim.x >> 5) ? scratch[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0)
+      scratch[0] = t;
+  }
+  __syncthreads();
+  t = scratch[0];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(UPDATE_THREADS)
+model_update_kernel(const UpdateParams p) {
+  SchedState *st = p.st;
+  if ((int)blockIdx.x >= st->n_live)
+    return;
+  const int m = p.live[blockIdx.x];
+  ModelDesc &md = p.models[m];
+  const int R = md.rank, col = md.col, cur = st->cur;
+  const int rows = p.rows, ld = p.ld, n = p.mode, N = p.n_modes;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int iters = md.iters;
+
+  extern __shared__ double sm[];
+  double *Hs = sm;                 // R x R : H, then its Cholesky factor (lower)
+  double *Gs = Hs + R * R;         // R x R : new Gramian of mode n
+  double *cstat = Gs + R * R;      // 2R : per column reduction value / index ; then lambda, 1/lambda
+  double *red = cstat + 2 * R;     // 32
+  double *S = red + 32;            // chunk_rows x R, pitch chunk_pitch
+  const int pitch = p.chunk_pitch, CR = p.chunk_rows;
+
+  double *grams = p.gram_pool + md.gram_off;
+  const double *Gm = p.G + (size_t)col * ld;
+  double *Fm = p.F[cur] + (size_t)col * ld;
+
+  // ---- H = hadamard of the other Gramians ----
+  for (int e = tid; e < R * R; e += nthr) {
+    double h = 1.0;
+    for (int k = 0; k < N; k++)
+      if (k != n)
+        h *= grams[(size_t)k * R * R + e];
+    Hs[e] = h;
+    Gs[e] = 0.0;
+  }
+  for (int e = tid; e < 2 * R; e += nthr)
+    cstat[e] = (e < R) ? -1.0 : 0.0; // value (sum of squares starts at 0 below; max-abs starts at -1), index
+  __syncthreads();
+  if (iters == 1)
+    for (int e = tid; e < R; e += nthr)
+      cstat[e] = 0.0;
+
+  // ---- Cholesky, right-looking, in shared memory ----
+  int chol_fail = 0;
+  for (int j = 0; j < R; j++) {
+    __syncthreads();
+    const double d = Hs[j + j * R];
+    if (!(d > 0.0))
+      chol_fail = 1; // LAPACK would stop here (info = j+1); the reference only logs it and carries on
+    const double sd = sqrt(d);
+    __syncthreads();
+    if (tid == 0)
+      Hs[j + j * R] = sd;
+    for (int i = j + 1 + tid; i < R; i += nthr)
+      Hs[i + j * R] /= sd;
+    __syncthreads();
+    // trailing update of the lower triangle: H[i][k] -= L[i][j] * L[k][j],  j < k <= i < R
+    const int t = R - j - 1;
+    for (int e = tid; e < t * t; e += nthr) {
+      const int i = j + 1 + e % t, k = j + 1 + e / t;
+      if (k <= i)
+        Hs[i + k * R] -= Hs[i + j * R] * Hs[k + j * R];
+    }
+  }
+  __syncthreads();
+
+  const bool jk_here = (md.jk_mode == n);
+  const int jk_row = md.jk_fiber;
+  const bool single = rows <= CR;
+
+  // ---- pass 1: solve rows, jackknife row, column statistics ----
+  for (int r0 = 0; r0 < rows; r0 += CR) {
+    const int nr = min(CR, rows - r0);
+    __syncthreads();
+    for (int e = tid; e < nr * R; e += nthr) {
+      const int rr = e % nr, j = e / nr;
+      S[rr + j * pitch] = Gm[(size_t)j * ld + r0 + rr];
+    }
+    __syncthreads();
+    for (int rr = tid; rr < nr; rr += nthr) {
+      double *row = S + rr;
+      // y L^T = g   (forward, right-looking)
+      for (int j = 0; j < R; j++) {
+        const double y = row[j * pitch] / Hs[j + j * R];
+        row[j * pitch] = y;
+        for (int k = j + 1; k < R; k++)
+          row[k * pitch] -= y * Hs[k + j * R];
+      }
+      // x L = y     (backward, right-looking)
+      for (int j = R - 1; j >= 0; j--) {
+        const double x = row[j * pitch] / Hs[j + j * R];
+        row[j * pitch] = x;
+        for (int k = 0; k < j; k++)
+          row[k * pitch] -= x * Hs[j + k * R];
+      }
+      if (jk_here && r0 + rr == jk_row)
+        for (int j = 0; j < R; j++)
+          row[j * pitch] *= 0.0;
+    }
+    __syncthreads();
+    // column statistics: warp per column
+    {
+      const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
+      for (int j = warp; j < R; j += nw) {
+        const double *cj = S + j * pitch;
+        if (iters == 1) {
+          double ss = 0.0;
+          for (int rr = lane; rr < nr; rr += 32)
+            ss += cj[rr] * cj[rr];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+          if (lane == 0)
+            cstat[j] += ss;
+        } else {
+          double best = -1.0;
+          int bi = 0x7fffffff;
+          for (int rr = lane; rr < nr; rr += 32) {
+            const double a = fabs(cj[rr]);
+            if (a > best) { // strictly greater keeps the first index within this lane's (increasing) sequence
+              best = a;
+              bi = r0 + rr;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) {
+              best = ob;
+              bi = oi;
+            }
+          }
+          if (lane == 0 && best > cstat[j]) { // earlier chunks win ties (first index of the maximum, as idamax)
+            cstat[j] = best;
+            cstat[R + j] = (double)bi;
+          }
+        }
+      }
+    }
+    if (!single) {
+      __syncthreads();
+      for (int e = tid; e < nr * R; e += nthr) {
+        const int rr = e % nr, j = e / nr;
+        Fm[(size_t)j * ld + r0 + rr] = S[rr + j * pitch];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- lambda ----
+  for (int j = tid; j < R; j += nthr) {
+    double lam;
+    if (iters == 1)
+      lam = sqrt(cstat[j]);
+    else {
+      const int bi = (int)cstat[R + j];
+      lam = single ? S[bi + j * pitch] : Fm[(size_t)j * ld + bi];
+    }
+    p.lambda_home[md.home_col + j] = lam;
+    cstat[j] = lam;
+    cstat[R + j] = (lam != 0.0) ? 1.0 / lam : 1.0;
+  }
+  __syncthreads();
+
+  // ---- pass 2: scale, write factor, accumulate Gramian (and <F, G> per column for the error) ----
+  const bool last_mode = (n == N - 1);
+  double term3 = 0.0;
+  for (int r0 = 0; r0 < rows; r0 += CR) {
+    const int nr = min(CR, rows - r0);
+    __syncthreads();
+    for (int e = tid; e < nr * R; e += nthr) {
+      const int rr = e % nr, j = e / nr;
+      const double raw = single ? S[rr + j * pitch] : Fm[(size_t)j * ld + r0 + rr];
+      const double v = raw * cstat[R + j];
+      S[rr + j * pitch] = v;
+      Fm[(size_t)j * ld + r0 + rr] = v;
+      if (last_mode)
+        term3 += cstat[j] * v * Gm[(size_t)j * ld + r0 + rr];
+    }
+    __syncthreads();
+    for (int e = tid; e < R * R; e += nthr) {
+      const int i = e % R, j = e / R;
+      const double *ci = S + i * pitch, *cj = S + j * pitch;
+      double g = 0.0;
+      for (int rr = 0; rr < nr; rr++)
+        g += ci[rr] * cj[rr];
+      Gs[e] += g;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < R * R; e += nthr)
+    grams[(size_t)n * R * R + e] = Gs[e];
+  if (tid == 0 && chol_fail)
+    md.chol_info += 1;
+
+  if (!last_mode)
+    return;
+
+  // ---- fast error, fit, eviction decision ----
+  double term2 = 0.0;
+  for (int e = tid; e < R * R; e += nthr) {
+    const int i = e % R, j = e / R;
+    double pe = Gs[e];
+    for (int k = 0; k < N - 1; k++)
+      pe *= grams[(size_t)k * R * R + e];
+    term2 += cstat[i] * cstat[j] * pe;
+  }
+  term2 = block_sum(term2, red);
+  term3 = block_sum(term3, red);
+  if (tid == 0) {
+    double xn = st->x_norm;
+    if (md.jk_mode >= 0 && p.x_norms_jk)
+      xn = p.x_norms_jk[md.jk_fiber];
+    const double err = sqrt(fmax(xn * xn + term2 - 2.0 * term3, 0.0));
+    const double old_fit = md.fit;
+    const double fit = 1.0 - fabs(err) / st->x_norm;
+    md.error = err;
+    md.old_fit = old_fit;
+    md.fit = fit;
+    if (!(st->flags & 2u)) {
+      bool evict;
+      if (st->flags & 1u)
+        evict = iters >= st->max_iter;
+      else
+        evict = (fabs(old_fit - fit) < st->tol) || (iters >= st->max_iter);
+      if (evict) {
+        md.state = MODEL_EVICT;
+        atomicAdd(&st->n_evict, 1);
+      } else
+        md.iters = iters + 1;
+    }
+  }
+}
+
+// Gramians of the incoming factors of every queued model (MultiKtensor::add computes them on admission,
+// reference src/multi_ktensor.cpp:89-95; here all at once before the loop starts).  One CTA per (model, mode).
+__global__ void __launch_bounds__(256)
+init_grams_kernel(const Geom geo, const FactorPtrs fac, const ModelDesc *__restrict__ models, double *gram_pool) {
+  const int m = blockIdx.x, n = blockIdx.y;
+  const ModelDesc &md = models[m];
+  const int R = md.rank, rows = geo.dims[n], ld = geo.ldF[n];
+  const double *F = fac.home[n] + (size_t)md.home_col * ld;
+  double *gr = gram_pool + md.gram_off + (size_t)n * R * R;
+  for (int e = threadIdx.x; e < R * R; e += blockDim.x) {
+    const int i = e % R, j = e / R;
+    const double *ci = F + (size_t)i * ld, *cj = F + (size_t)j * ld;
+    double g = 0.0;
+    for (int r = 0; r < rows; r++)
+      g += ci[r] * cj[r];
+    gr[e] = g;
+  }
+}
+
+} // namespace calsb200

@@ -1,0 +1,114 @@
+/* cals_b200.h -- C ABI of the B200-native CP-CALS hot path.
+ *
+ * The reference (HPAC/CP-CALS) has no FFI of its own: its accelerator seam is the C++ API
+ *     cals::cp_cals(const Tensor&, KtensorQueue&, CalsParams&)      reference include/cals.h:196
+ *     cals::jk_cp_cals(const Tensor&, vector<Ktensor>&, CalsParams&) reference include/cals.h:198
+ * with `CalsParams::cuda` (include/cals.h:150) routing the MTTKRP to cuBLAS + one kernel
+ * (src/utils/mttkrp.cpp:156-162,233-265,341-420; src/utils/khatri_rao.cu:40).  This header is the thin C layer that
+ * the C++ host code of this repository (include/cals.h ... , cp-cals_b200/host/) calls instead; a maintainer of the
+ * reference would bind exactly these entry points from src/cals.cpp.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (message via cals_b200_last_error); no
+ * exceptions cross this boundary; all pointers are HOST pointers unless the name ends in _dev; all matrices are
+ * FP64 column-major; the tensor is column-major with mode 0 fastest (reference src/tensor.cpp:143-180).  One
+ * context per caller thread.  There is no CPU fallback: without a CUDA device every call fails loudly.
+ */
+#ifndef CALS_B200_H
+#define CALS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cals_b200_ctx cals_b200_ctx;
+
+/* flags for cals_b200_configure (CalsParams::force_max_iter / always_evict_first, reference include/cals.h:158-159) */
+#define CALS_B200_FORCE_MAX_ITER 1u
+#define CALS_B200_ALWAYS_EVICT_FIRST 2u
+
+/* MTTKRP kernel variants (test hook / tuning knob; the product default is CALS_B200_MTTKRP_DMMA) */
+#define CALS_B200_MTTKRP_DMMA 0  /* TMA + mbarrier pipeline, FP64 tensor-core mma.sync, stream-K partials */
+#define CALS_B200_MTTKRP_NAIVE 1 /* one thread per output element; cross-check only */
+
+/* Filled by cals_b200_run: the fields of the reference's CalsReport (include/cals.h:27-63) that the path produces. */
+typedef struct cals_b200_report {
+  uint64_t iter;             /* CalsReport::iter: global CALS iterations executed */
+  uint64_t n_ktensors;       /* CalsReport::n_ktensors */
+  uint64_t ktensor_comp_sum; /* CalsReport::ktensor_comp_sum */
+  double x_norm;             /* CalsReport::X_norm */
+  double total_time;         /* seconds, host wall clock around the device loop (CalsReport::total_time) */
+  double device_ms;          /* CUDA-event time of the whole iteration loop */
+  double mttkrp_ms;          /* CUDA-event time summed over the MTTKRP kernels (0 unless timing enabled) */
+  double update_ms;          /* CUDA-event time summed over the per-model update/fit kernels (idem) */
+  uint64_t mttkrp_launches;  /* number of MTTKRP kernel launches */
+  uint64_t kernel_launches;  /* all kernels launched by this run */
+  double mttkrp_flops;       /* algorithmic flop executed by the MTTKRPs: sum over launches of 2*nX*C */
+} cals_b200_report;
+
+typedef struct cals_b200_model_stats {
+  uint64_t iters;    /* Ktensor::iters */
+  double error;      /* Ktensor::approx_error */
+  double fit;        /* Ktensor::fit */
+  double old_fit;    /* Ktensor::old_fit */
+  int32_t chol_info; /* number of Cholesky failures met (reference only logs dpotrf's info, update.cpp:184) */
+} cals_b200_model_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------ */
+int cals_b200_create(cals_b200_ctx **ctx, int device);
+int cals_b200_destroy(cals_b200_ctx *ctx);
+const char *cals_b200_last_error(const cals_b200_ctx *ctx); /* ctx may be NULL: last error of create() */
+
+/* ---- target tensor  (replaces X.allocate_cudata + send_to_device_async, reference src/cals.cpp:142-147) ------- */
+/* Uploads X (prod(modes) doubles, mode 0 fastest), builds the device layouts the kernels read, and computes
+ * ||X|| (Tensor::norm, include/tensor.h:196) on the device. */
+int cals_b200_set_tensor(cals_b200_ctx *ctx, int n_modes, const uint64_t *modes, const double *host_X);
+/* Same with X already in device memory (dense, unpadded). */
+int cals_b200_set_tensor_dev(cals_b200_ctx *ctx, int n_modes, const uint64_t *modes, const double *X_dev);
+
+/* ---- parameters (CalsParams, reference include/cals.h:138-159) ------------------------------------------------ */
+int cals_b200_configure(cals_b200_ctx *ctx, uint64_t buffer_cols, uint64_t max_iterations, double tol,
+                        unsigned flags);
+/* 0: no per-kernel timing (default).  1: bracket MTTKRP / update kernels with CUDA events (adds syncs at the end). */
+int cals_b200_set_timing(cals_b200_ctx *ctx, int level);
+int cals_b200_set_mttkrp_variant(cals_b200_ctx *ctx, int variant);
+
+/* ---- model queue (KtensorQueue, reference include/cals.h:22; MultiKtensor::add, src/multi_ktensor.cpp:41) ----- */
+int cals_b200_clear_models(cals_b200_ctx *ctx);
+/* host_factors[n] -> I_n x rank column-major (ld = I_n).  jk_mode < 0: regular model; else the model is a
+ * jackknife model with row jk_fiber of factor jk_mode forced to zero (Ktensor::to_jk, include/ktensor.h:276). */
+int cals_b200_enqueue_model(cals_b200_ctx *ctx, uint64_t rank, const double *const *host_factors, int jk_mode,
+                            int64_t jk_fiber, int *model_id);
+
+/* ---- the hot path: the do/while loop of cals::cp_cals (reference src/cals.cpp:174-382) ------------------------- */
+/* Uploads the queued models, runs concurrent ALS until every model has been evicted, leaves results on the device. */
+int cals_b200_run(cals_b200_ctx *ctx, cals_b200_report *report);
+/* Re-runs from the initial factors that are already resident on the device (no host->device traffic). */
+int cals_b200_rerun(cals_b200_ctx *ctx, cals_b200_report *report);
+
+/* ---- results (Ktensor::detach copies the result back, reference src/ktensor.cpp:127-135) ----------------------- */
+int cals_b200_fetch_model(cals_b200_ctx *ctx, int model_id, double *const *factors_out, double *lambda_out,
+                          cals_b200_model_stats *stats);
+/* All models at once: factors_out[model*n_modes + n]; lambda_out[model]; stats[model]. Any pointer may be NULL. */
+int cals_b200_fetch_all(cals_b200_ctx *ctx, double *const *factors_out, double *const *lambda_out,
+                        cals_b200_model_stats *stats);
+
+/* ---- single-operation hooks (parity tests against the oracle; also the reference's unit seams) ----------------- */
+int cals_b200_tensor_norm(cals_b200_ctx *ctx, double *norm_out);
+/* utils::calculate_jackknifing_norms (reference src/utils/utils.cpp:103-152): out has modes[0] entries. */
+int cals_b200_jk_norms(cals_b200_ctx *ctx, double *out);
+/* mttkrp::mttkrp (reference src/utils/mttkrp.cpp:562) over `cols` concatenated columns: host_factors[k] is
+ * I_k x cols (entry `mode` is ignored), host_G receives I_mode x cols.  *ms_out (may be NULL) = device time. */
+int cals_b200_mttkrp(cals_b200_ctx *ctx, int mode, uint64_t cols, const double *const *host_factors, double *host_G,
+                     int variant, int repeats, double *ms_out);
+
+/* ---- introspection --------------------------------------------------------------------------------------------- */
+int cals_b200_device_info(cals_b200_ctx *ctx, int *sm_count, size_t *free_bytes, size_t *total_bytes);
+const char *cals_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CALS_B200_H */

@@ -1,0 +1,177 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle and the golden fixtures.
+
+Tolerance (north_star): per-iteration fit and factor matrices within 1e-9 relative error in FP64.
+"""
+import numpy as np
+import pytest
+
+import caseio
+import oracle
+from helpers import RTOL, assert_models_close, load_golden, rel_err, to_ktensors
+
+pytestmark = pytest.mark.gpu
+
+MTTKRP_SHAPES = [
+    ((13, 12, 11), 30),      # tiny, ragged everything
+    ((40, 40, 40), 64),      # exact tiles in M/K
+    ((100, 100, 100), 220),  # BASELINE config 1
+    ((41, 30, 29), 7),       # odd extents (pitch padding), C < 8
+    ((9, 8, 7, 6), 20),      # 4 modes
+    ((20, 6, 5, 4, 3), 33),  # 5 modes
+    ((64, 24, 50), 300),     # two n-tiles
+    ((130, 17, 90), 513),    # several m-tiles, 3 n-tiles, K tail
+]
+
+
+@pytest.mark.parametrize("modes,C", MTTKRP_SHAPES)
+@pytest.mark.parametrize("variant", ["naive", "dmma"])
+def test_mttkrp_matches_oracle(pkg, engine, modes, C, variant):
+    rng = np.random.default_rng(hash((modes, C)) % 2 ** 32)
+    X = rng.uniform(-1, 1, size=modes)
+    fs = [rng.uniform(-1, 1, size=(i, C)) for i in modes]
+    engine.set_tensor(X)
+    v = pkg.MTTKRP_NAIVE if variant == "naive" else pkg.MTTKRP_DMMA
+    for n in range(len(modes)):
+        want = oracle.mttkrp(X, fs, n)
+        got, _ = engine.mttkrp(fs, n, variant=v)
+        e = rel_err(got, want)
+        assert e <= 1e-12, "%s mode %d rel err %.3e" % (variant, n, e)
+        # column-wise as well: no column may be off even if the matrix norm hides it
+        ce = np.linalg.norm(got - want, axis=0) / np.linalg.norm(want, axis=0)
+        assert ce.max() <= 1e-11, "%s mode %d worst column %.3e at %d" % (variant, n, ce.max(), ce.argmax())
+
+
+def test_norms(engine):
+    rng = np.random.default_rng(11)
+    for modes in [(13, 12, 11), (41, 30, 29), (100, 64, 50), (7, 6, 5, 4)]:
+        X = rng.uniform(-1, 1, size=modes)
+        engine.set_tensor(X)
+        assert abs(engine.tensor_norm() - oracle.norm(X)) <= 1e-12 * oracle.norm(X)
+        assert rel_err(engine.jk_norms(), oracle.jk_norms(X)) <= 1e-12
+
+
+GOLDEN_CASES = ["forced_3d_k1", "forced_3d_k2", "forced_3d_k5", "forced_4d_queue", "jackknife_3d", "evict_first_3d"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("variant", ["naive", "dmma"])
+def test_cp_cals_matches_golden(pkg, name, variant):
+    X, ins, refs, params, report = load_golden(name)
+    kts = to_ktensors(pkg, ins)
+    p = pkg.CalsParams(max_iterations=params["max_iter"], tol=params["tol"], buffer_size=params["buffer_size"],
+                       force_max_iter=bool(params.get("force_max_iter", False)),
+                       always_evict_first=bool(params.get("always_evict_first", False)))
+    rep = pkg.cp_cals(X, kts, p, mttkrp_variant=pkg.MTTKRP_NAIVE if variant == "naive" else pkg.MTTKRP_DMMA)
+    assert rep.iter == report["iter"]
+    assert rep.n_ktensors == report["n_ktensors"]
+    assert rep.ktensor_comp_sum == report["comp_sum"]
+    assert abs(rep.X_norm - report["x_norm"]) <= 1e-12 * report["x_norm"]
+    assert_models_close(kts, refs, report["x_norm"], what=name)
+    for g, r in zip(kts, refs):
+        assert abs(g.fit_diff - r.fit_diff) <= RTOL
+
+
+def test_cp_cals_queue_tol_golden(pkg):
+    """tol-based stopping with queueing/eviction/compaction (buffer 14 < sum of ranks).  Stopping can flip by one
+    iteration through rounding (the fast error is a cancellation), so iteration counts are compared leniently and
+    factors only where the counts agree."""
+    X, ins, refs, params, report = load_golden("queue_tol_3d")
+    kts = to_ktensors(pkg, ins)
+    p = pkg.CalsParams(max_iterations=params["max_iter"], tol=params["tol"], buffer_size=params["buffer_size"])
+    rep = pkg.cp_cals(X, kts, p)
+    assert rep.n_ktensors == report["n_ktensors"] and rep.ktensor_comp_sum == report["comp_sum"]
+    same = [i for i, (g, r) in enumerate(zip(kts, refs)) if g.iters == r.iters]
+    assert len(same) >= len(refs) - 2
+    assert_models_close([kts[i] for i in same], [refs[i] for i in same], report["x_norm"], rtol=1e-7, what="queue_tol")
+    for g, r in zip(kts, refs):
+        assert abs(g.fit - (1 - abs(r.error) / report["x_norm"])) < 1e-4
+
+
+@pytest.mark.parametrize("modes,ranks,K,buffer", [
+    ((30, 20, 25), list(range(1, 11)) * 2, 6, None),        # everything resident
+    ((30, 20, 25), list(range(1, 11)) * 2, 4, 25),           # queueing
+    ((12, 9, 8, 7), [3, 1, 4, 1, 5, 9, 2, 6], 5, 12),        # 4 modes + queueing
+    ((50, 41, 33), [20, 17, 1, 12], 5, None),                # larger ranks, odd extents
+])
+def test_cp_cals_per_iteration_vs_oracle(pkg, modes, ranks, K, buffer):
+    """Per-iteration parity: forced iteration counts k = 1..K, each compared with the oracle."""
+    rng = np.random.default_rng(hash((modes, K)) % 2 ** 32)
+    X = rng.uniform(-1, 1, size=modes)
+    ms = caseio.random_models(rng, modes, ranks)
+    bs = buffer or sum(ranks)
+    with pkg.Engine(0) as eng:
+        for k in range(1, K + 1):
+            want = oracle.cp_cals(X, ms, max_iter=k, force_max_iter=True, buffer_size=bs)
+            kts = to_ktensors(pkg, ms)
+            rep = pkg.cp_cals(X, kts, pkg.CalsParams(max_iterations=k, buffer_size=bs, force_max_iter=True), engine=eng)
+            assert rep.iter == want.iters
+            assert_models_close(kts, want.models, want.x_norm, what="k=%d" % k)
+            for g, r in zip(kts, want.models):
+                assert abs(g.fit - r.fit) <= RTOL and abs(g.old_fit - r.old_fit) <= RTOL
+
+
+def test_cp_cals_config1_shape_vs_oracle(pkg):
+    """BASELINE config 1: 100x100x100, 40 models of ranks 1..10 x4, forced iterations."""
+    rng = np.random.default_rng(1)
+    modes = (100, 100, 100)
+    X = rng.uniform(-1, 1, size=modes)
+    ranks = [r for r in range(1, 11) for _ in range(4)]
+    ms = caseio.random_models(rng, modes, ranks)
+    K = 5
+    want = oracle.cp_cals(X, ms, max_iter=K, force_max_iter=True)
+    kts = to_ktensors(pkg, ms)
+    rep = pkg.cp_cals(X, kts, pkg.CalsParams(max_iterations=K, buffer_size=sum(ranks), force_max_iter=True))
+    assert rep.iter == K
+    assert_models_close(kts, want.models, want.x_norm, what="cfg1")
+
+
+def test_rerun_is_deterministic(pkg):
+    rng = np.random.default_rng(2)
+    modes = (40, 30, 20)
+    X = rng.uniform(-1, 1, size=modes)
+    ms = caseio.random_models(rng, modes, [3, 5, 2, 8, 1])
+    with pkg.Engine(0) as eng:
+        eng.set_tensor(X)
+        eng.configure(19, 7, 1e-7, force_max_iter=True)
+        eng.clear_models()
+        for m in ms:
+            eng.enqueue(m.factors)
+        eng.run()
+        first = [eng.fetch(i) for i in range(len(ms))]
+        eng.rerun()
+        second = [eng.fetch(i) for i in range(len(ms))]
+        for (f1, l1, s1), (f2, l2, s2) in zip(first, second):
+            assert all(np.array_equal(a, b) for a, b in zip(f1, f2))  # bit-exact: no atomics, fixed reduction order
+            assert np.array_equal(l1, l2) and s1.error == s2.error and s1.iters == s2.iters
+
+
+def test_jk_cp_cals_vs_oracle(pkg):
+    """jk_cp_cals (reference src/cals.cpp:397-446, without the LSAP permutation) against the oracle's cp_cals on the
+    same flagged sub-models."""
+    rng = np.random.default_rng(6)
+    modes = (8, 7, 6)
+    fs = [rng.uniform(-1, 1, size=(i, 3)) for i in modes]
+    X = caseio.ktensor_to_tensor(fs, np.ones(3)) + 0.01 * rng.standard_normal(modes)
+    bases = [pkg.Ktensor(m.factors, m.lam) for m in caseio.random_models(rng, modes, [3, 2])]
+    p = pkg.CalsParams(max_iterations=10, buffer_size=12, force_max_iter=True)
+    rep, results = pkg.jk_cp_cals(X, bases, p)
+    # the same through the oracle
+    flat_in = []
+    for b in bases:
+        bb = b.copy().denormalize().normalize()
+        for i in range(modes[0]):
+            flat_in.append(caseio.Model(factors=[F.copy() for F in bb.factors], lam=bb.lam.copy(), jk_mode=0, jk_fiber=i))
+    want = oracle.cp_cals(X, flat_in, max_iter=10, force_max_iter=True, buffer_size=12)
+    assert rep.iter == want.iters
+    flat_out = [m for g in results for m in g]
+    for got, w in zip(flat_out, want.models):
+        wk = pkg.Ktensor([F.copy() for F in w.factors], w.lam.copy(), 0, w.jk_fiber)
+        wk.set_jk_fiber(0.0)
+        wk.denormalize().normalize()
+        for n in range(3):
+            a, b = got.factors[n].copy(), wk.factors[n].copy()
+            if n == 0:
+                assert np.isnan(a[got.jk_fiber]).all()
+                a[got.jk_fiber] = 0.0
+            assert rel_err(a, b) <= RTOL
+        assert rel_err(got.lam, wk.lam) <= RTOL
