@@ -45,6 +45,7 @@ struct SchedState {
   unsigned long long global_iter;
   unsigned long long n_admitted;
   unsigned long long comp_sum;
+  unsigned long long col_iter_sum; // sum over executed iterations of the active column count C
 };
 
 // Geometry shared by all kernels: extents and leading dimensions.

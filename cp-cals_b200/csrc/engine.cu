@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -44,6 +45,7 @@ struct Buffers {
   MttkrpMaps maps[CALS_MAX_MODES];
   MttkrpGeom mg[CALS_MAX_MODES];
   int wm[CALS_MAX_MODES];
+  PlanArgs plans{}; // per-mode work partition tables (device memory) + the inputs of mttkrp_make_plan
   std::vector<void *> allocs;
 };
 
@@ -143,21 +145,24 @@ void free_all(std::vector<void *> &v) {
 // tile configuration
 constexpr int WN_FIXED = 4;
 
-int pick_wm(int In) {
-  // All consumer warps share the M range of the CTA tile.  m8 sub-tiles that fall completely outside G are skipped
-  // by the kernel, so the cost of a choice is the number of m8 sub-tiles computed plus a per-tile overhead; prefer
-  // the larger tile on ties.  (WM = 7, 8 exceed the 168-register budget of a 288-thread CTA and spill.)
-  int best = 6;
-  double best_cost = 1e30;
-  for (int wm = 6; wm >= 4; wm--) {
-    const int mt = 8 * wm, tiles = (In + mt - 1) / mt;
-    const double cost = (double)((In + 7) / 8) + 0.25 * tiles;
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = wm;
-    }
+int wm_max() {
+  static int v = 0;
+  if (!v) {
+    const char *e = getenv("CALS_B200_WM_MAX"); // tuning knob: tallest CTA tile in m8 row groups (4..8)
+    v = e ? atoi(e) : 6;
+    if (v < 4 || v > 8)
+      v = 6;
   }
-  return best;
+  return v;
+}
+
+int pick_wm(int In) {
+  // m8 row groups are split evenly over ceil(In8 / wm_max) m-tiles; the tile is then only as tall as that split needs,
+  // so that most tiles are full and run the fully unrolled path.
+  const int In8 = (In + 7) / 8;
+  const int m_tiles = (In8 + wm_max() - 1) / wm_max();
+  const int wm = (In8 + m_tiles - 1) / m_tiles;
+  return wm < 4 ? 4 : wm;
 }
 
 template <int WM> int smem_bytes() { return TileCfg<WM, WN_FIXED>::SMEM_BYTES; }
@@ -289,10 +294,22 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
   if (build_mode_plans(c, b))
     return 1;
   size_t tiles = 0, tile_elems = 0;
-  const int n_tiles_max = (cols + TILE_N - 1) / TILE_N;
+  const int n_tiles_max = ((cols + 63) / 64 + OCT_TILE - 1) / OCT_TILE;
+  b.plans = PlanArgs{};
+  b.plans.n_modes = geo.n_modes;
+  b.plans.G = c->sm_count;
   for (int n = 0; n < geo.n_modes; n++) {
-    tiles = std::max(tiles, (size_t)(2 * c->sm_count + 2 * b.mg[n].m_tiles * n_tiles_max + 8));
+    const int pairs_max = b.mg[n].m_tiles * n_tiles_max;
+    tiles = std::max(tiles, (size_t)(c->sm_count + pairs_max + 2));
     tile_elems = std::max(tile_elems, (size_t)tile_m(b.wm[n]) * TILE_N);
+    if (dev_alloc(c, &b.plans.plan[n], (size_t)plan_capacity(c->sm_count, pairs_max), b.allocs))
+      return 1;
+    b.plans.In[n] = geo.dims[n];
+    b.plans.WM[n] = b.wm[n];
+    const long long tp = (long long)b.mg[n].P_tiles * b.mg[n].S * b.mg[n].QC;
+    if (tp * pairs_max > 0x7fffffffLL)
+      return fail(c, "tensor too large for 32-bit chunk indices");
+    b.plans.Tp[n] = (int)tp;
   }
   b.ws_tiles = tiles;
   if (dev_alloc(c, &b.ws, tiles * tile_elems, b.allocs))
@@ -308,10 +325,12 @@ int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override) {
     c->dmma_attr_done[WM] = true;
   }
   const int G = c->sm_count;
-  kern<<<G, MTTKRP_THREADS, smem_bytes<WM>(), c->stream>>>(b.maps[n], b.mg[n], c->d_st, b.fac, b.ws, C_override);
+  kern<<<G, MTTKRP_THREADS, smem_bytes<WM>(), c->stream>>>(b.maps[n], b.mg[n], c->d_st, b.fac, b.plans.plan[n], b.ws,
+                                                            C_override);
   const int cols = C_override > 0 ? C_override : b.cols;
   dim3 rg((cols + 31) / 32, (b.mg[n].In + 31) / 32);
-  mttkrp_reduce_kernel<8 * WM, TILE_N><<<rg, 256, 0, c->stream>>>(b.mg[n], c->d_st, b.ws, b.G, G, C_override);
+  mttkrp_reduce_kernel<8 * WM, TILE_N><<<rg, 256, 0, c->stream>>>(b.mg[n], c->d_st, b.plans.plan[n], b.ws, b.G, G,
+                                                                  C_override);
   return 0;
 }
 
@@ -339,8 +358,12 @@ int launch_mttkrp(cals_b200_ctx *c, Buffers &b, int n, int C_override, int varia
     return launch_dmma<4>(c, b, n, C_override);
   case 5:
     return launch_dmma<5>(c, b, n, C_override);
-  default:
+  case 6:
     return launch_dmma<6>(c, b, n, C_override);
+  case 7:
+    return launch_dmma<7>(c, b, n, C_override);
+  default:
+    return launch_dmma<8>(c, b, n, C_override);
   }
 }
 
@@ -549,7 +572,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
 
   init_grams_kernel<<<dim3(M, N), 256, 0, s>>>(geo, b.fac, c->d_models, c->d_gram);
 
-  SchedParams sp{c->d_st, c->d_models, c->d_live, c->d_live_tmp, c->d_gather, c->d_evict, c->d_flags};
+  SchedParams sp{c->d_st, c->d_models, c->d_live, c->d_live_tmp, c->d_gather, c->d_evict, c->d_flags, b.plans};
   const int max_live = std::min(M, c->buffer_cols);
   const dim3 move_grid((c->buffer_cols + MOVE_COLS - 1) / MOVE_COLS, N, 2);
 
@@ -657,14 +680,23 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_begin, ev_end);
     rep->device_ms = ms;
-    rep->mttkrp_launches = mttkrp_launches;
+    // Passes launched after the queue drained (host run-ahead) find C == 0 and exit at once: they are real launches
+    // (kernel_launches) but not MTTKRP work, so the per-launch statistics only count the st.global_iter real passes.
+    const uint64_t real_mttkrp = (uint64_t)st.global_iter * (uint64_t)N;
+    rep->mttkrp_launches = real_mttkrp;
     rep->kernel_launches = launches;
+    rep->mttkrp_flops = 2.0 * (double)c->nX * (double)N * (double)st.col_iter_sum;
     if (c->timing) {
       double mt = 0, ut = 0;
+      uint64_t seen_m = 0, seen_u = 0;
       for (auto &t : timed) {
         float e = 0;
         cudaEventElapsedTime(&e, get_event(c, t.first), get_event(c, t.first + 1));
-        (t.second == 0 ? mt : ut) += e;
+        if (t.second == 0) {
+          if (seen_m++ < real_mttkrp)
+            mt += e;
+        } else if (seen_u++ < real_mttkrp)
+          ut += e;
       }
       rep->mttkrp_ms = mt;
       rep->update_ms = ut;
@@ -978,6 +1010,7 @@ int cals_b200_mttkrp(cals_b200_ctx *c, int mode, uint64_t cols, const double *co
     cudaEvent_t e0 = get_event(c, 0), e1 = get_event(c, 1);
     if (repeats < 1)
       repeats = 1;
+    mttkrp_plan_kernel<<<1, 32, 0, c->stream>>>(b.plans, (int)cols);
     rc = launch_mttkrp(c, b, mode, (int)cols, variant); // warm-up + result
     cudaEventRecord(e0, c->stream);
     for (int r = 1; r < repeats && !rc; r++)

@@ -29,7 +29,8 @@ namespace calsb200 {
 constexpr int KT = 40;           // K tile along the contiguous mode (multiple of 8, == 8 mod 16)
 constexpr int OC = 8;            // outer indices per w-chunk
 constexpr int NUM_MMA_WARPS = 8;
-constexpr int MTTKRP_THREADS = (NUM_MMA_WARPS + 1) * 32;
+constexpr int NUM_PRODUCER_WARPS = 4; // a whole warpgroup, so that setmaxnreg can hand its registers to the MMA warps
+constexpr int MTTKRP_THREADS = (NUM_MMA_WARPS + NUM_PRODUCER_WARPS) * 32;
 constexpr int X_STAGES = 4;
 
 template <int WM, int WN> struct TileCfg {
@@ -38,7 +39,7 @@ template <int WM, int WN> struct TileCfg {
   static constexpr int X_STAGE_BYTES = M_TILE * KT * 8;
   static constexpr int B_BYTES = N_TILE * KT * 8;
   static constexpr int W_BYTES = N_TILE * OC * 8;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + B_BYTES + X_STAGES * X_STAGE_BYTES + 2 * W_BYTES + 256;
+  static constexpr int SMEM_BYTES = B_BYTES + X_STAGES * X_STAGE_BYTES + 2 * W_BYTES + 256;
 };
 
 struct MttkrpGeom {
@@ -108,45 +109,244 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Stream-K bookkeeping, shared by the MTTKRP kernel and the reduce kernel (and unit-tested on the host).
-struct StreamK {
-  long long total; // chunks over all (m,n) pairs
-  int Tp;          // chunks per pair
-  int G;           // CTAs
-  int kmax;        // workspace slots reserved per pair
-  __host__ __device__ static StreamK make(int pairs, int Tp, int G) {
-    StreamK s;
-    s.Tp = Tp;
-    s.total = (long long)pairs * Tp;
-    // never more CTAs than chunks: every participating CTA owns a non-empty range, CTAs >= G stay idle
-    s.G = (int)(s.total < (long long)G ? s.total : (long long)G);
-    if (s.G < 1)
-      s.G = 1;
-    const long long share = s.total / s.G > 0 ? s.total / s.G : 1;
-    long long k = (Tp + share - 1) / share + 1;
-    s.kmax = (int)(k < Tp ? k : Tp);
-    return s;
-  }
-  __host__ __device__ long long lo(int b) const { return s_mul(b); }
-  __host__ __device__ long long hi(int b) const { return s_mul(b + 1); }
-  __host__ __device__ long long s_mul(int b) const { return b >= G ? total : total * b / G; }
-  // the CTA whose range contains chunk x
-  __host__ __device__ int owner(long long x) const { return (int)(((x + 1) * G - 1) / total); }
-  __host__ __device__ int first_cta(int pair) const { return owner((long long)pair * Tp); }
-  __host__ __device__ int last_cta(int pair) const { return owner((long long)(pair + 1) * Tp - 1); }
+// Work partition ("plan"): cost-weighted stream-K, computed on the device by the scheduler (sched.cuh) whenever the
+// number of live columns changes, and read as tables by the MTTKRP and reduce kernels.
+//
+//   * G is split into m-tiles of at most WM m8 row groups (even split of ceil(In/8) groups, so tiles differ by at most
+//     one group) and into n-tiles of at most 4 "octets" (octet = 8 n8 column groups = 64 columns, one n8 group per MMA
+//     warp), again an even split.  Inside a tile, octet j / group w (columns 64*j + 8*w ..) belongs to warp w, so every
+//     warp of a CTA has the same number nn of column groups and no per-warp predicates are needed; only the last octet
+//     of the last tile can reach beyond C, where TMA zero-fills the factor tile.
+//   * Every (m,n) pair has Tp K-chunks; a chunk of pair (mt, nt) gets the weight 2*nm(mt)*nn(nt) + PLAN_FIXED_COST
+//     (DMMAs per K8 group per warp plus the per-stage overhead in the same unit).  The flattened chunk sequence is cut
+//     into G_eff = min(G, #chunks) contiguous ranges of (nearly) equal weight, every range non-empty.
+//   * A "segment" is the part of one CTA's range that lies in one pair; segments are numbered globally in chunk order
+//     and segment s writes workspace tile s.  The segments of a pair are consecutive: the reduce kernel sums tiles
+//     pair_seg0[pair] .. pair_seg0[pair+1]-1 in that order (deterministic, no atomics).
+constexpr int N8_TILE = 32; // n8 groups per full n-tile (8 warps x WN = 4)
+constexpr int OCT_TILE = 4; // octets per full n-tile
+constexpr int PLAN_HDR = 8;
+constexpr int PLAN_FIXED_COST = 8;
+
+struct PlanView {
+  int n_tiles, m_tiles, pairs, Tp, G_eff, n_segments, NO, In8; // NO = number of 64-column octets covering C
+  const int *cta_lo;    // [G + 1]
+  const int *cta_seg0;  // [G]
+  const int *pair_seg0; // [pairs + 1]
 };
 
+__host__ __device__ inline int plan_capacity(int G, int pairs_max) { return PLAN_HDR + (G + 1) + G + (pairs_max + 1); }
+__host__ __device__ inline int plan_wm(int mt, int In8, int m_tiles) {
+  return (int)(((long long)(mt + 1) * In8) / m_tiles - ((long long)mt * In8) / m_tiles);
+}
+__host__ __device__ inline int plan_m8_start(int mt, int In8, int m_tiles) {
+  return (int)(((long long)mt * In8) / m_tiles);
+}
+__host__ __device__ inline int plan_oct_start(int nt, int NO, int n_tiles) {
+  return (int)(((long long)nt * NO) / n_tiles);
+}
+__host__ __device__ inline int plan_nn(int nt, int NO, int n_tiles) {
+  return plan_oct_start(nt + 1, NO, n_tiles) - plan_oct_start(nt, NO, n_tiles);
+}
+// tile that holds item x under the even split of `count` items over `tiles` tiles (start(t) = floor(t*count/tiles))
+__host__ __device__ inline int plan_tile_of(int x, int count, int tiles) {
+  int t = (int)(((long long)(x + 1) * tiles - 1) / count);
+  while ((int)(((long long)t * count) / tiles) > x)
+    t--;
+  while (t + 1 < tiles && (int)(((long long)(t + 1) * count) / tiles) <= x)
+    t++;
+  return t;
+}
+__host__ __device__ inline PlanView plan_view(const int *plan, int G) {
+  PlanView v;
+  v.n_tiles = plan[0];
+  v.m_tiles = plan[1];
+  v.pairs = plan[2];
+  v.Tp = plan[3];
+  v.G_eff = plan[4];
+  v.n_segments = plan[5];
+  v.NO = plan[6];
+  v.In8 = plan[7];
+  v.cta_lo = plan + PLAN_HDR;
+  v.cta_seg0 = plan + PLAN_HDR + (G + 1);
+  v.pair_seg0 = plan + PLAN_HDR + (G + 1) + G;
+  return v;
+}
+
+// Builds the plan for one mode.  O(G + pairs) integer steps, single thread.
+__host__ __device__ inline void mttkrp_make_plan(int *plan, int In, int WM, int C, int Tp, int G) {
+  const int In8 = (In + 7) / 8, NO = (C + 63) / 64;
+  const int m_tiles = (In8 + WM - 1) / WM;
+  const int n_tiles = (NO + OCT_TILE - 1) / OCT_TILE;
+  const int pairs = m_tiles * n_tiles;
+  const long long total = (long long)pairs * Tp;
+  const int G_eff = (int)(total < (long long)G ? total : (long long)G);
+  int *cta_lo = plan + PLAN_HDR, *cta_seg0 = plan + PLAN_HDR + (G + 1), *pair_seg0 = plan + PLAN_HDR + (G + 1) + G;
+  // total weight: sum over pairs of Tp * (2*nm*nn + fixed);  sum_mt nm = In8, sum_nt nn = NO
+  const long long W = (long long)Tp * (2LL * In8 * NO + (long long)PLAN_FIXED_COST * pairs);
+
+  int pi = 0, k = 0, seg = 0;
+  long long cw = 0, done = 0;
+  for (int b = 0; b < G_eff; b++) {
+    cta_lo[b] = (int)done;
+    cta_seg0[b] = seg;
+    const long long target = (b == G_eff - 1) ? W : W * (b + 1) / G_eff;
+    const long long must_leave = G_eff - b - 1;
+    long long taken = 0;
+    while (pi < pairs) {
+      const int nt = pi / m_tiles, mt = pi - nt * m_tiles;
+      const long long w = 2LL * plan_wm(mt, In8, m_tiles) * plan_nn(nt, NO, n_tiles) + PLAN_FIXED_COST;
+      const long long r = Tp - k;
+      const long long avail = total - done - must_leave;
+      long long want = (cw + r * w <= target) ? r : (target - cw) / w;
+      if (taken == 0 && want <= 0)
+        want = 1;
+      if (want > r)
+        want = r;
+      if (want > avail)
+        want = avail;
+      if (want <= 0)
+        break;
+      if (k == 0)
+        pair_seg0[pi] = seg;
+      seg++;
+      k += (int)want;
+      cw += want * w;
+      done += want;
+      taken += want;
+      if (k == Tp) {
+        pi++;
+        k = 0;
+      } else
+        break;
+    }
+  }
+  for (int b = G_eff; b <= G; b++)
+    cta_lo[b] = (int)total;
+  for (int b = G_eff; b < G; b++)
+    cta_seg0[b] = seg;
+  pair_seg0[pairs] = seg;
+  plan[0] = n_tiles;
+  plan[1] = m_tiles;
+  plan[2] = pairs;
+  plan[3] = Tp;
+  plan[4] = G_eff;
+  plan[5] = seg;
+  plan[6] = NO;
+  plan[7] = In8;
+}
+
+// One thread per mode builds its plan (test hook path; the run loop plans inside sched_kernel).
+struct PlanArgs {
+  int n_modes;
+  int In[CALS_MAX_MODES], WM[CALS_MAX_MODES], Tp[CALS_MAX_MODES];
+  int *plan[CALS_MAX_MODES];
+  int G;
+};
+__global__ void mttkrp_plan_kernel(const PlanArgs a, int C) {
+  const int n = threadIdx.x;
+  if (n < a.n_modes && a.plan[n])
+    mttkrp_make_plan(a.plan[n], a.In[n], a.WM[n], C, a.Tp[n], a.G);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
-// The DMMA kernel.  288 threads: warps 0..7 consume (LDS + DMMA), warp 8 lane 0 produces (TMA).
+// One K8 group of one stage for one warp: NM valid m8 row groups x NN n8 column groups (both CTA-uniform, compile time).
+template <int WM, int WN, int NM, int NN>
+__device__ __forceinline__ void mma_group(double (&acc)[WM][WN][2], const double *__restrict__ Xt,
+                                          const double *__restrict__ Bw, const double (&wv)[WN], int gk, int r, int s) {
+  double2 b[NN];
+#pragma unroll
+  for (int j = 0; j < NN; j++) {
+    b[j] = *reinterpret_cast<const double2 *>(Bw + (j * 64 + r) * KT + gk * 8 + 2 * s);
+    b[j].x *= wv[j];
+    b[j].y *= wv[j];
+  }
+  // Row group by row group: k = 8*gk + 2s first, then k = 8*gk + 2s + 1; only one A fragment is live at a time.
+#pragma unroll
+  for (int i = 0; i < NM; i++) {
+    const double2 a = *reinterpret_cast<const double2 *>(Xt + (i * 8 + r) * KT + gk * 8 + 2 * s);
+#pragma unroll
+    for (int j = 0; j < NN; j++)
+      dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a.x, b[j].x);
+#pragma unroll
+    for (int j = 0; j < NN; j++)
+      dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a.y, b[j].y);
+  }
+}
+
+// All K8 groups of one stage for a compile-time (NM, NN).
+template <int WM, int WN, int NM, int NN>
+__device__ __forceinline__ void mma_stage_nm(double (&acc)[WM][WN][2], const double *Xt, const double *Bw,
+                                             const double (&wv)[WN], int ngroups, int r, int s) {
+  if (NM == WM && NN == WN && ngroups == KT / 8) { // the common case: fully unrolled
+#pragma unroll
+    for (int gk = 0; gk < KT / 8; gk++)
+      mma_group<WM, WN, NM, NN>(acc, Xt, Bw, wv, gk, r, s);
+  } else {
+#pragma unroll 1
+    for (int gk = 0; gk < ngroups; gk++) // K tail: rows of the K tile beyond Ip are zero-filled by TMA, skip them
+      mma_group<WM, WN, NM, NN>(acc, Xt, Bw, wv, gk, r, s);
+  }
+}
+
+template <int WM, int WN, int NM>
+__device__ __forceinline__ void mma_stage_n(double (&acc)[WM][WN][2], const double *Xt, const double *Bw,
+                                            const double (&wv)[WN], int ngroups, int r, int s, int nn) {
+  static_assert(WN == 4, "dispatch below assumes 4 column groups per warp");
+  switch (nn) {
+  case 1:
+    mma_stage_nm<WM, WN, NM, 1>(acc, Xt, Bw, wv, ngroups, r, s);
+    break;
+  case 2:
+    mma_stage_nm<WM, WN, NM, 2>(acc, Xt, Bw, wv, ngroups, r, s);
+    break;
+  case 3:
+    mma_stage_nm<WM, WN, NM, 3>(acc, Xt, Bw, wv, ngroups, r, s);
+    break;
+  default:
+    mma_stage_nm<WM, WN, NM, 4>(acc, Xt, Bw, wv, ngroups, r, s);
+    break;
+  }
+}
+
+template <int WM, int WN>
+__device__ __forceinline__ void mma_stage(double (&acc)[WM][WN][2], const double *Xt, const double *Bw,
+                                          const double (&wv)[WN], int ngroups, int r, int s, int nm, int nn) {
+  static_assert(WM >= 1 && WM <= 8, "extend the dispatch below");
+#define CALS_MMA_CASE(NMV)                                                                                             \
+  case NMV:                                                                                                            \
+    if (WM >= NMV)                                                                                                     \
+      mma_stage_n<WM, WN, (WM >= NMV ? NMV : 1)>(acc, Xt, Bw, wv, ngroups, r, s, nn);                                  \
+    break;
+  switch (nm) {
+    CALS_MMA_CASE(1)
+    CALS_MMA_CASE(2)
+    CALS_MMA_CASE(3)
+    CALS_MMA_CASE(4)
+    CALS_MMA_CASE(5)
+    CALS_MMA_CASE(6)
+    CALS_MMA_CASE(7)
+    CALS_MMA_CASE(8)
+  default:
+    break;
+  }
+#undef CALS_MMA_CASE
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The DMMA kernel.  384 threads: warps 0..7 consume (LDS + DMMA) with 232 registers each, warp 8 lane 0 produces (TMA);
+// warps 9..11 only exist so that the producer warpgroup can release its registers (setmaxnreg) and exit at once.
 template <int WM, int WN>
 __global__ void __launch_bounds__(MTTKRP_THREADS, 1)
 mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, const SchedState *__restrict__ st,
-                   const FactorPtrs fac, double *__restrict__ ws, int C_override) {
+                   const FactorPtrs fac, const int *__restrict__ plan, double *__restrict__ ws, int C_override) {
   using Cfg = TileCfg<WM, WN>;
   constexpr int M_TILE = Cfg::M_TILE, N_TILE = Cfg::N_TILE;
+  static_assert(WN * NUM_MMA_WARPS == N8_TILE, "n-tile must hold N8_TILE n8 groups");
 
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte aligned dynamic shared memory (TMA destinations need 128 B); indexing the array directly keeps the
+  // pointers in the shared address space (LDS instead of generic LD)
+  extern __shared__ __align__(1024) unsigned char smem[];
   double *Bs = (double *)smem;                                            // [N_TILE][KT]
   double *Xs = (double *)(smem + Cfg::B_BYTES);                           // [X_STAGES][M_TILE][KT]
   double *Ws = (double *)(smem + Cfg::B_BYTES + X_STAGES * Cfg::X_STAGE_BYTES); // [2][N_TILE][OC]
@@ -159,12 +359,11 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
   const int cur = C_override > 0 ? 0 : st->cur;
   if (C <= 0)
     return;
-  const int n_tiles = (C + N_TILE - 1) / N_TILE;
-  const int Tp = g.P_tiles * g.S * g.QC;
-  const StreamK sk = StreamK::make(g.m_tiles * n_tiles, Tp, gridDim.x);
-  const long long lo = sk.lo(blockIdx.x), hi = sk.hi(blockIdx.x);
+  const PlanView pv = plan_view(plan, gridDim.x);
+  const int lo = pv.cta_lo[blockIdx.x], hi = pv.cta_lo[blockIdx.x + 1];
   if (lo >= hi)
     return;
+  const int Tp = pv.Tp, m_tiles = pv.m_tiles, n_tiles = pv.n_tiles;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef CALS_B200_POISON_SMEM
@@ -194,19 +393,20 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
 
   const int Iq = g.outer_dim[0];
 
-  if (warp == NUM_MMA_WARPS) {
+  if (warp >= NUM_MMA_WARPS) {
     // ===================================== producer =====================================
-    if (lane != 0)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp != NUM_MMA_WARPS || lane != 0)
       return;
     const CUtensorMap *tmB = &maps.B[cur], *tmW = &maps.W[cur];
     int xs = 0, wsi = 0;
     uint32_t xph = 1, wph = 1; // ring "empty" barriers: the first pass over the ring does not block
     uint32_t bph = 0;          // empty_b: k-th reload waits for the k-th release by the consumers
     int prev_key = -1;
-    for (long long ch = lo; ch < hi; ch++) {
-      const int pair = (int)(ch / Tp);
-      int lc = (int)(ch - (long long)pair * Tp);
-      const int nt = pair / g.m_tiles, mt = pair - nt * g.m_tiles;
+    for (int ch = lo; ch < hi; ch++) {
+      const int pair = ch / Tp;
+      int lc = ch - pair * Tp;
+      const int nt = pair / m_tiles, mt = pair - nt * m_tiles;
       const int qc = lc % g.QC;
       lc /= g.QC;
       const int sl = lc % g.S, pt = lc / g.S;
@@ -217,13 +417,13 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
           bph ^= 1;
         }
         mbar_expect_tx(full_b, Cfg::B_BYTES);
-        tma_load_2d(Bs, tmB, full_b, pt * KT, nt * N_TILE);
+        tma_load_2d(Bs, tmB, full_b, pt * KT, 64 * plan_oct_start(nt, pv.NO, n_tiles));
         prev_key = key;
       }
       // w chunk
       mbar_wait(&empty_w[wsi], wph);
       mbar_expect_tx(&full_w[wsi], Cfg::W_BYTES);
-      tma_load_2d(Ws + wsi * (N_TILE * OC), tmW, &full_w[wsi], qc * OC, nt * N_TILE);
+      tma_load_2d(Ws + wsi * (N_TILE * OC), tmW, &full_w[wsi], qc * OC, 64 * plan_oct_start(nt, pv.NO, n_tiles));
       if (++wsi == 2) {
         wsi = 0;
         wph ^= 1;
@@ -239,13 +439,14 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
           ubase += ik * g.outer_umul[k];
         }
       }
+      const int m0 = 8 * plan_m8_start(mt, pv.In8, m_tiles);
       const int nvalid = min(OC, Iq - qc * OC);
       for (int o = 0; o < nvalid; o++) {
         const int iq = qc * OC + o;
         mbar_wait(&empty_x[xs], xph);
         mbar_expect_tx(&full_x[xs], Cfg::X_STAGE_BYTES);
-        tma_load_4d(Xs + xs * (M_TILE * KT), &maps.X, &full_x[xs], pt * KT, lbase + iq * g.outer_lmul[0],
-                    mt * M_TILE, ubase + iq * g.outer_umul[0]);
+        tma_load_4d(Xs + xs * (M_TILE * KT), &maps.X, &full_x[xs], pt * KT, lbase + iq * g.outer_lmul[0], m0,
+                    ubase + iq * g.outer_umul[0]);
         if (++xs == X_STAGES) {
           xs = 0;
           xph ^= 1;
@@ -256,8 +457,10 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
   }
 
   // ===================================== consumers =====================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
   const int r = lane >> 2, s = lane & 3;
-  const int wn0 = warp * (8 * WN);
+  // n8 group j*8 + warp of the n-tile belongs to this warp: column offset (j*8 + warp)*8 inside the tile
+  const double *Bw = Bs + warp * 8 * KT;
   double acc[WM][WN][2];
 #pragma unroll
   for (int i = 0; i < WM; i++)
@@ -272,33 +475,34 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
   int xs = 0, wsi = 0;
   uint32_t xph = 0, wph = 0, bph = 0;
   int prev_key = -1, prev_pair = -1, prev_sl = -1, prev_nt = -1;
+  int seg = pv.cta_seg0[blockIdx.x] - 1;
 
-  auto flush = [&](int pair) {
-    const int slot = pair * sk.kmax + ((int)blockIdx.x - sk.first_cta(pair));
-    double *tile = ws + (size_t)slot * (M_TILE * N_TILE);
+  auto flush = [&]() {
+    double *tile = ws + (size_t)seg * (M_TILE * N_TILE);
 #pragma unroll
     for (int i = 0; i < WM; i++)
 #pragma unroll
       for (int j = 0; j < WN; j++) {
         double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
-        *reinterpret_cast<double2 *>(tile + (i * 8 + r) * N_TILE + wn0 + j * 8 + 2 * s) = v;
+        *reinterpret_cast<double2 *>(tile + (i * 8 + r) * N_TILE + (j * 8 + warp) * 8 + 2 * s) = v;
         acc[i][j][0] = acc[i][j][1] = 0.0;
       }
   };
 
-  for (long long ch = lo; ch < hi; ch++) {
-    const int pair = (int)(ch / Tp);
-    int lc = (int)(ch - (long long)pair * Tp);
-    const int nt = pair / g.m_tiles, mt = pair - nt * g.m_tiles;
+  for (int ch = lo; ch < hi; ch++) {
+    const int pair = ch / Tp;
+    int lc = ch - pair * Tp;
+    const int nt = pair / m_tiles, mt = pair - nt * m_tiles;
     const int qc = lc % g.QC;
     lc /= g.QC;
     const int sl = lc % g.S, pt = lc / g.S;
-    // m8 / n8 sub-tiles that lie completely outside G are skipped (CTA-uniform resp. warp-uniform predicates)
-    const int wm_valid = min(WM, (g.In - mt * M_TILE + 7) >> 3);
-    const int wn_valid = max(0, min(WN, (C - nt * N_TILE - wn0 + 7) >> 3));
+    // number of valid m8 row groups / n8 column groups of this pair (CTA-uniform)
+    const int nm = plan_wm(mt, pv.In8, m_tiles);
+    const int nn = plan_nn(nt, pv.NO, n_tiles);
     if (pair != prev_pair) {
       if (prev_pair >= 0)
-        flush(prev_pair);
+        flush();
+      seg++;
       prev_pair = pair;
     }
     const int key = pt * n_tiles + nt;
@@ -322,7 +526,7 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
       }
 #pragma unroll
       for (int j = 0; j < WN; j++) {
-        const int c = nt * N_TILE + wn0 + j * 8 + r;
+        const int c = 64 * plan_oct_start(nt, pv.NO, n_tiles) + (j * 8 + warp) * 8 + r;
         double w = 1.0;
         if (c < C)
           for (int k = 1; k < g.n_outer; k++) {
@@ -336,7 +540,7 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
     prev_nt = nt;
 
     mbar_wait(&full_w[wsi], wph);
-    const double *Wc = Ws + wsi * (N_TILE * OC);
+    const double *Wc = Ws + wsi * (N_TILE * OC) + warp * 8 * OC;
     const int nvalid = min(OC, Iq - qc * OC);
     const int kvalid = min(KT, g.Ip - pt * KT);
     const int ngroups = (kvalid + 7) >> 3;
@@ -344,40 +548,9 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
       double wv[WN];
 #pragma unroll
       for (int j = 0; j < WN; j++)
-        wv[j] = Wc[(wn0 + j * 8 + r) * OC + o] * wslow[j];
+        wv[j] = Wc[(j * 64 + r) * OC + o] * wslow[j];
       mbar_wait(&full_x[xs], xph);
-      const double *Xt = Xs + xs * (M_TILE * KT);
-#pragma unroll
-      for (int gk = 0; gk < KT / 8; gk++) {
-        if (gk < ngroups) { // warp-uniform: rows of the K tile beyond Ip are zero-filled by TMA, skip them
-          double2 a[WM], b[WN];
-#pragma unroll
-          for (int i = 0; i < WM; i++)
-            a[i] = *reinterpret_cast<const double2 *>(Xt + (i * 8 + r) * KT + gk * 8 + 2 * s);
-#pragma unroll
-          for (int j = 0; j < WN; j++) {
-            b[j] = *reinterpret_cast<const double2 *>(Bs + (wn0 + j * 8 + r) * KT + gk * 8 + 2 * s);
-            b[j].x *= wv[j];
-            b[j].y *= wv[j];
-          }
-          // k = 8*gk + 2s in the first pass, 8*gk + 2s + 1 in the second: the two updates of one accumulator are
-          // WM*WN instructions apart (DMMA latency is ~26 cycles)
-#pragma unroll
-          for (int i = 0; i < WM; i++)
-            if (i < wm_valid)
-#pragma unroll
-              for (int j = 0; j < WN; j++)
-                if (j < wn_valid)
-                  dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
-#pragma unroll
-          for (int i = 0; i < WM; i++)
-            if (i < wm_valid)
-#pragma unroll
-              for (int j = 0; j < WN; j++)
-                if (j < wn_valid)
-                  dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
-        }
-      }
+      mma_stage<WM, WN>(acc, Xs + xs * (M_TILE * KT), Bw, wv, ngroups, r, s, nm, nn);
       __syncwarp();
       if (lane == 0)
         mbar_arrive(&empty_x[xs]);
@@ -394,35 +567,35 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
       wph ^= 1;
     }
   }
-  flush(prev_pair);
+  flush();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Sum the stream-K partial tiles of every (m,n) pair in CTA order and write G (In x C, column-major, ld = ldG).
+// Sum the partial tiles of every (m,n) pair in segment order and write G (In x C, column-major, ld = ldG).
 // One CTA per 32x32 patch of G; reads are coalesced along columns of the row-major tiles, writes along rows of G.
 template <int M_TILE, int N_TILE>
 __global__ void mttkrp_reduce_kernel(const MttkrpGeom g, const SchedState *__restrict__ st,
-                                     const double *__restrict__ ws, double *__restrict__ G, int grid_ctas,
-                                     int C_override) {
+                                     const int *__restrict__ plan, const double *__restrict__ ws,
+                                     double *__restrict__ G, int grid_ctas, int C_override) {
   const int C = C_override > 0 ? C_override : st->C;
   const int c0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
   if (c0 >= C)
     return;
   __shared__ double t[32][33];
-  const int n_tiles = (C + N_TILE - 1) / N_TILE;
-  const int Tp = g.P_tiles * g.S * g.QC;
-  const StreamK sk = StreamK::make(g.m_tiles * n_tiles, Tp, grid_ctas);
+  const PlanView pv = plan_view(plan, grid_ctas);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 256 threads: ty in 0..7
   for (int rr = ty; rr < 32; rr += 8) {
     const int m = m0 + rr, c = c0 + tx;
     double sum = 0.0;
     if (m < g.In && c < C) {
-      const int mt = m / M_TILE, nt = c / N_TILE;
-      const int pair = nt * g.m_tiles + mt;
-      const int nslots = sk.last_cta(pair) - sk.first_cta(pair) + 1;
-      const double *p = ws + (size_t)pair * sk.kmax * (M_TILE * N_TILE) + (m - mt * M_TILE) * N_TILE + (c - nt * N_TILE);
-      for (int k = 0; k < nslots; k++)
-        sum += p[(size_t)k * (M_TILE * N_TILE)];
+      const int mt = plan_tile_of(m >> 3, pv.In8, pv.m_tiles);
+      const int nt = plan_tile_of(c >> 6, pv.NO, pv.n_tiles);
+      const int pair = nt * pv.m_tiles + mt;
+      const int s0 = pv.pair_seg0[pair], s1 = pv.pair_seg0[pair + 1];
+      const double *p = ws + (size_t)s0 * (M_TILE * N_TILE) + (m - 8 * plan_m8_start(mt, pv.In8, pv.m_tiles)) * N_TILE +
+                        (c - 64 * plan_oct_start(nt, pv.NO, pv.n_tiles));
+      for (int k = s0; k < s1; k++, p += (size_t)(M_TILE * N_TILE))
+        sum += *p;
     }
     t[rr][tx] = sum;
   }

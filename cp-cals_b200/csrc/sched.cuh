@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include "common.cuh"
+#include "mttkrp.cuh"
 
 namespace calsb200 {
 
@@ -23,12 +24,27 @@ struct SchedParams {
   int *gather_src; // [buffer_cols] new column j <- (>=0: old buffer column, <0: home column -1-src)
   int *evict_dst;  // [buffer_cols] old column j -> home column, or -1
   int *host_flags; // mapped pinned host memory: [0] done, [1] global_iter (low 31 bits), [2] n_live
+  PlanArgs plans;  // MTTKRP work partition per mode, rebuilt whenever the live column count changes
 };
 
-// Single thread; the live list is short (<= buffer_cols entries) and this runs once per CALS iteration.
+// Thread 0 does the queue bookkeeping (the live list is short, <= buffer_cols entries, and this runs once per CALS
+// iteration); then one thread per mode rebuilds that mode's MTTKRP plan if the column count changed.
+__device__ void sched_serial(const SchedParams &p);
+
 __global__ void sched_kernel(const SchedParams p) {
-  if (threadIdx.x != 0 || blockIdx.x != 0)
-    return;
+  __shared__ int replan;
+  if (threadIdx.x == 0) {
+    const int C_before = p.st->C;
+    sched_serial(p);
+    replan = (p.st->C != C_before && p.st->C > 0) ? 1 : 0;
+  }
+  __syncthreads();
+  if (replan && (int)threadIdx.x < p.plans.n_modes)
+    mttkrp_make_plan(p.plans.plan[threadIdx.x], p.plans.In[threadIdx.x], p.plans.WM[threadIdx.x], p.st->C,
+                     p.plans.Tp[threadIdx.x], p.plans.G);
+}
+
+__device__ void sched_serial(const SchedParams &p) {
   SchedState *st = p.st;
   if (st->done) {
     st->changed = 0;
@@ -107,6 +123,7 @@ __global__ void sched_kernel(const SchedParams p) {
     st->done = 1;
   } else {
     st->global_iter += 1; // reference: rep.iter counts executed loop bodies (src/cals.cpp:175-176)
+    st->col_iter_sum += (unsigned long long)col;
   }
   p.host_flags[1] = (int)(st->global_iter & 0x7fffffff);
   p.host_flags[2] = n_live;
