@@ -96,9 +96,16 @@ struct cals_b200_ctx {
   std::vector<void *> run_allocs;
   int run_cols = 0, run_total_cols = 0, run_models = 0;
 
-  // host mirrors of results
-  std::vector<double> h_home[CALS_MAX_MODES];
-  std::vector<double> h_lambda;
+  // host mirrors of results: pinned staging buffers, reused from run to run
+  double *h_home[CALS_MAX_MODES] = {};
+  size_t h_home_cap[CALS_MAX_MODES] = {};
+  double *h_lambda = nullptr;
+  size_t h_lambda_cap = 0;
+  ModelDesc *h_desc_pin = nullptr;
+  size_t h_desc_cap = 0;
+  std::vector<int> run_sig; // (dims, buffer_cols, ranks): allocations are reused while this does not change
+  double *norm_partial = nullptr;
+  size_t norm_partial_cap = 0;
 
   std::vector<cudaEvent_t> ev_pool;
   bool dmma_attr_done[16] = {};
@@ -132,6 +139,20 @@ template <typename T> int dev_alloc(cals_b200_ctx *c, T **p, size_t n, std::vect
   CU_TRY(c, cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
   track.push_back(q);
   *p = (T *)q;
+  return 0;
+}
+
+template <typename T> int pinned_reserve(cals_b200_ctx *c, T **p, size_t *cap, size_t n) {
+  if (*p && *cap >= n)
+    return 0;
+  if (*p)
+    cudaFreeHost(*p);
+  *p = nullptr;
+  *cap = 0;
+  void *q = nullptr;
+  CU_TRY(c, cudaHostAlloc(&q, std::max<size_t>(n, 1) * sizeof(T), cudaHostAllocDefault));
+  *p = (T *)q;
+  *cap = n;
   return 0;
 }
 
@@ -385,6 +406,7 @@ void release_run(cals_b200_ctx *c) {
   c->d_live = c->d_live_tmp = c->d_gather = c->d_evict = nullptr;
   c->d_gram = c->d_lambda = nullptr;
   c->uploaded = false;
+  c->run_sig.clear();
 }
 
 void release_tensor(cals_b200_ctx *c) {
@@ -402,11 +424,17 @@ void release_tensor(cals_b200_ctx *c) {
 int install_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const double *src, bool src_on_device) {
   if (n_modes < 3 || n_modes > CALS_MAX_MODES)
     return fail(c, "n_modes must be in [3, %d], got %d", CALS_MAX_MODES, n_modes);
-  release_tensor(c);
-  long long nX = 1;
-  for (int n = 0; n < n_modes; n++) {
+  for (int n = 0; n < n_modes; n++)
     if (modes[n] < 1 || modes[n] > (1u << 30))
       return fail(c, "mode %d has unsupported extent %llu", n, (unsigned long long)modes[n]);
+  // same shape as the resident tensor: keep every allocation (and the TMA descriptors that point into them)
+  bool same = c->have_tensor && c->geo.n_modes == n_modes;
+  for (int n = 0; same && n < n_modes; n++)
+    same = c->geo.dims[n] == (int)modes[n];
+  if (!same)
+    release_tensor(c);
+  long long nX = 1;
+  for (int n = 0; n < n_modes; n++) {
     c->geo.dims[n] = (int)modes[n];
     c->geo.ldF[n] = round_up_int((int)modes[n], 2);
     nX *= (long long)modes[n];
@@ -417,6 +445,7 @@ int install_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const d
   c->ldX0 = round_up_int(I0, 2);
   c->ldX1 = round_up_int(I1, 2);
   const long long rest0 = nX / I0, rest2 = nX / ((long long)I0 * I1);
+  c->have_tensor = false;
 
   double *dense = nullptr;
   bool dense_owned = false;
@@ -429,7 +458,8 @@ int install_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const d
     dense_owned = true;
     CU_TRY(c, cudaMemcpyAsync(dense, src, (size_t)nX * 8, cudaMemcpyHostToDevice, c->stream));
   }
-  CU_TRY(c, cudaMalloc((void **)&c->Xp, (size_t)c->ldX0 * rest0 * 8));
+  if (!c->Xp)
+    CU_TRY(c, cudaMalloc((void **)&c->Xp, (size_t)c->ldX0 * rest0 * 8));
   if (!src_on_device && c->ldX0 == I0) {
     CU_TRY(c, cudaMemcpyAsync(c->Xp, src, (size_t)nX * 8, cudaMemcpyHostToDevice, c->stream));
     dense = c->Xp;
@@ -438,23 +468,29 @@ int install_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const d
   } else {
     pad_copy_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(dense, c->Xp, I0, c->ldX0, rest0);
   }
-  CU_TRY(c, cudaMalloc((void **)&c->Xt, (size_t)c->ldX1 * I0 * rest2 * 8));
+  if (!c->Xt)
+    CU_TRY(c, cudaMalloc((void **)&c->Xt, (size_t)c->ldX1 * I0 * rest2 * 8));
   {
     dim3 grid((I0 + 31) / 32, (I1 + 31) / 32, (unsigned)std::min<long long>(rest2, 65535));
     swap01_copy_kernel<<<grid, 256, 0, c->stream>>>(dense, c->Xt, I0, I1, c->ldX1, rest2);
   }
   // norms: one pass over Xp
-  CU_TRY(c, cudaMalloc((void **)&c->jk_norms, (size_t)(I0 + 1) * 8));
+  if (!c->jk_norms)
+    CU_TRY(c, cudaMalloc((void **)&c->jk_norms, (size_t)(I0 + 1) * 8));
   c->d_norm = c->jk_norms + I0;
   {
     const int ctas = (int)std::min<long long>(std::max<long long>(rest0 / 4, 1), (long long)c->sm_count * 4);
-    double *partial = nullptr;
-    CU_TRY(c, cudaMalloc((void **)&partial, (size_t)ctas * I0 * 8));
-    rowsumsq_partial_kernel<<<ctas, 256, 256 * 8, c->stream>>>(c->Xp, I0, c->ldX0, rest0, partial);
-    rowsumsq_final_kernel<<<1, 256, 0, c->stream>>>(partial, ctas, I0, c->jk_norms, c->d_norm);
+    if (c->norm_partial_cap < (size_t)ctas * I0) {
+      if (c->norm_partial)
+        cudaFree(c->norm_partial);
+      c->norm_partial = nullptr;
+      CU_TRY(c, cudaMalloc((void **)&c->norm_partial, (size_t)ctas * I0 * 8));
+      c->norm_partial_cap = (size_t)ctas * I0;
+    }
+    rowsumsq_partial_kernel<<<ctas, 256, 256 * 8, c->stream>>>(c->Xp, I0, c->ldX0, rest0, c->norm_partial);
+    rowsumsq_final_kernel<<<1, 256, 0, c->stream>>>(c->norm_partial, ctas, I0, c->jk_norms, c->d_norm);
     CU_TRY(c, cudaMemcpyAsync(&c->x_norm, c->d_norm, 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    cudaFree(partial);
   }
   if (dense_owned)
     cudaFree(dense);
@@ -471,7 +507,19 @@ int prepare_run(cals_b200_ctx *c) {
     return fail(c, "model queue is empty");
   const Geom &geo = c->geo;
   const int N = geo.n_modes, M = (int)c->hmodels.size();
-  release_run(c);
+
+  // allocation signature: everything below is sized by (dims, buffer_cols, rank sequence)
+  std::vector<int> sig;
+  sig.reserve((size_t)M + N + 2);
+  sig.push_back(N);
+  for (int n = 0; n < N; n++)
+    sig.push_back(geo.dims[n]);
+  sig.push_back(c->buffer_cols);
+  for (int m = 0; m < M; m++)
+    sig.push_back(c->hmodels[m].rank);
+  const bool reuse = !c->run_sig.empty() && sig == c->run_sig && c->d_models && c->bufs.cols == c->buffer_cols;
+  if (!reuse)
+    release_run(c);
 
   c->hdesc.assign(M, ModelDesc{});
   int col = 0, max_rank = 0;
@@ -495,40 +543,51 @@ int prepare_run(cals_b200_ctx *c) {
   c->max_rank = max_rank;
   c->gram_doubles = goff;
 
-  if (alloc_buffers(c, c->bufs, c->buffer_cols, true, c->total_cols))
-    return 1;
-  if (dev_alloc(c, &c->d_models, (size_t)M, c->run_allocs) || dev_alloc(c, &c->d_live, (size_t)M, c->run_allocs) ||
-      dev_alloc(c, &c->d_live_tmp, (size_t)M, c->run_allocs) ||
-      dev_alloc(c, &c->d_gather, (size_t)c->buffer_cols, c->run_allocs) ||
-      dev_alloc(c, &c->d_evict, (size_t)c->buffer_cols, c->run_allocs) ||
-      dev_alloc(c, &c->d_gram, (size_t)goff, c->run_allocs) ||
-      dev_alloc(c, &c->d_lambda, (size_t)c->total_cols, c->run_allocs))
-    return 1;
+  if (!reuse) {
+    if (alloc_buffers(c, c->bufs, c->buffer_cols, true, c->total_cols))
+      return 1;
+    if (dev_alloc(c, &c->d_models, (size_t)M, c->run_allocs) || dev_alloc(c, &c->d_live, (size_t)M, c->run_allocs) ||
+        dev_alloc(c, &c->d_live_tmp, (size_t)M, c->run_allocs) ||
+        dev_alloc(c, &c->d_gather, (size_t)c->buffer_cols, c->run_allocs) ||
+        dev_alloc(c, &c->d_evict, (size_t)c->buffer_cols, c->run_allocs) ||
+        dev_alloc(c, &c->d_gram, (size_t)goff, c->run_allocs) ||
+        dev_alloc(c, &c->d_lambda, (size_t)c->total_cols, c->run_allocs))
+      return 1;
+    for (int n = 0; n < N; n++)
+      if (dev_alloc(c, &c->home0[n], (size_t)geo.ldF[n] * c->total_cols, c->run_allocs))
+        return 1;
+  }
   if (ensure_dummy_state(c))
     return 1;
 
-  // pack and upload the home matrices (pitch ldF)
+  // pack the home matrices (pitch ldF) into pinned staging and upload
   for (int n = 0; n < N; n++) {
     const int rows = geo.dims[n], ld = geo.ldF[n];
-    std::vector<double> &h = c->h_home[n];
-    h.assign((size_t)ld * c->total_cols, 0.0);
+    const size_t count = (size_t)ld * c->total_cols;
+    if (pinned_reserve(c, &c->h_home[n], &c->h_home_cap[n], count))
+      return 1;
+    double *h = c->h_home[n];
     for (int m = 0; m < M; m++) {
       const HostModel &hm = c->hmodels[m];
       size_t off = 0;
       for (int k = 0; k < n; k++)
         off += (size_t)geo.dims[k] * hm.rank;
-      for (int j = 0; j < hm.rank; j++)
-        memcpy(&h[(size_t)(c->hdesc[m].home_col + j) * ld], &hm.factors[off + (size_t)j * rows], (size_t)rows * 8);
+      for (int j = 0; j < hm.rank; j++) {
+        double *dst = &h[(size_t)(c->hdesc[m].home_col + j) * ld];
+        memcpy(dst, &hm.factors[off + (size_t)j * rows], (size_t)rows * 8);
+        if (ld > rows)
+          dst[rows] = 0.0;
+      }
     }
-    CU_TRY(c, cudaMemcpyAsync(c->bufs.fac.home[n], h.data(), h.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    if (dev_alloc(c, &c->home0[n], h.size(), c->run_allocs))
-      return 1;
-    CU_TRY(c, cudaMemcpyAsync(c->home0[n], c->bufs.fac.home[n], h.size() * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->bufs.fac.home[n], h, count * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->home0[n], c->bufs.fac.home[n], count * 8, cudaMemcpyDeviceToDevice, c->stream));
   }
-  c->h_lambda.assign((size_t)c->total_cols, 0.0);
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  if (pinned_reserve(c, &c->h_lambda, &c->h_lambda_cap, (size_t)c->total_cols) ||
+      pinned_reserve(c, &c->h_desc_pin, &c->h_desc_cap, (size_t)M))
+    return 1;
   c->uploaded = true;
   c->run_cols = c->buffer_cols;
+  c->run_sig = sig;
   return 0;
 }
 
@@ -559,7 +618,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     d.chol_info = 0;
     d.error = d.fit = d.old_fit = 0.0;
   }
-  CU_TRY(c, cudaMemcpyAsync(c->d_models, c->hdesc.data(), (size_t)M * sizeof(ModelDesc), cudaMemcpyHostToDevice, s));
+  memcpy(c->h_desc_pin, c->hdesc.data(), (size_t)M * sizeof(ModelDesc));
+  CU_TRY(c, cudaMemcpyAsync(c->d_models, c->h_desc_pin, (size_t)M * sizeof(ModelDesc), cudaMemcpyHostToDevice, s));
   SchedState st{};
   st.n_models = M;
   st.flags = (int)c->flags;
@@ -713,13 +773,13 @@ int download_results(cals_b200_ctx *c) {
     return fail(c, "no run to fetch results from");
   const Geom &geo = c->geo;
   for (int n = 0; n < geo.n_modes; n++)
-    CU_TRY(c, cudaMemcpyAsync(c->h_home[n].data(), c->bufs.fac.home[n], c->h_home[n].size() * 8,
+    CU_TRY(c, cudaMemcpyAsync(c->h_home[n], c->bufs.fac.home[n], (size_t)geo.ldF[n] * c->total_cols * 8,
                               cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaMemcpyAsync(c->h_lambda.data(), c->d_lambda, c->h_lambda.size() * 8, cudaMemcpyDeviceToHost,
-                            c->stream));
-  CU_TRY(c, cudaMemcpyAsync(c->hdesc.data(), c->d_models, c->hdesc.size() * sizeof(ModelDesc), cudaMemcpyDeviceToHost,
+  CU_TRY(c, cudaMemcpyAsync(c->h_lambda, c->d_lambda, (size_t)c->total_cols * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->h_desc_pin, c->d_models, c->hdesc.size() * sizeof(ModelDesc), cudaMemcpyDeviceToHost,
                             c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
+  memcpy(c->hdesc.data(), c->h_desc_pin, c->hdesc.size() * sizeof(ModelDesc));
   c->results_fresh = true;
   return 0;
 }
@@ -811,6 +871,15 @@ int cals_b200_destroy(cals_b200_ctx *c) {
     cudaFree(c->d_st);
   if (c->h_flags)
     cudaFreeHost(c->h_flags);
+  for (auto &p : c->h_home)
+    if (p)
+      cudaFreeHost(p);
+  if (c->h_lambda)
+    cudaFreeHost(c->h_lambda);
+  if (c->h_desc_pin)
+    cudaFreeHost(c->h_desc_pin);
+  if (c->norm_partial)
+    cudaFree(c->norm_partial);
   for (auto e : c->ev_pool)
     cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
