@@ -31,7 +31,8 @@ ABI_SYMBOLS = [
     "cals_b200_set_tensor_dev", "cals_b200_configure", "cals_b200_set_timing", "cals_b200_set_mttkrp_variant",
     "cals_b200_clear_models", "cals_b200_enqueue_model", "cals_b200_run", "cals_b200_rerun",
     "cals_b200_fetch_model", "cals_b200_fetch_all", "cals_b200_tensor_norm", "cals_b200_jk_norms",
-    "cals_b200_mttkrp", "cals_b200_device_info", "cals_b200_version",
+    "cals_b200_mttkrp", "cals_b200_device_info", "cals_b200_version", "cals_b200_fetch_iteration_cols",
+    "cals_b200_host_alloc", "cals_b200_host_free",
 ]
 
 
@@ -88,6 +89,10 @@ def lib():
     L.cals_b200_mttkrp.argtypes = [vp, i, u64, C.POINTER(vp), vp, i, i, C.POINTER(dbl)]
     L.cals_b200_device_info.argtypes = [vp, C.POINTER(i), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.cals_b200_version.restype = C.c_char_p
+    L.cals_b200_fetch_iteration_cols.argtypes = [vp, C.POINTER(C.c_uint32), u64, C.POINTER(u64)]
+    L.cals_b200_host_alloc.argtypes = [C.c_size_t]
+    L.cals_b200_host_alloc.restype = vp
+    L.cals_b200_host_free.argtypes = [vp]
     _lib = L
     return L
 
@@ -304,6 +309,16 @@ class Engine:
         ms = C.c_double()
         self._ck(self._L.cals_b200_mttkrp(self._ctx, mode, cols, ptrs, G.ctypes.data, variant, repeats, C.byref(ms)))
         return G, ms.value
+
+    def iteration_cols(self) -> np.ndarray:
+        """CalsReport::cols of the last run: active multi-factor columns per global iteration."""
+        n = C.c_uint64()
+        self._ck(self._L.cals_b200_fetch_iteration_cols(self._ctx, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint32)
+        if n.value:
+            self._ck(self._L.cals_b200_fetch_iteration_cols(self._ctx, out.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                            n.value, C.byref(n)))
+        return out
 
     def device_info(self):
         sm, fr, tot = C.c_int(), C.c_size_t(), C.c_size_t()

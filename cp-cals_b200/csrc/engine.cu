@@ -93,6 +93,8 @@ struct cals_b200_ctx {
   int *d_live = nullptr, *d_live_tmp = nullptr, *d_gather = nullptr, *d_evict = nullptr;
   double *d_gram = nullptr, *d_lambda = nullptr;
   int *h_flags = nullptr, *d_flags = nullptr;
+  unsigned *d_iter_cols = nullptr; // [ITER_LOG_CAP]
+  unsigned long long last_global_iter = 0;
   std::vector<void *> run_allocs;
   int run_cols = 0, run_total_cols = 0, run_models = 0;
 
@@ -393,6 +395,8 @@ int ensure_dummy_state(cals_b200_ctx *c) {
     CU_TRY(c, cudaMalloc((void **)&c->d_st, sizeof(SchedState)));
     CU_TRY(c, cudaMemset(c->d_st, 0, sizeof(SchedState)));
   }
+  if (!c->d_iter_cols)
+    CU_TRY(c, cudaMalloc((void **)&c->d_iter_cols, (size_t)ITER_LOG_CAP * sizeof(unsigned)));
   return 0;
 }
 
@@ -632,7 +636,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
 
   init_grams_kernel<<<dim3(M, N), 256, 0, s>>>(geo, b.fac, c->d_models, c->d_gram);
 
-  SchedParams sp{c->d_st, c->d_models, c->d_live, c->d_live_tmp, c->d_gather, c->d_evict, c->d_flags, b.plans};
+  SchedParams sp{c->d_st,    c->d_models, c->d_live, c->d_live_tmp,  c->d_gather,
+                 c->d_evict, c->d_flags,  b.plans,   c->d_iter_cols};
   const int max_live = std::min(M, c->buffer_cols);
   const dim3 move_grid((c->buffer_cols + MOVE_COLS - 1) / MOVE_COLS, N, 2);
 
@@ -730,6 +735,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
 
   // scalars back
   CU_TRY(c, cudaMemcpy(&st, c->d_st, sizeof st, cudaMemcpyDeviceToHost));
+  c->last_global_iter = st.global_iter;
   if (rep) {
     memset(rep, 0, sizeof *rep);
     rep->iter = st.global_iter;
@@ -869,6 +875,8 @@ int cals_b200_destroy(cals_b200_ctx *c) {
   release_tensor(c);
   if (c->d_st)
     cudaFree(c->d_st);
+  if (c->d_iter_cols)
+    cudaFree(c->d_iter_cols);
   if (c->h_flags)
     cudaFreeHost(c->h_flags);
   for (auto &p : c->h_home)
@@ -1104,6 +1112,35 @@ int cals_b200_mttkrp(cals_b200_ctx *c, int mode, uint64_t cols, const double *co
   }
   free_all(b.allocs);
   return rc;
+}
+
+int cals_b200_fetch_iteration_cols(cals_b200_ctx *c, uint32_t *cols_out, uint64_t capacity, uint64_t *n_out) {
+  if (!c || !n_out)
+    return fail(c, "null argument");
+  cudaSetDevice(c->device);
+  const uint64_t logged = std::min<uint64_t>(c->last_global_iter, (uint64_t)ITER_LOG_CAP);
+  *n_out = logged;
+  const uint64_t n = std::min<uint64_t>(logged, capacity);
+  if (n && cols_out) {
+    if (!c->d_iter_cols)
+      return fail(c, "no run to fetch the iteration log from");
+    CU_TRY(c, cudaMemcpy(cols_out, c->d_iter_cols, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+void *cals_b200_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError(); // no device / out of pinned memory: the caller falls back to pageable memory
+    return nullptr;
+  }
+  return p;
+}
+
+void cals_b200_host_free(void *p) {
+  if (p)
+    cudaFreeHost(p);
 }
 
 int cals_b200_device_info(cals_b200_ctx *c, int *sm_count, size_t *free_bytes, size_t *total_bytes) {

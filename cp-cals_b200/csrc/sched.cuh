@@ -25,7 +25,9 @@ struct SchedParams {
   int *evict_dst;  // [buffer_cols] old column j -> home column, or -1
   int *host_flags; // mapped pinned host memory: [0] done, [1] global_iter (low 31 bits), [2] n_live
   PlanArgs plans;  // MTTKRP work partition per mode, rebuilt whenever the live column count changes
+  unsigned *iter_cols; // [ITER_LOG_CAP] active column count of every executed iteration (CalsReport::cols)
 };
+constexpr int ITER_LOG_CAP = 65536;
 
 // Thread 0 does the queue bookkeeping (the live list is short, <= buffer_cols entries, and this runs once per CALS
 // iteration); then one thread per mode rebuilds that mode's MTTKRP plan if the column count changed.
@@ -122,6 +124,8 @@ __device__ void sched_serial(const SchedParams &p) {
   if (n_live == 0 && st->next >= st->n_models) {
     st->done = 1;
   } else {
+    if (st->global_iter < (unsigned long long)ITER_LOG_CAP)
+      p.iter_cols[st->global_iter] = (unsigned)col;
     st->global_iter += 1; // reference: rep.iter counts executed loop bodies (src/cals.cpp:175-176)
     st->col_iter_sum += (unsigned long long)col;
   }

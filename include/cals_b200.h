@@ -104,6 +104,16 @@ int cals_b200_jk_norms(cals_b200_ctx *ctx, double *out);
 int cals_b200_mttkrp(cals_b200_ctx *ctx, int mode, uint64_t cols, const double *const *host_factors, double *host_G,
                      int variant, int repeats, double *ms_out);
 
+/* CalsReport::cols (reference include/cals.h:62, filled at src/cals.cpp:214): the number of active multi-factor
+ * columns in every global iteration of the last run.  Writes min(*n_out, capacity) entries; *n_out = iterations
+ * logged (the device keeps the first 65536). */
+int cals_b200_fetch_iteration_cols(cals_b200_ctx *ctx, uint32_t *cols_out, uint64_t capacity, uint64_t *n_out);
+
+/* ---- page-locked host memory for the caller's tensors (so that set_tensor / enqueue run at full link speed) ------ */
+/* Returns NULL when there is no CUDA device (callers then use ordinary memory); free with cals_b200_host_free. */
+void *cals_b200_host_alloc(size_t bytes);
+void cals_b200_host_free(void *p);
+
 /* ---- introspection --------------------------------------------------------------------------------------------- */
 int cals_b200_device_info(cals_b200_ctx *ctx, int *sm_count, size_t *free_bytes, size_t *total_bytes);
 const char *cals_b200_version(void);
