@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "cals_b200_clear_models", "cals_b200_enqueue_model", "cals_b200_run", "cals_b200_rerun",
     "cals_b200_fetch_model", "cals_b200_fetch_all", "cals_b200_tensor_norm", "cals_b200_jk_norms",
     "cals_b200_mttkrp", "cals_b200_device_info", "cals_b200_version", "cals_b200_fetch_iteration_cols",
-    "cals_b200_host_alloc", "cals_b200_host_free",
+    "cals_b200_host_alloc", "cals_b200_host_free", "cals_b200_stream",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
     L.cals_b200_host_alloc.argtypes = [C.c_size_t]
     L.cals_b200_host_alloc.restype = vp
     L.cals_b200_host_free.argtypes = [vp]
+    L.cals_b200_stream.argtypes = [vp, C.POINTER(vp)]
     _lib = L
     return L
 
@@ -319,6 +320,12 @@ class Engine:
             self._ck(self._L.cals_b200_fetch_iteration_cols(self._ctx, out.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                             n.value, C.byref(n)))
         return out
+
+    def stream_handle(self) -> int:
+        """cudaStream_t of this context as an integer (wrap with torch.cuda.ExternalStream to record events on it)."""
+        out = C.c_void_p()
+        self._ck(self._L.cals_b200_stream(self._ctx, C.byref(out)))
+        return int(out.value or 0)
 
     def device_info(self):
         sm, fr, tot = C.c_int(), C.c_size_t(), C.c_size_t()

@@ -1143,6 +1143,13 @@ void cals_b200_host_free(void *p) {
     cudaFreeHost(p);
 }
 
+int cals_b200_stream(cals_b200_ctx *c, void **stream_out) {
+  if (!c || !stream_out)
+    return fail(c, "null argument");
+  *stream_out = (void *)c->stream;
+  return 0;
+}
+
 int cals_b200_device_info(cals_b200_ctx *c, int *sm_count, size_t *free_bytes, size_t *total_bytes) {
   if (!c)
     return 1;

@@ -115,6 +115,9 @@ void *cals_b200_host_alloc(size_t bytes);
 void cals_b200_host_free(void *p);
 
 /* ---- introspection --------------------------------------------------------------------------------------------- */
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so that a caller can record its
+ * own CUDA events around calls (bench.py times the steps with events on this stream). */
+int cals_b200_stream(cals_b200_ctx *ctx, void **stream_out);
 int cals_b200_device_info(cals_b200_ctx *ctx, int *sm_count, size_t *free_bytes, size_t *total_bytes);
 const char *cals_b200_version(void);
 
