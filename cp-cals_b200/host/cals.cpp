@@ -1,0 +1,359 @@
+// cals::cp_cals / cals::jk_cp_cals on the B200 (reference src/cals.cpp:19-446).
+//
+// What the reference does on the host inside its do/while loop -- admission, MTTKRP, per-model update, error, eviction,
+// compaction -- runs on the device behind cals_b200_run (cp-cals_b200/csrc).  The host side left here is: validate the
+// parameters, hand X and the queued models to the C ABI, copy the fitted models back into the caller's Ktensors and
+// fill the report.  With CalsParams::devices = {d0, d1, ..} the model set is sharded over several GPUs of the box (X
+// replicated, one host thread per device, no data-path collective).
+#include <algorithm>
+#include <cmath>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <numeric>
+#include <thread>
+
+#include "cals.h"
+#include "engine_pool.h"
+
+namespace cals {
+namespace detail {
+
+namespace {
+std::mutex g_pool_mu;
+std::map<int, std::unique_ptr<EngineHandle>> g_pool;
+
+struct PoolCleaner { // destroy the contexts before the CUDA runtime is torn down at exit
+  ~PoolCleaner() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (auto &kv : g_pool)
+      if (kv.second->ctx)
+        cals_b200_destroy(kv.second->ctx);
+    g_pool.clear();
+  }
+} g_cleaner;
+} // namespace
+
+EngineHandle &engine_for_device(int device) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto it = g_pool.find(device);
+  if (it != g_pool.end())
+    return *it->second;
+  auto h = std::make_unique<EngineHandle>();
+  h->device = device;
+  if (cals_b200_create(&h->ctx, device) != 0)
+    throw B200Error(std::string("cals_b200_create(device ") + std::to_string(device) +
+                    ") failed: " + cals_b200_last_error(nullptr));
+  return *(g_pool[device] = std::move(h));
+}
+
+void check(EngineHandle &e, int rc, const char *what) {
+  if (rc != 0)
+    throw B200Error(std::string(what) + ": " + cals_b200_last_error(e.ctx));
+}
+
+void upload_tensor(EngineHandle &e, const Tensor &X, bool may_skip) {
+  const vector<dim_t> modes = X.get_modes();
+  if (may_skip && e.resident_data == X.get_data() && e.resident_modes == modes)
+    return;
+  std::vector<uint64_t> m(modes.begin(), modes.end());
+  e.resident_data = nullptr;
+  check(e, cals_b200_set_tensor(e.ctx, static_cast<int>(m.size()), m.data(), X.get_data()), "cals_b200_set_tensor");
+  e.resident_data = X.get_data();
+  e.resident_modes = modes;
+}
+
+RunResult run_on_device(int device, const Tensor &X, const std::vector<Ktensor *> &models, const RunOptions &opt) {
+  EngineHandle &e = engine_for_device(device);
+  std::lock_guard<std::mutex> lk(e.mu);
+  RunResult out;
+  if (models.empty())
+    return out;
+  upload_tensor(e, X, opt.skip_upload_if_resident);
+  const unsigned flags = (opt.force_max_iter ? CALS_B200_FORCE_MAX_ITER : 0u) |
+                         (opt.always_evict_first ? CALS_B200_ALWAYS_EVICT_FIRST : 0u);
+  // A buffer wider than the whole queue behaves exactly like one that just holds it (everything is admitted at once),
+  // so the device buffers are sized by what can actually be resident.
+  dim_t sum_ranks = 0;
+  for (const Ktensor *kt : models)
+    sum_ranks += kt->get_components();
+  const dim_t buffer = std::max<dim_t>(std::min(opt.buffer_size, sum_ranks), 1);
+  check(e, cals_b200_configure(e.ctx, buffer, opt.max_iterations, opt.tol, flags), "cals_b200_configure");
+  check(e, cals_b200_set_timing(e.ctx, opt.timing), "cals_b200_set_timing");
+  check(e, cals_b200_clear_models(e.ctx), "cals_b200_clear_models");
+
+  const dim_t N = X.get_n_modes();
+  std::vector<const double *> in(N);
+  for (Ktensor *kt : models) {
+    if (kt->get_n_modes() != N)
+      throw B200Error("cp_cals: a Ktensor has a different number of modes than the tensor");
+    for (dim_t n = 0; n < N; n++) {
+      if (kt->get_factor(n).get_rows() != X.get_modes()[n])
+        throw B200Error("cp_cals: a Ktensor factor does not match the tensor extents");
+      in[n] = kt->get_factor(n).get_data();
+    }
+    int id = -1;
+    check(e,
+          cals_b200_enqueue_model(e.ctx, kt->get_components(), in.data(), kt->is_jk() ? (int)kt->get_jk_mode() : -1,
+                                  kt->is_jk() ? (int64_t)kt->get_jk_fiber() : 0, &id),
+          "cals_b200_enqueue_model");
+  }
+  check(e, cals_b200_run(e.ctx, &out.rep), "cals_b200_run");
+
+  // results straight into the callers' storage (Ktensor::detach of the reference, src/ktensor.cpp:127-135)
+  const size_t M = models.size();
+  std::vector<double *> fptr(M * N), lptr(M);
+  std::vector<cals_b200_model_stats> stats(M);
+  for (size_t m = 0; m < M; m++) {
+    for (dim_t n = 0; n < N; n++)
+      fptr[m * N + n] = models[m]->get_factor(n).get_data();
+    lptr[m] = models[m]->get_lambda().data();
+  }
+  check(e, cals_b200_fetch_all(e.ctx, fptr.data(), lptr.data(), stats.data()), "cals_b200_fetch_all");
+  for (size_t m = 0; m < M; m++) {
+    models[m]->set_iters(static_cast<dim_t>(stats[m].iters));
+    models[m]->set_approximation_error(stats[m].error);
+    models[m]->set_fit(stats[m].fit, stats[m].old_fit);
+  }
+  uint64_t n_it = 0;
+  check(e, cals_b200_fetch_iteration_cols(e.ctx, nullptr, 0, &n_it), "cals_b200_fetch_iteration_cols");
+  std::vector<uint32_t> c32(n_it);
+  if (n_it)
+    check(e, cals_b200_fetch_iteration_cols(e.ctx, c32.data(), n_it, &n_it), "cals_b200_fetch_iteration_cols");
+  out.cols.assign(c32.begin(), c32.end());
+  return out;
+}
+
+std::vector<std::vector<size_t>> shard_models(const std::vector<dim_t> &ranks, size_t n_parts) {
+  std::vector<std::vector<size_t>> parts(std::max<size_t>(n_parts, 1));
+  std::vector<dim_t> load(parts.size(), 0);
+  for (size_t i = 0; i < ranks.size(); i++) {
+    size_t best = 0;
+    for (size_t p = 1; p < parts.size(); p++)
+      if (load[p] < load[best])
+        best = p;
+    parts[best].push_back(i);
+    load[best] += ranks[i];
+  }
+  return parts;
+}
+
+} // namespace detail
+
+// ---------------------------------------------------------------------------------------------------------------------
+static void reject_unsupported(update::UPDATE_METHOD um, bool line_search, const char *who) {
+  if (um != update::UNCONSTRAINED)
+    throw B200Error(std::string(who) + ": update method '" + update::update_method_names[um] +
+                    "' is not on the B200 path (only 'unconstrained'); there is no CPU fallback");
+  if (line_search)
+    throw B200Error(std::string(who) + ": line search is not on the B200 path; there is no CPU fallback");
+}
+
+CalsReport cp_cals(const Tensor &X, KtensorQueue &kt_queue, CalsParams &cals_params) {
+  reject_unsupported(cals_params.update_method, cals_params.line_search, "cp_cals");
+  if (X.get_n_modes() < 3)
+    throw B200Error("cp_cals: tensors need at least 3 modes (the reference asserts the same, src/cals.cpp:52)");
+
+  CalsReport rep;
+  rep.tensor_rank = X.get_rank();
+  rep.n_modes = X.get_n_modes();
+  rep.modes = X.get_modes();
+  rep.max_iter = cals_params.max_iterations;
+  rep.n_threads = get_threads();
+  rep.buffer_size = cals_params.buffer_size;
+  rep.tol = cals_params.tol;
+  rep.cuda = true;
+  rep.update_method = cals_params.update_method;
+  rep.line_search = cals_params.line_search;
+  rep.line_search_interval = cals_params.line_search_interval;
+  rep.line_search_step = cals_params.line_search_step;
+  rep.line_search_method = cals_params.line_search_method;
+
+  Timer total;
+  total.start();
+
+  // drain the queue (the reference pops every model it admits, src/cals.cpp:182-192)
+  std::vector<Ktensor *> models;
+  models.reserve(kt_queue.size());
+  while (!kt_queue.empty()) {
+    models.push_back(&kt_queue.front().get());
+    kt_queue.pop();
+  }
+
+  detail::RunOptions opt;
+  opt.buffer_size = cals_params.buffer_size;
+  opt.max_iterations = cals_params.max_iterations;
+  opt.tol = cals_params.tol;
+  opt.force_max_iter = cals_params.force_max_iter;
+  opt.always_evict_first = cals_params.always_evict_first;
+  opt.timing = cals_params.timing;
+
+  std::vector<int> devices = cals_params.devices.empty() ? std::vector<int>{0} : cals_params.devices;
+  rep.n_devices = static_cast<int>(devices.size());
+
+  std::vector<detail::RunResult> results(devices.size());
+  if (devices.size() == 1) {
+    results[0] = detail::run_on_device(devices[0], X, models, opt);
+  } else {
+    std::vector<dim_t> ranks(models.size());
+    for (size_t i = 0; i < models.size(); i++)
+      ranks[i] = models[i]->get_components();
+    const auto parts = detail::shard_models(ranks, devices.size());
+    std::vector<std::thread> workers;
+    std::vector<std::string> errors(devices.size());
+    for (size_t d = 0; d < devices.size(); d++)
+      workers.emplace_back([&, d] {
+        try {
+          std::vector<Ktensor *> mine;
+          for (size_t i : parts[d])
+            mine.push_back(models[i]);
+          results[d] = detail::run_on_device(devices[d], X, mine, opt);
+        } catch (const std::exception &ex) {
+          errors[d] = ex.what();
+        }
+      });
+    for (auto &w : workers)
+      w.join();
+    for (size_t d = 0; d < devices.size(); d++)
+      if (!errors[d].empty())
+        throw B200Error("cp_cals on device " + std::to_string(devices[d]) + ": " + errors[d]);
+  }
+  total.stop();
+
+  // merge the per-device reports: iteration i of the job = iteration i of every shard, side by side
+  for (const auto &r : results) {
+    rep.iter = std::max<dim_t>(rep.iter, r.rep.iter);
+    rep.n_ktensors += static_cast<int>(r.rep.n_ktensors);
+    rep.ktensor_comp_sum += static_cast<int>(r.rep.ktensor_comp_sum);
+    if (r.rep.x_norm > 0)
+      rep.X_norm = r.rep.x_norm;
+    rep.device_ms = std::max(rep.device_ms, r.rep.device_ms);
+    rep.mttkrp_ms = std::max(rep.mttkrp_ms, r.rep.mttkrp_ms);
+    rep.update_ms = std::max(rep.update_ms, r.rep.update_ms);
+    rep.kernel_launches += r.rep.kernel_launches;
+    rep.mttkrp_flops += r.rep.mttkrp_flops;
+  }
+  if (models.empty())
+    rep.X_norm = X.norm();
+  rep.total_time = total.get_time();
+
+  const dim_t its = rep.iter;
+  rep.cols.assign(its, 0);
+  for (const auto &r : results)
+    for (dim_t i = 0; i < r.cols.size() && i < its; i++)
+      rep.cols[i] += r.cols[i];
+  rep.flops_per_iteration.assign(its, 0);
+  for (dim_t i = 0; i < its; i++)
+    rep.flops_per_iteration[i] = 2ull * rep.n_modes * X.get_n_elements() * rep.cols[i];
+
+  rep.als_times = Matrix(AlsTimers::LENGTH, std::max<dim_t>(its, 1));
+  rep.mode_times = Matrix(ModeTimers::LENGTH * rep.n_modes, std::max<dim_t>(its, 1));
+  rep.mttkrp_times = Matrix(MttkrpTimers::LENGTH * rep.n_modes, std::max<dim_t>(its, 1));
+  rep.als_times.zero();
+  rep.mode_times.zero();
+  rep.mttkrp_times.zero();
+  for (dim_t i = 0; i < its; i++) {
+    rep.als_times(AlsTimers::ITERATION, i) = rep.device_ms * 1e-3 / static_cast<double>(its);
+    for (dim_t n = 0; n < rep.n_modes; n++) {
+      rep.mode_times(n * ModeTimers::LENGTH + ModeTimers::MTTKRP, i) =
+          rep.mttkrp_ms * 1e-3 / static_cast<double>(its * rep.n_modes);
+      rep.mode_times(n * ModeTimers::LENGTH + ModeTimers::UPDATE, i) =
+          rep.update_ms * 1e-3 / static_cast<double>(its * rep.n_modes);
+    }
+  }
+  return rep;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+JKReport jk_cp_cals(const Tensor &X, vector<Ktensor> &kt_vector, CalsParams &cals_params) {
+  vector<Ktensor> bases(kt_vector);
+  for (Ktensor &b : bases)
+    b.denormalize().normalize();
+
+  Timer pre, run;
+  pre.start();
+  vector<vector<Ktensor>> jk_input(bases.size());
+  for (size_t b = 0; b < bases.size(); b++)
+    utils::generate_jk_ktensors(bases[b], jk_input[b]);
+  KtensorQueue queue;
+  for (auto &group : jk_input)
+    for (Ktensor &m : group)
+      queue.emplace(m);
+  pre.stop();
+
+  run.start();
+  cp_cals(X, queue, cals_params);
+  run.stop();
+
+  // reference src/cals.cpp:431-437
+  for (auto &group : jk_input)
+    for (Ktensor &m : group) {
+      m.set_jk_fiber(0.0);
+      m.denormalize();
+      m.normalize();
+      m.set_jk_fiber(NAN);
+    }
+  for (size_t b = 0; b < bases.size(); b++)
+    utils::jk_permutation_adjustment(bases[b], jk_input[b]);
+
+  return JKReport{JKTime{pre.get_time(), run.get_time()}, std::move(jk_input)};
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+void CalsParams::print() const {
+  using std::cout;
+  using std::endl;
+  const char *rule = "---------------------------------------";
+  cout << rule << "\nCALS parameters\n" << rule << endl;
+  cout << "Tol:             " << tol << endl;
+  cout << "Max Iterations:  " << max_iterations << endl;
+  cout << "Buffer Size:     " << buffer_size << endl;
+  cout << "Mttkrp Method:   " << mttkrp::mttkrp_method_names[mttkrp_method] << " (ignored: B200 kernels)" << endl;
+  cout << "Update Method:   " << update::update_method_names[update_method] << endl;
+  cout << "Line Search:     " << (line_search ? "true" : "false") << endl;
+  if (line_search) {
+    cout << "-Line Search Interval: " << line_search_interval << " iterations" << endl;
+    cout << "-Line Search Method:   " << ls::ls_method_names[line_search_method] << endl;
+  }
+  cout << "CUDA:            true (B200, devices:";
+  if (devices.empty())
+    cout << " 0";
+  for (int d : devices)
+    cout << " " << d;
+  cout << ")" << endl << rule << endl;
+}
+
+// CSV layout of the reference (include/cals.h:70-132): one header line, then one line per CALS iteration.
+void CalsReport::print_header(const std::string &file_name, const std::string &sep) const {
+  std::ofstream file(file_name, std::ios::out);
+  for (const char *name : {"TENSOR_RANK", "TENSOR_MODES", "BUFFER_SIZE", "N_KTENSORS", "KTENSOR_COMP_SUM",
+                           "UPDATE_METHOD", "LINE_SEARCH", "MAX_ITERS", "ITER", "NUM_THREADS", "TOTAL", "FLOPS", "COLS"})
+    file << name << sep;
+  AlsTimers at;
+  ModeTimers mt;
+  for (const auto &name : at.names)
+    file << name << sep;
+  for (dim_t n = 0; n < modes.size(); n++)
+    for (const auto &name : mt.names)
+      file << "MODE_" << n << "_" << name << sep;
+  file << std::endl;
+}
+
+void CalsReport::print_to_file(const std::string &file_name, const std::string &sep) const {
+  std::ofstream file(file_name, std::ios::app);
+  for (dim_t it = 0; it < iter; it++) {
+    file << tensor_rank << sep << utils::mode_string(modes) << sep << buffer_size << sep << n_ktensors << sep
+         << ktensor_comp_sum << sep << update::update_method_names[update_method] << sep << line_search << sep
+         << max_iter << sep << it + 1 << sep << n_threads << sep << total_time << sep;
+    file << flops_per_iteration[it] << sep << cols[it] << sep;
+    file << std::scientific;
+    for (dim_t i = 0; i < als_times.get_rows(); i++)
+      file << als_times(i, it) << sep;
+    for (dim_t i = 0; i < mode_times.get_rows(); i++)
+      file << mode_times(i, it) << sep;
+    file << std::defaultfloat << std::endl;
+  }
+}
+
+} // namespace cals

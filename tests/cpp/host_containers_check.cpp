@@ -1,0 +1,188 @@
+// Host-only checks of the cals:: containers (no device needed): Tensor / Matrix / Ktensor bookkeeping, normalisation
+// identities, jackknife helpers, linear sum assignment, the model sharding plan.  Prints OK and exits 0 on success.
+#include <cmath>
+#include <cstdio>
+#include <numeric>
+#include <random>
+
+#include "cals.h"
+#include "utils/error.h"
+
+#define REQUIRE(c)                                                                                                     \
+  do {                                                                                                                 \
+    if (!(c)) {                                                                                                        \
+      std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #c);                                                       \
+      return 1;                                                                                                        \
+    }                                                                                                                  \
+  } while (0)
+
+namespace cals::detail {
+std::vector<std::vector<size_t>> shard_models(const std::vector<dim_t> &ranks, size_t n_parts);
+}
+
+int main() {
+  using namespace cals;
+  std::mt19937 gen(0);
+  std::uniform_real_distribution<double> dist(-1.0, 1.0);
+  auto draw = [&] { return dist(gen); };
+
+  // Tensor: layout, views, copies, unfolding geometry
+  Tensor T(std::vector<dim_t>{4, 3, 2});
+  T.fill(draw);
+  REQUIRE(T.get_n_elements() == 24 && T.get_n_modes() == 3 && !T.is_view());
+  Tensor V(std::vector<dim_t>{4, 3, 2}, T.get_data());
+  REQUIRE(V.is_view() && V.get_data() == T.get_data());
+  Tensor Tc(T);
+  REQUIRE(Tc.get_data() != T.get_data() && Tc[5] == T[5]);
+  double ss = 0;
+  for (dim_t i = 0; i < 24; i++)
+    ss += T[i] * T[i];
+  REQUIRE(std::fabs(T.norm() - std::sqrt(ss)) < 1e-14);
+  Unfolding u0 = T.implicit_unfold(0), u1 = T.implicit_unfold(1), u2 = T.implicit_unfold(2);
+  REQUIRE(u0.n_blocks == 1 && u0.rows == 4 && u0.cols == 6);
+  REQUIRE(u1.n_blocks == 2 && u1.rows == 3 && u1.cols == 4 && u1.block_offset == 12);
+  REQUIRE(u2.n_blocks == 1 && u2.rows == 2 && u2.cols == 12);
+
+  // Matrix
+  Matrix M(3, 2);
+  M.fill(draw);
+  REQUIRE(M(2, 1) == M.get_data()[5] && M.get_col_stride() == 3);
+  Matrix Mt(2, 3);
+  Mt.transpose_copy(M); // Mt holds the row-major image of M
+  REQUIRE(Mt.get_data()[1 + 2 * 2] == M(2, 1));
+
+  // Ktensor: fill + normalise, reconstruction invariance under denormalize/normalize
+  Ktensor K(3, {5, 4, 6});
+  K.fill(draw);
+  for (dim_t n = 0; n < 3; n++)
+    for (dim_t c = 0; c < 3; c++) {
+      double s = 0;
+      for (dim_t r = 0; r < K.get_factor(n).get_rows(); r++)
+        s += K.get_factor(n)(r, c) * K.get_factor(n)(r, c);
+      REQUIRE(std::fabs(s - 1.0) < 1e-13);
+    }
+  Tensor R0 = K.to_tensor();
+  K.denormalize().normalize();
+  Tensor R1 = K.to_tensor();
+  double gap = 0;
+  for (dim_t i = 0; i < R0.get_n_elements(); i++)
+    gap = std::max(gap, std::fabs(R0[i] - R1[i]));
+  REQUIRE(gap < 1e-13);
+  // signed max-abs normalisation of later iterations: lambda = entry of largest magnitude, first index on ties
+  Ktensor S(1, {4, 3, 3});
+  S.get_factor(0)(0, 0) = 0.5, S.get_factor(0)(1, 0) = -2.0, S.get_factor(0)(2, 0) = 2.0, S.get_factor(0)(3, 0) = 1.0;
+  S.normalize(0, 2);
+  REQUIRE(S.get_lambda()[0] == -2.0 && S.get_factor(0)(1, 0) == 1.0 && S.get_factor(0)(2, 0) == -1.0);
+  // copies get new ids, copy() keeps the id
+  Ktensor K2(K);
+  REQUIRE(K2.get_id() != K.get_id() && K2.get_components() == 3);
+  const int id2 = K2.get_id();
+  K2.copy(K);
+  REQUIRE(K2.get_id() == id2);
+
+  // jackknife helpers
+  std::vector<Ktensor> jk;
+  utils::generate_jk_ktensors(K, jk);
+  REQUIRE(jk.size() == 5 && jk[3].is_jk() && jk[3].get_jk_fiber() == 3 && jk[3].get_jk_mode() == 0);
+  jk[3].set_jk_fiber(0.0);
+  REQUIRE(jk[3].get_factor(0)(3, 1) == 0.0);
+  Ktensor reg = jk[3].to_regular();
+  REQUIRE(reg.get_factor(0).get_rows() == 4 && reg.get_factor(0)(3, 2) == jk[3].get_factor(0)(4, 2));
+  jk[3].set_jk_fiber(NAN);
+  REQUIRE(std::isnan(jk[3].get_factor(0)(3, 0)));
+  // permutation adjustment: a leave-one-out model whose components are a permutation of the base model's.  The
+  // reference applies new[:, c] = old[:, p[c]] with p[c] = base component matched to component c (src/utils/utils.cpp:
+  // 88-99), which undoes the permutation when it is its own inverse -- a swap here.
+  std::vector<Ktensor> shuffled;
+  shuffled.emplace_back(K);
+  const dim_t perm[3] = {2, 1, 0};
+  for (dim_t n = 0; n < 3; n++)
+    for (dim_t c = 0; c < 3; c++)
+      for (dim_t r = 0; r < K.get_factor(n).get_rows(); r++)
+        shuffled[0].get_factor(n)(r, c) = K.get_factor(n)(r, perm[c]);
+  utils::jk_permutation_adjustment(K, shuffled);
+  for (dim_t n = 0; n < 3; n++)
+    for (dim_t e = 0; e < K.get_factor(n).get_n_elements(); e++)
+      REQUIRE(shuffled[0].get_factor(n)[e] == K.get_factor(n)[e]);
+
+  // linear sum assignment against brute force
+  for (int trial = 0; trial < 20; trial++) {
+    const dim_t n = 5;
+    std::vector<double> cost(n * n);
+    for (double &c : cost)
+      c = draw();
+    std::vector<int64_t> assign;
+    utils::linear_sum_assignment(n, cost.data(), true, assign);
+    double got = 0;
+    for (dim_t i = 0; i < n; i++)
+      got += cost[i * n + assign[i]];
+    std::vector<int> p(n);
+    std::iota(p.begin(), p.end(), 0);
+    double best = -1e300;
+    do {
+      double s = 0;
+      for (dim_t i = 0; i < n; i++)
+        s += cost[i * n + p[i]];
+      best = std::max(best, s);
+    } while (std::next_permutation(p.begin(), p.end()));
+    REQUIRE(std::fabs(got - best) < 1e-12);
+  }
+
+  // fast error == explicit error on the host helpers
+  {
+    Ktensor A(2, {4, 3, 5});
+    A.fill(draw);
+    Tensor X = A.to_tensor();
+    std::vector<Matrix> grams;
+    for (dim_t n = 0; n < 3; n++)
+      grams.emplace_back(2, 2);
+    ops::update_gramians(A, grams);
+    ops::hadamard_all(grams);
+    // G_last = X_(2) * KRP(A1, A0) = A2 * diag(lambda) * hadamard(gram0, gram1) for an exact model
+    Matrix G(5, 2);
+    std::vector<Matrix> g01;
+    g01.emplace_back(2, 2);
+    g01.emplace_back(2, 2);
+    ops::update_gramian(A.get_factor(0), g01[0]);
+    ops::update_gramian(A.get_factor(1), g01[1]);
+    g01[0].hadamard(g01[1]);
+    for (dim_t i = 0; i < 5; i++)
+      for (dim_t c = 0; c < 2; c++) {
+        double s = 0;
+        for (dim_t r = 0; r < 2; r++)
+          s += A.get_factor(2)(i, r) * A.get_lambda()[r] * g01[0](r, c);
+        G(i, c) = s;
+      }
+    const double e = error::compute_fast_error(X.norm(), A.get_lambda(), A.get_factor(2), G, grams[0]);
+    REQUIRE(e < 1e-6 * X.norm()); // the formula is a cancellation: ~sqrt(eps) * ||X||
+    Matrix w1, w2;
+    REQUIRE(error::compute_error(X, A, w1, w2) < 1e-13 * X.norm());
+  }
+
+  // sharding plan: every model exactly once, queue order kept inside a shard, loads balanced
+  {
+    std::vector<dim_t> ranks;
+    for (dim_t r = 1; r <= 20; r++)
+      ranks.insert(ranks.end(), 10, r);
+    auto parts = detail::shard_models(ranks, 8);
+    std::vector<int> seen(ranks.size(), 0);
+    dim_t lo = ~dim_t(0), hi = 0;
+    for (auto &p : parts) {
+      dim_t load = 0;
+      for (size_t k = 0; k < p.size(); k++) {
+        seen[p[k]]++;
+        load += ranks[p[k]];
+        REQUIRE(k == 0 || p[k] > p[k - 1]);
+      }
+      lo = std::min(lo, load), hi = std::max(hi, load);
+    }
+    for (int s : seen)
+      REQUIRE(s == 1);
+    REQUIRE(hi - lo <= 20);
+  }
+
+  set_threads(6);
+  REQUIRE(get_threads() == 6);
+  std::printf("OK\n");
+  return 0;
+}

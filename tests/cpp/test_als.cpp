@@ -1,0 +1,117 @@
+// cals::cp_als on the B200 path, restating the reference's tests/als/test_als.cpp: the fitted model reconstructs the
+// tensor, every MTTKRP method knob leads to the same result (here: to the same kernels), and the fast error formula
+// equals the explicit ||X - model||.  Needs a B200: run by pytest -m gpu (tests/test_cpp_api.py).
+#include <cmath>
+#include <random>
+
+#include "gtest/gtest.h"
+
+#include "als.h"
+#include "cals.h"
+
+using cals::Ktensor;
+using cals::Tensor;
+
+static double explicit_error(const Tensor &X, Ktensor &k) {
+  Tensor approx = k.to_tensor();
+  for (dim_t i = 0; i < X.get_n_elements(); i++)
+    approx[i] = X[i] - approx[i];
+  return approx.norm();
+}
+
+// reference Als.ComputeCorrectResult3D (tests/als/test_als.cpp:10-60)
+TEST(Als, EveryMttkrpMethodKnobGivesTheSameFit3D) {
+  const std::vector<dim_t> modes{9, 4, 2};
+  Tensor X(5, modes);
+  Ktensor k(5, modes);
+  const cals::mttkrp::MTTKRP_METHOD knobs[] = {cals::mttkrp::MTTKRP, cals::mttkrp::TWOSTEP0, cals::mttkrp::TWOSTEP1,
+                                               cals::mttkrp::AUTO};
+  for (int trial = 0; trial < 10; trial++) {
+    k.randomize();
+    double first = 0.0;
+    for (int v = 0; v < 4; v++) {
+      cals::AlsParams p;
+      p.max_iterations = 100;
+      p.mttkrp_method = knobs[v];
+      p.suppress_lut_warning = true;
+      Ktensor fitted(k);
+      cals::cp_als(X, fitted, p);
+      const double err = explicit_error(X, fitted);
+      EXPECT_FALSE(std::isnan(err));
+      EXPECT_LT(err, 50);
+      if (v == 0)
+        first = err;
+      EXPECT_NEAR(err, first, 1e-8);
+    }
+  }
+}
+
+// reference Als.ComputeCorrectResult4D (tests/als/test_als.cpp:104-123)
+TEST(Als, FitsAnExactRankFiveTensor4D) {
+  Tensor X(5, {3, 3, 3, 3});
+  Ktensor k(7, {3, 3, 3, 3});
+  k.randomize();
+  cals::AlsParams p;
+  p.max_iterations = 100;
+  p.suppress_lut_warning = true;
+  cals::cp_als(X, k, p);
+  const double err = explicit_error(X, k);
+  EXPECT_FALSE(std::isnan(err));
+  EXPECT_LT(err, 1e-1);
+}
+
+// reference Als.ComputeCorrectError (tests/als/test_als.cpp:125-145)
+TEST(Als, FastErrorEqualsExplicitError) {
+  Tensor X(5, {9, 3, 2});
+  Ktensor k(5, {9, 3, 2});
+  k.randomize();
+  cals::AlsParams p;
+  p.max_iterations = 3;
+  p.suppress_lut_warning = true;
+  const cals::AlsReport rep = cals::cp_als(X, k, p);
+  EXPECT_LE(rep.iter, (dim_t)3);
+  EXPECT_NEAR(k.get_approximation_error(), explicit_error(X, k), 1e-10);
+}
+
+// The single-operation seam: mttkrp::mttkrp overwrites the factor of the requested mode with X_(n) * KRP.
+TEST(Als, MttkrpHookMatchesDirectEvaluation) {
+  const std::vector<dim_t> modes{7, 6, 5};
+  Tensor X(modes);
+  std::mt19937 gen(1);
+  std::uniform_real_distribution<double> dist(-1.0, 1.0);
+  X.fill([&] { return dist(gen); });
+  Ktensor k(4, modes);
+  k.fill([&] { return dist(gen); });
+  for (dim_t n = 0; n < 3; n++) {
+    Ktensor u(k);
+    std::vector<cals::Matrix> ws;
+    cals::mttkrp::MttkrpParams mp;
+    cals::Matrix &G = cals::mttkrp::mttkrp(X, u, ws, n, mp);
+    double worst = 0.0;
+    for (dim_t c = 0; c < 4; c++)
+      for (dim_t i = 0; i < modes[n]; i++) {
+        double want = 0.0;
+        dim_t idx[3];
+        for (idx[2] = 0; idx[2] < modes[2]; idx[2]++)
+          for (idx[1] = 0; idx[1] < modes[1]; idx[1]++)
+            for (idx[0] = 0; idx[0] < modes[0]; idx[0]++) {
+              if (idx[n] != i)
+                continue;
+              double w = X[idx[0] + modes[0] * (idx[1] + modes[1] * idx[2])];
+              for (dim_t m = 0; m < 3; m++)
+                if (m != n)
+                  w *= k.get_factor(m)(idx[m], c);
+              want += w;
+            }
+        worst = std::max(worst, std::fabs(G(i, c) - want));
+      }
+    EXPECT_LT(worst, 1e-12);
+    EXPECT_EQ(mp.flops, 2ull * X.get_n_elements() * 4);
+  }
+}
+
+int main(int argc, char **argv) {
+  set_threads(4);
+  ::testing::InitGoogleTest(&argc, argv);
+  return RUN_ALL_TESTS();
+}

@@ -5,4 +5,5 @@ cd "$(dirname "${BASH_SOURCE[0]}")/.."
 make -s -C cp-cals_b200
 make -s -C oracle
 [ -d /root/reference ] && [ ! -x oracle/_ref/cals_ref ] && oracle/build_ref.sh
+[ -d /root/reference ] && tools/build_ref_compat.sh >/dev/null
 exec /usr/local/graft/bin/gpurun "$@"
