@@ -328,8 +328,8 @@ def main():
                                    "%d forced ALS iterations per model per step" % ALS_ITERS,
                        "models_per_gpu": n_models, "sum_ranks": C, "als_iters_per_step": ALS_ITERS,
                        "parallelism": "model set sharded over %d GPU(s), tensor replicated" % world,
-                       "l2": "per-iteration working set (64 MB tensor read once per mode + 2 x 77 MB partial tiles) "
-                             "exceeds what stays in the 126 MB L2 between iterations; no explicit flush"},
+                       "l2": "inputs larger than L2: every ALS iteration streams both 64 MB device copies of the tensor "
+                             "(128 MB > 126 MB L2) plus ~15 MB of partial tiles per mode; no explicit flush"},
             "wall_ms_per_step": wall / steps * 1e3,
             "timing": "CUDA events on the engine's stream around the K steps (barrier + synchronize on both sides), "
                       "max over ranks",
