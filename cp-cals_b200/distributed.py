@@ -1,0 +1,135 @@
+"""Multi-GPU host logic of the B200 CP-CALS path: one process per GPU (torch.distributed), the tensor replicated, the
+model set -- or, for the jackknife, the leave-one-out sub-models -- sharded across ranks.
+
+Models are independent given X, so there is NO collective on the data path: every rank runs the single-GPU loop
+(cp_cals over its own Engine) on its shard; one all-gather of the packed results at the end gives every rank all
+fitted models (NCCL over NVLink on a GPU box; gloo in the CPU tests, which exercise exactly this file with a stand-in
+fit function).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+
+def shard_models(ranks: Sequence[int], n_parts: int) -> List[List[int]]:
+    """Deterministic split of a FIFO model list over n_parts shards: every model goes to the shard with the smallest
+    sum of ranks so far (ties: lowest shard index); inside a shard the queue order is kept.  Same rule as the C++
+    host layer (cals::detail::shard_models, cp-cals_b200/host/cals.cpp)."""
+    parts: List[List[int]] = [[] for _ in range(max(1, n_parts))]
+    load = [0] * len(parts)
+    for i, r in enumerate(ranks):
+        best = min(range(len(parts)), key=lambda p: (load[p], p))
+        parts[best].append(i)
+        load[best] += int(r)
+    return parts
+
+
+def shard_slabs(extent: int, n_parts: int, align: int = 2) -> List[tuple]:
+    """Cut [0, extent) into n_parts contiguous slabs whose inner boundaries are multiples of `align` (the engine reads
+    factor rows through TMA descriptors whose base must be 16-byte aligned => even row offsets)."""
+    cuts = [0]
+    for p in range(1, n_parts):
+        c = int(p * extent / n_parts / align + 0.5) * align
+        cuts.append(min(max(c, cuts[-1]), extent))
+    cuts.append(extent)
+    return [(cuts[p], cuts[p + 1]) for p in range(n_parts)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+_STATS = 5  # iters, error, fit, old_fit, chol_info
+
+
+def pack_models(models) -> np.ndarray:
+    """Flatten fitted models (objects with .factors .lam .iters .error .fit .old_fit .chol_info) into one float64 vector."""
+    chunks = []
+    for m in models:
+        chunks.append(np.array([m.iters, m.error, m.fit, m.old_fit, getattr(m, "chol_info", 0)], dtype=np.float64))
+        chunks.append(np.asarray(m.lam, dtype=np.float64).ravel())
+        for F in m.factors:
+            chunks.append(np.asarray(F, dtype=np.float64).ravel(order="F"))
+    return np.concatenate(chunks) if chunks else np.zeros(0)
+
+
+def unpack_models(buf: np.ndarray, models) -> None:
+    """Inverse of pack_models: overwrite `models` (whose factor shapes are known) in place."""
+    off = 0
+    for m in models:
+        st = buf[off:off + _STATS]
+        off += _STATS
+        m.iters, m.error, m.fit, m.old_fit = int(st[0]), float(st[1]), float(st[2]), float(st[3])
+        m.chol_info = int(st[4])
+        R = m.factors[0].shape[1]
+        m.lam = buf[off:off + R].copy()
+        off += R
+        for n, F in enumerate(m.factors):
+            cnt = F.shape[0] * R
+            m.factors[n] = np.asfortranarray(buf[off:off + cnt].reshape(F.shape, order="F").copy())
+            off += cnt
+    assert off == buf.size, (off, buf.size)
+
+
+def packed_size(models) -> int:
+    return sum(_STATS + m.factors[0].shape[1] * (1 + sum(F.shape[0] for F in m.factors)) for m in models)
+
+
+def all_gather_packed(local: np.ndarray, sizes: Sequence[int], group=None, device=None) -> List[np.ndarray]:
+    """All-gather of per-rank float64 vectors of known (different) sizes.  Buffers are padded to the largest size so one
+    collective suffices; on NCCL the staging tensors live on `device`."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    cap = max(max(sizes), 1)
+    send = torch.zeros(cap, dtype=torch.float64, device=device)
+    if local.size:
+        send[:local.size] = torch.from_numpy(local).to(send.device)
+    recv = [torch.empty(cap, dtype=torch.float64, device=device) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    return [r[:n].cpu().numpy() for r, n in zip(recv, sizes)]
+
+
+def cp_cals_sharded(X: np.ndarray, ktensors, params, *, fit_fn: Optional[Callable] = None, group=None,
+                    gather_device=None, gather: bool = True, **kw):
+    """cals::cp_cals with the model set sharded over the ranks of `group` (default: the world).
+
+    Every rank passes the SAME `ktensors` list (same initial values).  Rank r fits shard r of shard_models() on its own
+    GPU; with gather=True every rank ends up with all fitted models, as if it had fitted them itself.  Returns
+    (report_of_this_rank, indices_of_this_rank's_shard).  `fit_fn(X, kts, params, **kw)` defaults to this package's
+    cp_cals (the CUDA path, no fallback; pass device=<CUDA ordinal> through **kw); the CPU tests pass a stand-in to
+    exercise the host logic over gloo.  `gather_device`: torch device of the all-gather staging buffers (a CUDA device
+    for NCCL, None for gloo).
+    """
+    import torch.distributed as dist
+    if fit_fn is None:
+        from . import cp_cals as fit_fn  # noqa: N813
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    parts = shard_models([k.rank for k in ktensors], world)
+    mine = [ktensors[i] for i in parts[rank]]
+    rep = fit_fn(X, mine, params, **kw) if mine else None
+    if gather and world > 1:
+        sizes = [packed_size([ktensors[i] for i in p]) for p in parts]
+        bufs = all_gather_packed(pack_models(mine), sizes, group=group, device=gather_device)
+        for r, p in enumerate(parts):
+            if r != rank:
+                unpack_models(bufs[r], [ktensors[i] for i in p])
+    return rep, parts[rank]
+
+
+def jk_cp_cals_sharded(X: np.ndarray, ktensors, params, *, fit_fn: Optional[Callable] = None, group=None,
+                       gather_device=None, **kw):
+    """cals::jk_cp_cals (reference src/cals.cpp:397-446, without the LSAP column matching) with the leave-one-out
+    sub-models -- not the base models -- sharded across ranks.  Returns (report_of_this_rank, results[b][i])."""
+    from . import generate_jk_ktensors
+    bases = [kt.copy().denormalize().normalize() for kt in ktensors]
+    groups = [generate_jk_ktensors(b) for b in bases]
+    flat = [m for g in groups for m in g]
+    rep, _ = cp_cals_sharded(X, flat, params, fit_fn=fit_fn, group=group, gather_device=gather_device, gather=True,
+                             **kw)
+    for m in flat:
+        m.set_jk_fiber(0.0)
+        m.denormalize()
+        m.normalize()
+        m.set_jk_fiber(float("nan"))
+    return rep, groups

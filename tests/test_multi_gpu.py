@@ -1,0 +1,162 @@
+"""N > 1 host logic on the CPU: world_size-2 gloo process groups exercise cp-cals_b200/distributed.py
+(sharding plan, packing, the all-gather of results, jackknife sub-model sharding) with the oracle standing in for the
+per-rank CUDA loop.  The -m gpu variant runs the real engine on as many GPUs as the box has."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle_fit(X, kts, params, **kw):
+    """Stand-in for cp_cals on one rank: the CPU oracle (test infrastructure) writing results back into the Ktensors."""
+    import caseio
+    import oracle
+    ms = [caseio.Model(factors=[F.copy() for F in k.factors], jk_mode=k.jk_mode, jk_fiber=k.jk_fiber) for k in kts]
+    res = oracle.cp_cals(X, ms, max_iter=params.max_iterations, tol=params.tol, buffer_size=params.buffer_size,
+                         force_max_iter=params.force_max_iter)
+    for k, r in zip(kts, res.models):
+        k.factors, k.lam, k.iters, k.error, k.fit, k.old_fit = r.factors, r.lam, r.iters, r.error, r.fit, r.old_fit
+    return res
+
+
+def _case():
+    rng = np.random.default_rng(42)
+    modes = (9, 8, 7)
+    X = rng.uniform(-1, 1, size=modes)
+    ranks = [3, 1, 4, 1, 5, 2, 6, 2]
+    import caseio
+    return X, modes, ranks, caseio.random_models(rng, modes, ranks)
+
+
+def _worker(rank, world, port, backend, use_engine, out_dir):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import torch.distributed as dist
+    from conftest import load_package
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    device = None
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        device = torch.device("cuda", rank)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    try:
+        pkg = load_package()
+        import importlib
+        d = importlib.import_module("cp_cals_b200.distributed")
+        X, modes, ranks, ms = _case()
+        kts = [pkg.Ktensor([F.copy() for F in m.factors]) for m in ms]
+        params = pkg.CalsParams(max_iterations=6, buffer_size=9, force_max_iter=True)
+        kw = dict(device=rank, gather_device=device) if use_engine else dict(fit_fn=_oracle_fit)
+        rep, mine = d.cp_cals_sharded(X, kts, params, **kw)
+        np.savez(os.path.join(out_dir, "cals_rank%d.npz" % rank), mine=np.array(mine),
+                 **{"m%d_f%d" % (i, n): F for i, k in enumerate(kts) for n, F in enumerate(k.factors)},
+                 **{"m%d_lam" % i: k.lam for i, k in enumerate(kts)},
+                 **{"m%d_st" % i: np.array([k.iters, k.error, k.fit]) for i, k in enumerate(kts)})
+        # jackknife: the leave-one-out sub-models are what is sharded
+        bases = [pkg.Ktensor([F.copy() for F in m.factors], m.lam.copy()) for m in ms[:2]]
+        rep, groups = d.jk_cp_cals_sharded(X, bases, params, **kw)
+        np.savez(os.path.join(out_dir, "jk_rank%d.npz" % rank),
+                 **{"b%d_i%d_f%d" % (b, i, n): F for b, g in enumerate(groups) for i, k in enumerate(g)
+                    for n, F in enumerate(k.factors)})
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn(world, backend, use_engine, tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, backend, use_engine, str(tmp_path)), nprocs=world, join=True)
+
+
+def _check_outputs(tmp_path, world, rtol):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import caseio
+    import oracle
+    X, modes, ranks, ms = _case()
+    outs = [np.load(os.path.join(tmp_path, "cals_rank%d.npz" % r)) for r in range(world)]
+    # the shards partition the model set
+    all_mine = sorted(int(i) for o in outs for i in o["mine"])
+    assert all_mine == list(range(len(ranks)))
+    # every rank holds every fitted model, identical across ranks, and equal to fitting each shard alone
+    from conftest import load_package
+    d = __import__("importlib").import_module("cp_cals_b200.distributed") if load_package() else None
+    parts = d.shard_models(ranks, world)
+    for r, p in enumerate(parts):
+        assert sorted(int(i) for i in outs[r]["mine"]) == p
+        want = oracle.cp_cals(X, [ms[i] for i in p], max_iter=6, buffer_size=9, force_max_iter=True)
+        for i, w in zip(p, want.models):
+            for o in outs:
+                for n in range(len(modes)):
+                    a = o["m%d_f%d" % (i, n)]
+                    assert np.linalg.norm(a - w.factors[n]) <= rtol * np.linalg.norm(w.factors[n])
+                assert np.linalg.norm(o["m%d_lam" % i] - w.lam) <= rtol * np.linalg.norm(w.lam)
+                st = o["m%d_st" % i]
+                assert int(st[0]) == w.iters and abs(st[2] - w.fit) <= rtol
+    jk = [np.load(os.path.join(tmp_path, "jk_rank%d.npz" % r)) for r in range(world)]
+    for k in jk[0].files:
+        for o in jk[1:]:
+            assert np.array_equal(jk[0][k], o[k], equal_nan=True)
+    assert len(jk[0].files) == 2 * modes[0] * len(modes)
+
+
+def test_shard_models_plan(pkg):
+    import importlib
+    d = importlib.import_module("cp_cals_b200.distributed")
+    ranks = [r for r in range(1, 21) for _ in range(10)]
+    for world in (1, 2, 4, 8):
+        parts = d.shard_models(ranks, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(ranks)))
+        assert all(p == sorted(p) for p in parts)  # FIFO order inside a shard
+        loads = [sum(ranks[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(ranks)
+    assert d.shard_slabs(1000, 8) == [(0, 126), (126, 250), (250, 376), (376, 500), (500, 626), (626, 750), (750, 876),
+                                      (876, 1000)]
+    assert d.shard_slabs(7, 3) == [(0, 2), (2, 4), (4, 7)]
+    assert all(lo % 2 == 0 for lo, _ in d.shard_slabs(299, 8))
+
+
+def test_pack_unpack_roundtrip(pkg):
+    import importlib
+    d = importlib.import_module("cp_cals_b200.distributed")
+    rng = np.random.default_rng(0)
+    ms = [pkg.Ktensor([np.asfortranarray(rng.uniform(-1, 1, size=(i, r))) for i in (5, 4, 3)], rng.uniform(size=r))
+          for r in (2, 1, 3)]
+    for i, m in enumerate(ms):
+        m.iters, m.error, m.fit, m.old_fit, m.chol_info = 3 + i, 0.5 * i, 0.9, 0.8, i
+    buf = d.pack_models(ms)
+    assert buf.size == d.packed_size(ms)
+    blank = [pkg.Ktensor([np.zeros_like(F) for F in m.factors]) for m in ms]
+    d.unpack_models(buf, blank)
+    for a, b in zip(ms, blank):
+        assert all(np.array_equal(x, y) for x, y in zip(a.factors, b.factors)) and np.array_equal(a.lam, b.lam)
+        assert (a.iters, a.error, a.fit, a.old_fit, a.chol_info) == (b.iters, b.error, b.fit, b.old_fit, b.chol_info)
+
+
+def test_world2_gloo_sharded_cp_cals_and_jackknife(tmp_path):
+    _spawn(2, "gloo", False, tmp_path)
+    _check_outputs(str(tmp_path), 2, 1e-12)
+
+
+@pytest.mark.gpu
+def test_multi_gpu_nccl_sharded_cp_cals(tmp_path):
+    import torch
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    _spawn(world, "nccl", True, tmp_path)
+    _check_outputs(str(tmp_path), world, 1e-9)
