@@ -1,13 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 CP-CALS hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4] [--strong]
 
-Metric (BASELINE.json): concurrent-ALS iterations per second summed over all models ("model-iterations/s"), on
-BASELINE config 2: synthetic 200x200x200 FP64 tensor, 200 concurrent models (ranks 1..20 x 10), buffer = sum of ranks,
-forced iteration count.  One "step" = one complete cals::cp_cals pass: all models x ALS_ITERS ALS iterations.
+Metric (BASELINE.json): concurrent-ALS iterations per second summed over all models ("model-iterations/s").  The
+default workload is BASELINE config 2 (the largest configuration the metric is quoted on that fits one GPU): synthetic
+200x200x200 FP64 tensor, 200 concurrent models (ranks 1..20 x 10), buffer = sum of ranks, forced iteration count.
+One "step" = one complete cals::cp_cals pass: all models x ALS_ITERS ALS iterations.
 
-  value    : whole-job throughput with the tensor and the initial models already resident in HBM (cals_b200_rerun)
+  value    : whole-job throughput with the tensor and the initial models already resident in HBM (cals_b200_rerun),
+             timed with CUDA events on the engine's stream, max over ranks
   e2e      : same metric through the public API (cp_cals over HOST buffers in pinned memory): H2D of X and of the
              initial models, the loop, and D2H of every fitted model inside the timed region
   roofline : the MTTKRP kernel (dominant), algorithmic 2*nX*C flop per launch / CUDA-event time per launch, against the
@@ -15,8 +17,9 @@ forced iteration count.  One "step" = one complete cals::cp_cals pass: all model
              entry)
   cpu_baseline : the UNMODIFIED reference (oracle/_ref) timed on the box's host cores on a bounded sample
 
-N > 1 (torchrun): the model set is the unit of sharding -- X is replicated, every rank fits its own 200 models, no
-collective on the data path ("scaling": "weak").
+N > 1 (torchrun): the model set is the unit of sharding -- X is replicated, no collective on the data path.  Default is
+weak scaling (every rank fits its own full model set); --strong shards ONE model set over the ranks.
+Other configs (--config 1, 3, 4) are measurement aids for DESIGN.md, not the headline.
 """
 import argparse
 import json
@@ -31,12 +34,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-MODES = (200, 200, 200)
-RANKS = [r for r in range(1, 21) for _ in range(10)]
-ALS_ITERS = 10        # ALS iterations per model per step (forced)
-REF_SAMPLE_ITERS = 2  # ALS iterations per model in one reference-arm step (bounded sample)
 METRIC = "concurrent-ALS iters/sec (all models)"
 UNIT = "model-iterations/s"
+
+# BASELINE.json configs.  als_iters: forced ALS iterations per model per step; ref_iters: per reference-arm step.
+CONFIGS = {
+    1: dict(name="config 1: 100x100x100 tensor, 40 models (ranks 1..10 x4), buffer 220", modes=(100, 100, 100),
+            ranks=[r for r in range(1, 11) for _ in range(4)], als_iters=50, ref_iters=20, jk=False),
+    2: dict(name="config 2: 200x200x200 tensor, 200 models (ranks 1..20 x10), buffer 2100", modes=(200, 200, 200),
+            ranks=[r for r in range(1, 21) for _ in range(10)], als_iters=10, ref_iters=2, jk=False),
+    3: dict(name="config 3: jackknife on a 299x301x41 tensor (fluorescence_cancer_UD shape, synthetic), all 299 "
+                 "leave-one-out sub-models of base models of ranks 3,5,7,9", modes=(299, 301, 41),
+            ranks=[r for r in (3, 5, 7, 9) for _ in range(299)], als_iters=10, ref_iters=1, jk=True),
+    4: dict(name="config 4: 80x80x80x80 tensor, 150 models (ranks 1..30 x5), buffer 2325", modes=(80, 80, 80, 80),
+            ranks=[r for r in range(1, 31) for _ in range(5)], als_iters=4, ref_iters=1, jk=False),
+}
 
 
 def load_pkg():
@@ -44,20 +56,29 @@ def load_pkg():
     return load_package()
 
 
-def workload(seed):
+def workload(cfg, seed):
     """Synthetic inputs as the reference driver makes them (src/examples/driver.cpp:133-153): X uniform(-1,1), models
-    uniform(-1,1) then Ktensor::normalize().  X is the same on every rank (replicated); models differ per rank."""
+    uniform(-1,1) then Ktensor::normalize().  X is the same on every rank (replicated); models differ with `seed`.
+    Jackknife config: sub-model i of a base model is that model flagged "leave mode-0 sample i out" (the reference
+    derives them from fitted base models; for throughput the starting values do not matter)."""
+    modes = cfg["modes"]
     rng = np.random.default_rng(1234)
-    X = np.asfortranarray(rng.uniform(-1.0, 1.0, size=MODES))
+    X = np.asfortranarray(rng.uniform(-1.0, 1.0, size=modes))
     mrng = np.random.default_rng(1000 + seed)
-    models = []
-    for r in RANKS:
-        fs = []
-        for i in MODES:
-            F = mrng.uniform(-1.0, 1.0, size=(i, r))
-            fs.append(np.asfortranarray(F / np.linalg.norm(F, axis=0)))
+    models, jk = [], []
+    base = {}
+    for idx, r in enumerate(cfg["ranks"]):
+        if cfg["jk"] and r in base:
+            fs = base[r]
+        else:
+            fs = []
+            for i in modes:
+                F = mrng.uniform(-1.0, 1.0, size=(i, r))
+                fs.append(np.asfortranarray(F / np.linalg.norm(F, axis=0)))
+            base[r] = fs
         models.append(fs)
-    return X, models
+        jk.append((0, idx % modes[0]) if cfg["jk"] else (-1, 0))
+    return X, models, jk
 
 
 class ClockSampler:
@@ -121,50 +142,54 @@ def fp64_peak():
         return 37.0, "fallback (no profiles/fp64_peak_r01.json)"
 
 
-def run_reference_sample(X, models, iters, threads):
+def run_reference_sample(X, models, jk, iters, threads):
     import caseio  # oracle/ (test infrastructure): allowed here as the CPU baseline / reference arm only
-    ms = [caseio.Model(factors=fs) for fs in models]
+    ms = [caseio.Model(factors=fs, jk_mode=j[0], jk_fiber=j[1]) for fs, j in zip(models, jk)]
     res = caseio.run_reference(X, ms, max_iter=iters, force_max_iter=True, threads=threads,
                                buffer_size=sum(m.rank for m in ms))
     return res.seconds
 
 
-def cpu_baseline(X, models, iters=REF_SAMPLE_ITERS):
+def cpu_baseline(cfg, X, models, jk):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import caseio
     if not caseio.ref_available():
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+    iters = cfg["ref_iters"]
     ncpu = os.cpu_count() or 1
     best = None
     for th in sorted({1, ncpu}):
-        sec = run_reference_sample(X, models, iters, th)
+        sec = run_reference_sample(X, models, jk, iters, th)
         v = len(models) * iters / sec
         if best is None or v > best[0]:
             best = (v, th, sec)
     return {"value": best[0], "unit": UNIT, "cores": best[1], "kind": "reference",
-            "sample": "unmodified reference cp_cals (OpenBLAS), full config-2 model set, %d forced ALS iterations, "
-                      "%.2f s of cp_cals time; better of 1 and %d threads (OMP_WAIT_POLICY=passive)" % (iters, best[2], ncpu)}
+            "sample": "unmodified reference cp_cals (OpenBLAS), full model set of the workload, %d forced ALS "
+                      "iterations, %.2f s of cp_cals time; better of 1 and %d threads (OMP_WAIT_POLICY=passive)"
+                      % (iters, best[2], ncpu)}
 
 
-def reference_arm(args, rank, world):
+def reference_arm(args, cfg, rank):
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    X, models = workload(0)
+    X, models, jk = workload(cfg, 0)
     ncpu = os.cpu_count() or 1
-    for _ in range(args.warmup if args.warmup is not None else 1):
-        run_reference_sample(X, models, 1, ncpu)
+    warm = args.warmup if args.warmup is not None else 1
+    for _ in range(warm):
+        run_reference_sample(X, models, jk, 1, ncpu)
     steps = args.steps if args.steps is not None else 3
-    secs = [run_reference_sample(X, models, REF_SAMPLE_ITERS, ncpu) for _ in range(steps)]
+    it = cfg["ref_iters"]
+    secs = [run_reference_sample(X, models, jk, it, ncpu) for _ in range(steps)]
     t = float(np.mean(secs))
-    v = len(models) * REF_SAMPLE_ITERS / t
+    v = len(models) * it / t
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 0, "steps": steps,
-            "warmup": args.warmup if args.warmup is not None else 1, "ms_per_step": t * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config 2: 200x200x200, 200 models ranks 1..20 x10, buffer 2100",
-                       "als_iters_per_step": REF_SAMPLE_ITERS, "l2": "inputs larger than L2"},
+            "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "als_iters_per_step": it, "l2": "inputs larger than L2"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": ncpu, "kind": "reference",
-                             "sample": "each step = %d forced ALS iterations of the full model set" % REF_SAMPLE_ITERS},
+                             "sample": "each step = %d forced ALS iterations of the full model set through the "
+                                       "unmodified reference's cp_cals, %d threads" % (it, ncpu)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -175,19 +200,23 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--strong", action="store_true", help="N > 1: shard ONE model set over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        reference_arm(args, rank, world)
+        reference_arm(args, cfg, rank)
         return
 
     steps = args.steps if args.steps is not None else 10
     warmup = max(3, args.warmup if args.warmup is not None else 3)
+    als_iters = cfg["als_iters"]
 
     import torch
     if not torch.cuda.is_available():
@@ -199,10 +228,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     pkg = load_pkg()
-    X, models = workload(rank)
+    import importlib
+    dmod = importlib.import_module("cp_cals_b200.distributed")
+    X, models, jk = workload(cfg, 0 if args.strong else rank)
+    total_models = len(models) if args.strong else world * len(models)
+    if args.strong and world > 1:
+        mine = dmod.shard_models([fs[0].shape[1] for fs in models], world)[rank]
+        models, jk = [models[i] for i in mine], [jk[i] for i in mine]
     nX = X.size
-    C = sum(RANKS)
-    n_models = len(RANKS)
+    C = sum(fs[0].shape[1] for fs in models)
+    n_models = len(models)
 
     def barrier():
         if dist is not None:
@@ -218,10 +253,10 @@ def main():
 
     eng = pkg.Engine(local_rank)
     eng.set_tensor(X)
-    eng.configure(C, ALS_ITERS, 1e-7, force_max_iter=True)
+    eng.configure(C, als_iters, 1e-7, force_max_iter=True)
     eng.clear_models()
-    for fs in models:
-        eng.enqueue(fs)
+    for fs, j in zip(models, jk):
+        eng.enqueue(fs, j[0], j[1])
     eng.run()  # uploads + first pass (untimed)
     # CUDA events are recorded on the stream the engine launches on (torch's current stream would see nothing)
     es = torch.cuda.ExternalStream(eng.stream_handle(), device=torch.device("cuda", local_rank))
@@ -246,10 +281,10 @@ def main():
     ev_ms, wall, reps = timed(eng.rerun, steps)
     clocks = sampler.stop()
     launches = sum(r.kernel_launches for r in reps)
-    assert all(r.iter == ALS_ITERS and r.n_ktensors == n_models for r in reps)
+    assert all(r.iter == als_iters and r.n_ktensors == n_models for r in reps)
     ev_ms = max_over_ranks(ev_ms)       # CUDA events on the engine stream around the K steps, max over ranks
     wall = max_over_ranks(wall)         # host clock around the same region (reported beside it)
-    value = world * n_models * ALS_ITERS * steps / (ev_ms * 1e-3)
+    value = total_models * als_iters * steps / (ev_ms * 1e-3)
 
     # ---------------- roofline of the dominant kernel (extra passes with per-kernel CUDA events) ----------------
     eng.set_timing(1)
@@ -264,11 +299,12 @@ def main():
     ach = flops_per_launch / (mt_ms / mt_launches * 1e-3) / 1e12
     peak, peak_src = fp64_peak()
     traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "mttkrp_traffic_r01.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    if args.config == 2 and world == 1:
+        try:
+            with open(os.path.join(ROOT, "profiles", "mttkrp_traffic_r01.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
     roofline = {"bound": "tensor", "kernel": "mttkrp_dmma_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "mttkrp_ms_per_launch": mt_ms / mt_launches, "flops_per_launch": flops_per_launch,
@@ -292,12 +328,12 @@ def main():
             keep.append(t)
             row.append(v)
         pinned_models.append(row)
-    params = pkg.CalsParams(max_iterations=ALS_ITERS, buffer_size=C, force_max_iter=True)
+    params = pkg.CalsParams(max_iterations=als_iters, buffer_size=C, force_max_iter=True)
     h2d = X.nbytes + sum(F.nbytes for fs in models for F in fs)
     d2h = sum(F.nbytes for fs in models for F in fs) + 8 * C + n_models * 40
 
     def e2e_step():
-        kts = [pkg.Ktensor(list(fs)) for fs in pinned_models]
+        kts = [pkg.Ktensor(list(fs), None, j[0], j[1]) for fs, j in zip(pinned_models, jk)]
         rep = pkg.cp_cals(Xp, kts, params, engine=eng)
         return rep, kts
 
@@ -310,26 +346,29 @@ def main():
     # the end-to-end step includes host work (queue packing, result unpacking) that no CUDA event sees once the
     # stream is idle, so the slower of the two clocks is the honest one
     e2e_t = max(e2e_ms * 1e-3, e2e_wall)
-    e2e_value = world * n_models * ALS_ITERS * e2e_steps / e2e_t
+    e2e_value = total_models * als_iters * e2e_steps / e2e_t
     fit_checksum = float(np.mean([k.fit for k in kts]))
 
     if rank == 0:
         cb = None
         if not args.no_cpu_baseline and world == 1:
             try:
-                cb = cpu_baseline(X, models)
+                cb = cpu_baseline(cfg, X, models, jk)
             except Exception as e:  # the baseline is reported, never allowed to break the bench line
                 cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config 2: 200x200x200 tensor, 200 models (ranks 1..20 x10), buffer 2100, "
-                                   "%d forced ALS iterations per model per step" % ALS_ITERS,
-                       "models_per_gpu": n_models, "sum_ranks": C, "als_iters_per_step": ALS_ITERS,
-                       "parallelism": "model set sharded over %d GPU(s), tensor replicated" % world,
-                       "l2": "inputs larger than L2: every ALS iteration streams both 64 MB device copies of the tensor "
-                             "(128 MB > 126 MB L2) plus ~15 MB of partial tiles per mode; no explicit flush"},
+            "ms_per_step": ev_ms / steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s, %d forced ALS iterations per model per step" % (cfg["name"], als_iters),
+                       "models_per_gpu": n_models, "sum_ranks_per_gpu": C, "als_iters_per_step": als_iters,
+                       "parallelism": "model set sharded over %d GPU(s) (%s), tensor replicated, no data-path "
+                                      "collective" % (world, "one set split" if args.strong else "one full set per GPU"),
+                       "l2": ("inputs larger than L2: every ALS iteration streams both device copies of the tensor "
+                              "(2 x %.0f MB) plus the partial-tile workspace; no explicit flush" % (nX * 8 / 1e6))
+                       if 2 * nX * 8 > 126e6 else
+                       ("working set (2 x %.0f MB tensor copies) fits the 126 MB L2 -- that is this workload's "
+                        "steady state inside cp_cals, not a cache artefact of the timing loop" % (nX * 8 / 1e6))},
             "wall_ms_per_step": wall / steps * 1e3,
             "timing": "CUDA events on the engine's stream around the K steps (barrier + synchronize on both sides), "
                       "max over ranks",

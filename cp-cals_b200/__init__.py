@@ -33,6 +33,8 @@ ABI_SYMBOLS = [
     "cals_b200_fetch_model", "cals_b200_fetch_all", "cals_b200_tensor_norm", "cals_b200_jk_norms",
     "cals_b200_mttkrp", "cals_b200_device_info", "cals_b200_version", "cals_b200_fetch_iteration_cols",
     "cals_b200_host_alloc", "cals_b200_host_free", "cals_b200_stream",
+    "cals_b200_comm_alloc", "cals_b200_comm_local_block", "cals_b200_comm_connect", "cals_b200_set_tensor_slab",
+    "cals_b200_set_tensor_norm",
 ]
 
 
@@ -94,6 +96,11 @@ def lib():
     L.cals_b200_host_alloc.restype = vp
     L.cals_b200_host_free.argtypes = [vp]
     L.cals_b200_stream.argtypes = [vp, C.POINTER(vp)]
+    L.cals_b200_comm_alloc.argtypes = [vp, i, i, u64, vp]
+    L.cals_b200_comm_local_block.argtypes = [vp, C.POINTER(vp)]
+    L.cals_b200_comm_connect.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(i)]
+    L.cals_b200_set_tensor_slab.argtypes = [vp, i, C.POINTER(u64), i, C.POINTER(u64), vp]
+    L.cals_b200_set_tensor_norm.argtypes = [vp, dbl]
     _lib = L
     return L
 
@@ -238,6 +245,44 @@ class Engine:
         m = (C.c_uint64 * len(modes))(*modes)
         self._ck(self._L.cals_b200_set_tensor_dev(self._ctx, len(modes), m, C.c_void_p(dev_ptr)))
         self.modes = tuple(modes)
+
+    # -- tensor sliced over several GPUs (BASELINE config 5) ---------------------------------------------------------
+    def comm_alloc(self, rank: int, world: int, capacity_doubles: int) -> bytes:
+        """Allocate the exchange block; returns its 64-byte CUDA IPC handle."""
+        h = C.create_string_buffer(64)
+        self._ck(self._L.cals_b200_comm_alloc(self._ctx, rank, world, capacity_doubles, h))
+        self.comm_rank, self.comm_world = rank, world
+        return h.raw
+
+    def comm_local_block(self) -> int:
+        out = C.c_void_p()
+        self._ck(self._L.cals_b200_comm_local_block(self._ctx, C.byref(out)))
+        return int(out.value)
+
+    def comm_connect_ipc(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.comm_world
+        self._ck(self._L.cals_b200_comm_connect(self._ctx, blob, None, None))
+
+    def comm_connect_ptr(self, blocks: Sequence[int], devices: Sequence[int]):
+        bl = (C.c_void_p * len(blocks))(*blocks)
+        dv = (C.c_int * len(devices))(*devices)
+        self._ck(self._L.cals_b200_comm_connect(self._ctx, None, bl, dv))
+
+    def set_tensor_slab(self, modes: Sequence[int], slice_mode: int, cuts: Sequence[int], slab: np.ndarray):
+        """slab: this rank's part X[..., cuts[rank]:cuts[rank+1], ...] along slice_mode (dense)."""
+        Sf = np.asfortranarray(slab, dtype=np.float64)
+        want = tuple((cuts[self.comm_rank + 1] - cuts[self.comm_rank]) if n == slice_mode else m
+                     for n, m in enumerate(modes))
+        if tuple(Sf.shape) != want:
+            raise ValueError("slab shape %s does not match %s" % (Sf.shape, want))
+        m = (C.c_uint64 * len(modes))(*modes)
+        cu = (C.c_uint64 * len(cuts))(*cuts)
+        self._ck(self._L.cals_b200_set_tensor_slab(self._ctx, len(modes), m, slice_mode, cu, Sf.ctypes.data))
+        self.modes = tuple(modes)
+
+    def set_tensor_norm(self, norm: float):
+        self._ck(self._L.cals_b200_set_tensor_norm(self._ctx, norm))
 
     def tensor_norm(self) -> float:
         out = C.c_double()

@@ -39,7 +39,7 @@ struct SchedState {
   int max_iter;
   int buffer_cols;
   int n_evict; // models flagged for eviction by the last fit step
-  int pad_;
+  int comm_error; // set by the exchange kernel when a peer GPU never arrived (slab mode)
   double tol;
   double x_norm;
   unsigned long long global_iter;

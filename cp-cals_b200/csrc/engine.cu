@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/cals_b200.h"
+#include "comm.cuh"
 #include "common.cuh"
 #include "mttkrp.cuh"
 #include "prep.cuh"
@@ -58,8 +59,13 @@ struct cals_b200_ctx {
   std::string err;
   PFN_encodeTiled encode = nullptr;
 
-  // tensor
+  // tensor.  geo.dims are the extents of the FACTORS (the whole problem); xd are the extents of the tensor held by this
+  // device: equal to geo.dims, except for the sliced mode in slab mode, where the device holds rows
+  // [roff, roff + xd) of that mode (BASELINE config 5).
   Geom geo{};
+  int xd[CALS_MAX_MODES] = {};
+  int roff[CALS_MAX_MODES] = {};
+  int slice_mode = -1;
   long long nX = 0;
   double *Xp = nullptr; // original order, pitch ldX0
   double *Xt = nullptr; // modes 0 and 1 swapped, pitch ldX1
@@ -108,6 +114,16 @@ struct cals_b200_ctx {
   std::vector<int> run_sig; // (dims, buffer_cols, ranks): allocations are reused while this does not change
   double *norm_partial = nullptr;
   size_t norm_partial_cap = 0;
+
+  // slab-mode exchange over peer memory (comm.cuh)
+  int comm_rank = 0, comm_world = 1;
+  void *xblock = nullptr;         // [flags | 2 x xcap doubles], one cudaMalloc so that one IPC handle covers it
+  size_t xcap = 0;                // doubles per exchange buffer
+  void *peer_block[CALS_MAX_PEERS] = {};
+  bool peer_is_ipc[CALS_MAX_PEERS] = {};
+  bool comm_connected = false;
+  int cuts[CALS_MAX_PEERS + 1] = {};
+  unsigned long long seq_base = 0;
 
   std::vector<cudaEvent_t> ev_pool;
   bool dmma_attr_done[16] = {};
@@ -205,17 +221,20 @@ int encode_map(cals_b200_ctx *c, CUtensorMap *map, void *base, int rank, const c
   return 0;
 }
 
-// Build per-mode geometry and TMA descriptors for a set of buffers.
+// Build per-mode geometry and TMA descriptors for a set of buffers.  Tensor extents come from c->xd (the slab held by
+// this device), factor pitches from c->geo; c->roff shifts every access to the sliced mode's factor.
 int build_mode_plans(cals_b200_ctx *c, Buffers &b) {
   const Geom &geo = c->geo;
+  const int *xd = c->xd;
   const int N = geo.n_modes;
   for (int n = 0; n < N; n++) {
     MttkrpGeom g{};
     g.mode = n;
-    g.In = geo.dims[n];
+    g.In = xd[n];
     g.p_mode = (n == 0) ? 1 : 0;
-    g.Ip = geo.dims[g.p_mode];
+    g.Ip = xd[g.p_mode];
     g.ldG = geo.ldF[n];
+    g.g_row_off = c->roff[n];
     for (int k = 0; k < N; k++)
       g.ldF[k] = geo.ldF[k];
     int no = 0;
@@ -224,15 +243,16 @@ int build_mode_plans(cals_b200_ctx *c, Buffers &b) {
       if (k == n || k == g.p_mode)
         continue;
       g.outer_mode[no] = k;
-      g.outer_dim[no] = geo.dims[k];
+      g.outer_dim[no] = xd[k];
+      g.outer_off[no] = c->roff[k];
       if (n != 0 && k < n) {
         g.outer_lmul[no] = (int)lmul;
         g.outer_umul[no] = 0;
-        lmul *= geo.dims[k];
+        lmul *= xd[k];
       } else {
         g.outer_lmul[no] = 0;
         g.outer_umul[no] = (int)umul;
-        umul *= geo.dims[k];
+        umul *= xd[k];
       }
       no++;
     }
@@ -259,36 +279,37 @@ int build_mode_plans(cals_b200_ctx *c, Buffers &b) {
     void *base;
     if (n == 0) {
       base = c->Xt;
-      dims[0] = geo.dims[1];
+      dims[0] = xd[1];
       dims[1] = 1;
-      dims[2] = geo.dims[0];
+      dims[2] = xd[0];
       dims[3] = (cuuint64_t)U;
       strides[0] = (cuuint64_t)c->ldX1 * 8;
       strides[1] = (cuuint64_t)c->ldX1 * 8;
-      strides[2] = (cuuint64_t)c->ldX1 * geo.dims[0] * 8;
+      strides[2] = (cuuint64_t)c->ldX1 * xd[0] * 8;
     } else {
       base = c->Xp;
-      dims[0] = geo.dims[0];
+      dims[0] = xd[0];
       dims[1] = (cuuint64_t)Lp;
-      dims[2] = geo.dims[n];
+      dims[2] = xd[n];
       dims[3] = (cuuint64_t)U;
       strides[0] = (cuuint64_t)c->ldX0 * 8;
       strides[1] = (cuuint64_t)c->ldX0 * Lp * 8;
-      strides[2] = (cuuint64_t)c->ldX0 * Lp * geo.dims[n] * 8;
+      strides[2] = (cuuint64_t)c->ldX0 * Lp * xd[n] * 8;
     }
     if (encode_map(c, &b.maps[n].X, base, 4, dims, strides, box))
       return 1;
     for (int cu = 0; cu < 2; cu++) {
+      // factor tiles: rows [roff, roff + xd) of the factor (roff is even, so the base stays 16-byte aligned)
       cuuint64_t d2[2] = {(cuuint64_t)g.Ip, (cuuint64_t)b.cols};
       cuuint64_t s2[1] = {(cuuint64_t)geo.ldF[g.p_mode] * 8};
       cuuint32_t bx[2] = {(cuuint32_t)KT, (cuuint32_t)TILE_N};
-      if (encode_map(c, &b.maps[n].B[cu], b.fac.buf[cu][g.p_mode], 2, d2, s2, bx))
+      if (encode_map(c, &b.maps[n].B[cu], b.fac.buf[cu][g.p_mode] + c->roff[g.p_mode], 2, d2, s2, bx))
         return 1;
       const int q = g.outer_mode[0];
-      cuuint64_t d3[2] = {(cuuint64_t)geo.dims[q], (cuuint64_t)b.cols};
+      cuuint64_t d3[2] = {(cuuint64_t)xd[q], (cuuint64_t)b.cols};
       cuuint64_t s3[1] = {(cuuint64_t)geo.ldF[q] * 8};
       cuuint32_t bw[2] = {(cuuint32_t)OC, (cuuint32_t)TILE_N};
-      if (encode_map(c, &b.maps[n].W[cu], b.fac.buf[cu][q], 2, d3, s3, bw))
+      if (encode_map(c, &b.maps[n].W[cu], b.fac.buf[cu][q] + c->roff[q], 2, d3, s3, bw))
         return 1;
     }
   }
@@ -327,7 +348,7 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
     tile_elems = std::max(tile_elems, (size_t)tile_m(b.wm[n]) * TILE_N);
     if (dev_alloc(c, &b.plans.plan[n], (size_t)plan_capacity(c->sm_count, pairs_max), b.allocs))
       return 1;
-    b.plans.In[n] = geo.dims[n];
+    b.plans.In[n] = c->xd[n];
     b.plans.WM[n] = b.wm[n];
     const long long tp = (long long)b.mg[n].P_tiles * b.mg[n].S * b.mg[n].QC;
     if (tp * pairs_max > 0x7fffffffLL)
@@ -340,8 +361,10 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
   return 0;
 }
 
+double *exchange_data(cals_b200_ctx *c) { return (double *)((char *)c->xblock + COMM_FLAG_BYTES); }
+
 template <int WM>
-int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override) {
+int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchange) {
   auto kern = mttkrp_dmma_kernel<WM, WN_FIXED>;
   if (!c->dmma_attr_done[WM]) {
     CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<WM>()));
@@ -352,22 +375,26 @@ int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override) {
                                                             C_override);
   const int cols = C_override > 0 ? C_override : b.cols;
   dim3 rg((cols + 31) / 32, (b.mg[n].In + 31) / 32);
-  mttkrp_reduce_kernel<8 * WM, TILE_N><<<rg, 256, 0, c->stream>>>(b.mg[n], c->d_st, b.plans.plan[n], b.ws, b.G, G,
-                                                                  C_override);
+  mttkrp_reduce_kernel<8 * WM, TILE_N><<<rg, 256, 0, c->stream>>>(
+      b.mg[n], c->d_st, b.plans.plan[n], b.ws, b.G, G, C_override, exchange ? exchange_data(c) : nullptr,
+      (unsigned long long)c->xcap, c->seq_base, c->geo.n_modes);
   return 0;
 }
 
-int launch_mttkrp(cals_b200_ctx *c, Buffers &b, int n, int C_override, int variant) {
+int launch_mttkrp(cals_b200_ctx *c, Buffers &b, int n, int C_override, int variant, bool exchange = false) {
   if (variant == CALS_B200_MTTKRP_NAIVE) {
+    if (exchange)
+      return fail(c, "the naive MTTKRP variant does not support a sliced tensor over several GPUs");
     NaiveGeom ng{};
     ng.n_modes = c->geo.n_modes;
     ng.mode = n;
     long long stride = 1;
     for (int k = 0; k < ng.n_modes; k++) {
-      ng.dims[k] = c->geo.dims[k];
+      ng.dims[k] = c->xd[k];
       ng.ldF[k] = c->geo.ldF[k];
+      ng.off[k] = c->roff[k];
       ng.xstride[k] = stride;
-      stride *= (k == 0) ? c->ldX0 : c->geo.dims[k];
+      stride *= (k == 0) ? c->ldX0 : c->xd[k];
     }
     ng.ldG = c->geo.ldF[n];
     const int cols = C_override > 0 ? C_override : b.cols;
@@ -378,15 +405,15 @@ int launch_mttkrp(cals_b200_ctx *c, Buffers &b, int n, int C_override, int varia
   }
   switch (b.wm[n]) {
   case 4:
-    return launch_dmma<4>(c, b, n, C_override);
+    return launch_dmma<4>(c, b, n, C_override, exchange);
   case 5:
-    return launch_dmma<5>(c, b, n, C_override);
+    return launch_dmma<5>(c, b, n, C_override, exchange);
   case 6:
-    return launch_dmma<6>(c, b, n, C_override);
+    return launch_dmma<6>(c, b, n, C_override, exchange);
   case 7:
-    return launch_dmma<7>(c, b, n, C_override);
+    return launch_dmma<7>(c, b, n, C_override, exchange);
   default:
-    return launch_dmma<8>(c, b, n, C_override);
+    return launch_dmma<8>(c, b, n, C_override, exchange);
   }
 }
 
@@ -413,6 +440,22 @@ void release_run(cals_b200_ctx *c) {
   c->run_sig.clear();
 }
 
+void release_comm(cals_b200_ctx *c) {
+  for (int r = 0; r < CALS_MAX_PEERS; r++) {
+    if (c->peer_block[r] && c->peer_is_ipc[r])
+      cudaIpcCloseMemHandle(c->peer_block[r]);
+    c->peer_block[r] = nullptr;
+    c->peer_is_ipc[r] = false;
+  }
+  if (c->xblock)
+    cudaFree(c->xblock);
+  c->xblock = nullptr;
+  c->xcap = 0;
+  c->comm_connected = false;
+  c->comm_rank = 0;
+  c->comm_world = 1;
+}
+
 void release_tensor(cals_b200_ctx *c) {
   release_run(c);
   if (c->Xt && c->Xt != c->Xp)
@@ -425,27 +468,42 @@ void release_tensor(cals_b200_ctx *c) {
   c->have_tensor = false;
 }
 
-int install_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const double *src, bool src_on_device) {
+// `modes` are the extents of the whole problem.  slice_mode >= 0: `src` holds only the slab [lo, hi) of that mode
+// (dense, same layout, extent hi - lo along slice_mode); the factors keep their full extents.
+int install_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const double *src, bool src_on_device,
+                   int slice_mode = -1, long long lo = 0, long long hi = 0) {
   if (n_modes < 3 || n_modes > CALS_MAX_MODES)
     return fail(c, "n_modes must be in [3, %d], got %d", CALS_MAX_MODES, n_modes);
   for (int n = 0; n < n_modes; n++)
     if (modes[n] < 1 || modes[n] > (1u << 30))
       return fail(c, "mode %d has unsupported extent %llu", n, (unsigned long long)modes[n]);
+  if (slice_mode >= n_modes)
+    return fail(c, "slice_mode %d out of range", slice_mode);
+  if (slice_mode >= 0 && (lo < 0 || hi <= lo || hi > (long long)modes[slice_mode] || (lo & 1)))
+    return fail(c, "slab [%lld, %lld) of mode %d is empty, out of range or starts at an odd row", lo, hi, slice_mode);
+  int xd[CALS_MAX_MODES], roff[CALS_MAX_MODES];
+  for (int n = 0; n < n_modes; n++) {
+    xd[n] = (n == slice_mode) ? (int)(hi - lo) : (int)modes[n];
+    roff[n] = (n == slice_mode) ? (int)lo : 0;
+  }
   // same shape as the resident tensor: keep every allocation (and the TMA descriptors that point into them)
   bool same = c->have_tensor && c->geo.n_modes == n_modes;
   for (int n = 0; same && n < n_modes; n++)
-    same = c->geo.dims[n] == (int)modes[n];
+    same = c->geo.dims[n] == (int)modes[n] && c->xd[n] == xd[n] && c->roff[n] == roff[n];
   if (!same)
     release_tensor(c);
   long long nX = 1;
   for (int n = 0; n < n_modes; n++) {
     c->geo.dims[n] = (int)modes[n];
     c->geo.ldF[n] = round_up_int((int)modes[n], 2);
-    nX *= (long long)modes[n];
+    c->xd[n] = xd[n];
+    c->roff[n] = roff[n];
+    nX *= (long long)xd[n];
   }
   c->geo.n_modes = n_modes;
+  c->slice_mode = slice_mode;
   c->nX = nX;
-  const int I0 = c->geo.dims[0], I1 = c->geo.dims[1];
+  const int I0 = c->xd[0], I1 = c->xd[1];
   c->ldX0 = round_up_int(I0, 2);
   c->ldX1 = round_up_int(I1, 2);
   const long long rest0 = nX / I0, rest2 = nX / ((long long)I0 * I1);
@@ -516,8 +574,11 @@ int prepare_run(cals_b200_ctx *c) {
   std::vector<int> sig;
   sig.reserve((size_t)M + N + 2);
   sig.push_back(N);
-  for (int n = 0; n < N; n++)
+  for (int n = 0; n < N; n++) {
     sig.push_back(geo.dims[n]);
+    sig.push_back(c->xd[n]);
+    sig.push_back(c->roff[n]);
+  }
   sig.push_back(c->buffer_cols);
   for (int m = 0; m < M; m++)
     sig.push_back(c->hmodels[m].rank);
@@ -682,6 +743,33 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     }
   }
 
+  // slab mode over several GPUs: every MTTKRP is followed by the peer-memory exchange (comm.cuh)
+  const bool exchange = c->slice_mode >= 0 && c->comm_world > 1;
+  CommParams cp{};
+  size_t max_ld = 0;
+  for (int n = 0; n < N; n++)
+    max_ld = std::max<size_t>(max_ld, (size_t)geo.ldF[n]);
+  if (exchange) {
+    if (!c->comm_connected)
+      return fail(c, "the tensor is sliced over %d GPUs but the peers are not connected (cals_b200_comm_connect)",
+                  c->comm_world);
+    if (max_ld * (size_t)c->buffer_cols > c->xcap)
+      return fail(c, "exchange buffers hold %zu doubles, this run needs %zu (cals_b200_comm_alloc capacity)", c->xcap,
+                  max_ld * (size_t)c->buffer_cols);
+    cp.rank = c->comm_rank;
+    cp.world = c->comm_world;
+    cp.slice_mode = c->slice_mode;
+    for (int r = 0; r <= c->comm_world; r++)
+      cp.cuts[r] = c->cuts[r];
+    for (int r = 0; r < c->comm_world; r++) {
+      cp.peer_flags[r] = (unsigned long long *)c->peer_block[r];
+      cp.peer_x[r] = (const double *)((char *)c->peer_block[r] + COMM_FLAG_BYTES);
+    }
+    cp.cap = c->xcap;
+    cp.seq_base = c->seq_base;
+    cp.spin_limit = 40000000000ll; // ~20 s at 1.97 GHz: a peer that has not arrived by then is gone
+  }
+
   const int RA = 4; // host run-ahead in CALS iterations
   cudaEvent_t ring[RA];
   for (int i = 0; i < RA; i++)
@@ -703,8 +791,12 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
         timed.push_back({ev_next, 0});
         cudaEventRecord(get_event(c, ev_next), s);
       }
-      if (launch_mttkrp(c, b, n, 0, c->variant))
+      if (launch_mttkrp(c, b, n, 0, c->variant, exchange))
         return 1;
+      if (exchange) {
+        exchange_sum_kernel<<<c->sm_count * 2, 256, 0, s>>>(cp, c->d_st, b.G, n, N, geo.dims[n], geo.ldF[n]);
+        launches++;
+      }
       mttkrp_launches++;
       launches += (c->variant == CALS_B200_MTTKRP_NAIVE) ? 1 : 2;
       if (c->timing) {
@@ -736,6 +828,12 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   // scalars back
   CU_TRY(c, cudaMemcpy(&st, c->d_st, sizeof st, cudaMemcpyDeviceToHost));
   c->last_global_iter = st.global_iter;
+  if (exchange) {
+    c->seq_base += st.global_iter * (unsigned long long)N; // the next run's first exchange continues the sequence
+    if (st.comm_error)
+      return fail(c, "a peer GPU did not reach an exchange point within the time limit (rank %d of %d)", c->comm_rank,
+                  c->comm_world);
+  }
   if (rep) {
     memset(rep, 0, sizeof *rep);
     rep->iter = st.global_iter;
@@ -877,6 +975,7 @@ int cals_b200_destroy(cals_b200_ctx *c) {
     cudaFree(c->d_st);
   if (c->d_iter_cols)
     cudaFree(c->d_iter_cols);
+  release_comm(c);
   if (c->h_flags)
     cudaFreeHost(c->h_flags);
   for (auto &p : c->h_home)
@@ -907,6 +1006,108 @@ int cals_b200_set_tensor_dev(cals_b200_ctx *c, int n_modes, const uint64_t *mode
     return fail(c, "null argument");
   cudaSetDevice(c->device);
   return install_tensor(c, n_modes, modes, X_dev, true);
+}
+
+int cals_b200_set_tensor_slab(cals_b200_ctx *c, int n_modes, const uint64_t *modes, int slice_mode,
+                              const uint64_t *cuts, const double *host_slab) {
+  if (!c || !modes || !cuts || !host_slab)
+    return fail(c, "null argument");
+  cudaSetDevice(c->device);
+  if (slice_mode < 0 || slice_mode >= n_modes)
+    return fail(c, "slice_mode %d out of range", slice_mode);
+  const int W = c->comm_world;
+  if (cuts[0] != 0 || cuts[W] != modes[slice_mode])
+    return fail(c, "slab boundaries must run from 0 to the extent of mode %d", slice_mode);
+  for (int r = 0; r < W; r++)
+    if (cuts[r + 1] <= cuts[r] || (cuts[r] & 1))
+      return fail(c, "slab %d is empty or starts at an odd row", r);
+  for (int r = 0; r <= W; r++)
+    c->cuts[r] = (int)cuts[r];
+  return install_tensor(c, n_modes, modes, host_slab, false, slice_mode, (long long)cuts[c->comm_rank],
+                        (long long)cuts[c->comm_rank + 1]);
+}
+
+int cals_b200_set_tensor_norm(cals_b200_ctx *c, double norm) {
+  if (!c)
+    return 1;
+  if (!c->have_tensor)
+    return fail(c, "no tensor set");
+  if (!(norm > 0.0))
+    return fail(c, "the tensor norm must be positive");
+  c->x_norm = norm;
+  return 0;
+}
+
+int cals_b200_comm_alloc(cals_b200_ctx *c, int rank, int world, uint64_t capacity_doubles, void *ipc_handle_out) {
+  if (!c)
+    return 1;
+  if (world < 1 || world > CALS_MAX_PEERS || rank < 0 || rank >= world)
+    return fail(c, "rank %d / world %d out of range (at most %d GPUs)", rank, world, CALS_MAX_PEERS);
+  cudaSetDevice(c->device);
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  release_comm(c);
+  c->comm_rank = rank;
+  c->comm_world = world;
+  const size_t bytes = COMM_FLAG_BYTES + 2 * (size_t)capacity_doubles * 8;
+  CU_TRY(c, cudaMalloc(&c->xblock, bytes));
+  CU_TRY(c, cudaMemset(c->xblock, 0, bytes));
+  c->xcap = (size_t)capacity_doubles;
+  c->seq_base = 0;
+  c->peer_block[rank] = c->xblock;
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t h;
+    CU_TRY(c, cudaIpcGetMemHandle(&h, c->xblock));
+    static_assert(sizeof(h) == 64, "cals_b200.h documents 64-byte handles");
+    memcpy(ipc_handle_out, &h, sizeof h);
+  }
+  c->comm_connected = (world == 1);
+  return 0;
+}
+
+int cals_b200_comm_local_block(cals_b200_ctx *c, void **block_dev_out) {
+  if (!c || !block_dev_out)
+    return fail(c, "null argument");
+  if (!c->xblock)
+    return fail(c, "cals_b200_comm_alloc has not been called");
+  *block_dev_out = c->xblock;
+  return 0;
+}
+
+int cals_b200_comm_connect(cals_b200_ctx *c, const void *ipc_handles, void *const *peer_blocks_dev,
+                           const int *peer_devices) {
+  if (!c)
+    return 1;
+  if (!c->xblock)
+    return fail(c, "cals_b200_comm_alloc has not been called");
+  if (!ipc_handles && !(peer_blocks_dev && peer_devices))
+    return fail(c, "pass either the IPC handles of all ranks or their device pointers and device ordinals");
+  cudaSetDevice(c->device);
+  for (int r = 0; r < c->comm_world; r++) {
+    if (r == c->comm_rank)
+      continue;
+    if (ipc_handles) { // one process per GPU
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char *)ipc_handles + (size_t)r * sizeof h, sizeof h);
+      void *p = nullptr;
+      CU_TRY(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      c->peer_block[r] = p;
+      c->peer_is_ipc[r] = true;
+    } else { // several GPUs driven by one process
+      int can = 0;
+      CU_TRY(c, cudaDeviceCanAccessPeer(&can, c->device, peer_devices[r]));
+      if (!can)
+        return fail(c, "device %d cannot access device %d", c->device, peer_devices[r]);
+      cudaError_t e = cudaDeviceEnablePeerAccess(peer_devices[r], 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled)
+        cudaGetLastError();
+      else if (e != cudaSuccess)
+        return fail(c, "cudaDeviceEnablePeerAccess(%d): %s", peer_devices[r], cudaGetErrorString(e));
+      c->peer_block[r] = peer_blocks_dev[r];
+      c->peer_is_ipc[r] = false;
+    }
+  }
+  c->comm_connected = true;
+  return 0;
 }
 
 int cals_b200_configure(cals_b200_ctx *c, uint64_t buffer_cols, uint64_t max_iterations, double tol, unsigned flags) {
@@ -964,6 +1165,8 @@ int cals_b200_enqueue_model(cals_b200_ctx *c, uint64_t rank, const double *const
     return fail(c, "jk_mode %d out of range", jk_mode);
   if (jk_mode >= 0 && (jk_fiber < 0 || jk_fiber >= geo.dims[jk_mode]))
     return fail(c, "jk_fiber %lld out of range", (long long)jk_fiber);
+  if (jk_mode >= 0 && c->slice_mode >= 0)
+    return fail(c, "jackknife models are not supported on a sliced tensor (shard the sub-models instead)");
   HostModel hm;
   hm.rank = (int)rank;
   hm.jk_mode = jk_mode < 0 ? -1 : jk_mode;
@@ -1087,6 +1290,8 @@ int cals_b200_mttkrp(cals_b200_ctx *c, int mode, uint64_t cols, const double *co
     cudaEvent_t e0 = get_event(c, 0), e1 = get_event(c, 1);
     if (repeats < 1)
       repeats = 1;
+    if (c->slice_mode >= 0) // rows outside this device's slab are not produced: the hook returns them as zeros
+      cudaMemsetAsync(b.G, 0, (size_t)geo.ldF[mode] * cols * 8, c->stream);
     mttkrp_plan_kernel<<<1, 32, 0, c->stream>>>(b.plans, (int)cols);
     rc = launch_mttkrp(c, b, mode, (int)cols, variant); // warm-up + result
     cudaEventRecord(e0, c->stream);

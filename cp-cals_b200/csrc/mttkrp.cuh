@@ -58,6 +58,10 @@ struct MttkrpGeom {
   int m_tiles; // ceil(In / M_TILE)
   int ldG;
   int ldF[CALS_MAX_MODES];
+  // Slab mode (tensor sliced along one mode over several GPUs, BASELINE config 5): the tensor on this device covers
+  // rows [off, off + extent) of the sliced mode's factor.  Offsets are 0 everywhere else.
+  int outer_off[CALS_MAX_OUTER]; // row offset into the factor of every outer mode
+  int g_row_off;                 // row offset of this device's G rows (non-zero only when mode == sliced mode)
 };
 
 struct MttkrpMaps {
@@ -531,7 +535,7 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
         if (c < C)
           for (int k = 1; k < g.n_outer; k++) {
             const int md = g.outer_mode[k];
-            w *= __ldg(fac.buf[cur][md] + (size_t)c * g.ldF[md] + idx[k]);
+            w *= __ldg(fac.buf[cur][md] + (size_t)c * g.ldF[md] + idx[k] + g.outer_off[k]);
           }
         wslow[j] = w;
       }
@@ -573,11 +577,20 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
 // ------------------------------------------------------------------------------------------------------------------
 // Sum the partial tiles of every (m,n) pair in segment order and write G (In x C, column-major, ld = ldG).
 // One CTA per 32x32 patch of G; reads are coalesced along columns of the row-major tiles, writes along rows of G.
+//
+// Slab mode: xbuf != nullptr -> the sum is this device's PARTIAL result and goes to the exchange buffer
+// xbuf + ((seq_base + global_iter * n_modes + mode + 1) & 1) * xcap, from where comm.cuh's exchange kernel of every
+// rank collects it.
 template <int M_TILE, int N_TILE>
 __global__ void mttkrp_reduce_kernel(const MttkrpGeom g, const SchedState *__restrict__ st,
                                      const int *__restrict__ plan, const double *__restrict__ ws,
-                                     double *__restrict__ G, int grid_ctas, int C_override) {
+                                     double *__restrict__ G, int grid_ctas, int C_override, double *xbuf,
+                                     unsigned long long xcap, unsigned long long seq_base, int n_modes) {
   const int C = C_override > 0 ? C_override : st->C;
+  if (xbuf != nullptr) {
+    const unsigned long long seq = seq_base + st->global_iter * (unsigned long long)n_modes + g.mode + 1;
+    G = xbuf + (seq & 1ull) * xcap;
+  }
   const int c0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
   if (c0 >= C)
     return;
@@ -603,7 +616,7 @@ __global__ void mttkrp_reduce_kernel(const MttkrpGeom g, const SchedState *__res
   for (int cc = ty; cc < 32; cc += 8) {
     const int m = m0 + tx, c = c0 + cc;
     if (m < g.In && c < C)
-      G[(size_t)c * g.ldG + m] = t[tx][cc];
+      G[(size_t)c * g.ldG + m + g.g_row_off] = t[tx][cc];
   }
 }
 
@@ -616,6 +629,7 @@ struct NaiveGeom {
   int ldF[CALS_MAX_MODES];
   long long xstride[CALS_MAX_MODES]; // element strides of the padded device copy of X
   int ldG;
+  int off[CALS_MAX_MODES]; // slab mode: row offset into each factor (and into G for the output mode)
 };
 
 __global__ void mttkrp_naive_kernel(const NaiveGeom g, const SchedState *__restrict__ st, const double *__restrict__ X,
@@ -638,7 +652,7 @@ __global__ void mttkrp_naive_kernel(const NaiveGeom g, const SchedState *__restr
     for (int k = 0; k < g.n_modes; k++) {
       off += idx[k] * g.xstride[k];
       if (k != g.mode)
-        w *= fac.buf[cur][k][(size_t)c * g.ldF[k] + idx[k]];
+        w *= fac.buf[cur][k][(size_t)c * g.ldF[k] + idx[k] + g.off[k]];
     }
     sum += X[off] * w;
     int k = 0;
@@ -652,7 +666,7 @@ __global__ void mttkrp_naive_kernel(const NaiveGeom g, const SchedState *__restr
     if (k == g.n_modes)
       break;
   }
-  G[(size_t)c * g.ldG + i] = sum;
+  G[(size_t)c * g.ldG + i + g.off[g.mode]] = sum;
 }
 
 } // namespace calsb200

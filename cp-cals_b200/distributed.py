@@ -133,3 +133,67 @@ def jk_cp_cals_sharded(X: np.ndarray, ktensors, params, *, fit_fn: Optional[Call
         m.normalize()
         m.set_jk_fiber(float("nan"))
     return rep, groups
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def exchange_capacity(modes: Sequence[int], buffer_cols: int) -> int:
+    """Doubles per exchange buffer: the largest G matrix (pitch = extent rounded up to even) x buffer columns."""
+    return max((m + 1) // 2 * 2 for m in modes) * int(buffer_cols)
+
+
+def cp_cals_sliced(slab: np.ndarray, modes: Sequence[int], slice_mode: int, ktensors, params, *, engine=None,
+                   device: int = 0, group=None, timing: int = 0):
+    """cals::cp_cals for a tensor too large for one GPU (BASELINE config 5): X is cut into slabs along `slice_mode`
+    (shard_slabs), rank r holds `slab` = X[.., cuts[r]:cuts[r+1], ..] and ALL models; every MTTKRP is combined across
+    GPUs by the engine's own exchange kernel over NVLink peer memory (csrc/comm.cuh), the per-model updates run
+    replicated.  Every rank passes the same `ktensors` and ends up with the same fitted models (bit-identical).
+    torch.distributed is used only to pass the CUDA IPC handles and the slab norms around."""
+    import torch
+    import torch.distributed as dist
+    from . import CalsReport, Engine, _check_params
+    _check_params(params)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    cuts = [0] + [hi for _, hi in shard_slabs(modes[slice_mode], world)]
+    own = engine is None
+    eng = engine or Engine(device)
+    try:
+        buffer_cols = min(params.buffer_size, sum(k.rank for k in ktensors))
+        handle = eng.comm_alloc(rank, world, exchange_capacity(modes, buffer_cols))
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=group)
+            eng.comm_connect_ipc(handles)
+        eng.set_tensor_slab(modes, slice_mode, cuts, slab)
+        sq = torch.tensor([eng.tensor_norm() ** 2], dtype=torch.float64,
+                          device=torch.device("cuda", device) if world > 1 and dist.get_backend(group) == "nccl"
+                          else None)
+        if world > 1:
+            parts = [torch.zeros_like(sq) for _ in range(world)]
+            dist.all_gather(parts, sq, group=group)
+            total = sum(float(p.item()) for p in parts)  # rank order: the same value on every rank
+        else:
+            total = float(sq.item())
+        eng.set_tensor_norm(total ** 0.5)
+        eng.configure(buffer_cols, params.max_iterations, params.tol, params.force_max_iter, params.always_evict_first)
+        eng.set_timing(timing)
+        eng.clear_models()
+        for kt in ktensors:
+            eng.enqueue(kt.factors, kt.jk_mode, kt.jk_fiber)
+        if world > 1:
+            dist.barrier(group=group)  # every peer's exchange block is mapped before anyone starts to signal
+        rep = eng.run()
+        for i, kt in enumerate(ktensors):
+            fs, lam, st = eng.fetch(i)
+            kt.factors, kt.lam = fs, lam
+            kt.iters, kt.error, kt.fit, kt.old_fit, kt.chol_info = st.iters, st.error, st.fit, st.old_fit, st.chol_info
+        if world > 1:
+            dist.barrier(group=group)  # nobody frees its exchange block while a peer may still read it
+        return CalsReport(n_modes=len(modes), modes=tuple(modes), X_norm=rep.x_norm, iter=rep.iter,
+                          max_iter=params.max_iterations, buffer_size=params.buffer_size, n_ktensors=rep.n_ktensors,
+                          ktensor_comp_sum=rep.ktensor_comp_sum, tol=params.tol, total_time=rep.total_time,
+                          device_ms=rep.device_ms, mttkrp_ms=rep.mttkrp_ms, update_ms=rep.update_ms,
+                          mttkrp_launches=rep.mttkrp_launches, kernel_launches=rep.kernel_launches)
+    finally:
+        if own:
+            eng.close()

@@ -68,6 +68,30 @@ int cals_b200_set_tensor(cals_b200_ctx *ctx, int n_modes, const uint64_t *modes,
 /* Same with X already in device memory (dense, unpadded). */
 int cals_b200_set_tensor_dev(cals_b200_ctx *ctx, int n_modes, const uint64_t *modes, const double *X_dev);
 
+/* ---- tensor sliced along one mode over several GPUs (BASELINE config 5; no reference counterpart) ------------- */
+/* Every GPU holds the slab [cuts[rank], cuts[rank+1]) of mode `slice_mode` (host_slab: dense, same layout as X with
+ * that extent along slice_mode) and ALL factor columns; every MTTKRP is followed by an exchange over NVLink peer
+ * memory (partial sums added in rank order on every GPU, row blocks gathered for the sliced mode), after which the
+ * per-model updates run replicated and bit-identical on all GPUs.  Call order on every rank:
+ *   cals_b200_comm_alloc -> exchange handles / pointers between ranks -> cals_b200_comm_connect ->
+ *   cals_b200_set_tensor_slab -> combine the local norms: cals_b200_tensor_norm / cals_b200_set_tensor_norm ->
+ *   configure / enqueue the SAME models on every rank / run / fetch (every rank holds all results).
+ * `modes` are the extents of the whole tensor; cuts has world+1 entries, inner cuts even. */
+int cals_b200_comm_alloc(cals_b200_ctx *ctx, int rank, int world, uint64_t capacity_doubles,
+                         void *ipc_handle_out /* 64 bytes (cudaIpcMemHandle_t) or NULL */);
+/* capacity_doubles >= max_n(I_n rounded up to even) * buffer_cols. */
+int cals_b200_comm_local_block(cals_b200_ctx *ctx, void **block_dev_out);
+/* One process per GPU: ipc_handles = world x 64 bytes in rank order (own entry ignored), the other two NULL.
+ * One process driving all GPUs: ipc_handles NULL, peer_blocks_dev[r] = cals_b200_comm_local_block of rank r,
+ * peer_devices[r] = its CUDA ordinal. */
+int cals_b200_comm_connect(cals_b200_ctx *ctx, const void *ipc_handles, void *const *peer_blocks_dev,
+                           const int *peer_devices);
+int cals_b200_set_tensor_slab(cals_b200_ctx *ctx, int n_modes, const uint64_t *modes, int slice_mode,
+                              const uint64_t *cuts, const double *host_slab);
+/* After set_tensor_slab, cals_b200_tensor_norm returns the norm of the local slab; the caller combines
+ * sqrt(sum_r norm_r^2) and installs it with this call (Tensor::norm of the whole tensor). */
+int cals_b200_set_tensor_norm(cals_b200_ctx *ctx, double norm);
+
 /* ---- parameters (CalsParams, reference include/cals.h:138-159) ------------------------------------------------ */
 int cals_b200_configure(cals_b200_ctx *ctx, uint64_t buffer_cols, uint64_t max_iterations, double tol,
                         unsigned flags);

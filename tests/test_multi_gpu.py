@@ -160,3 +160,131 @@ def test_multi_gpu_nccl_sharded_cp_cals(tmp_path):
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
     _spawn(world, "nccl", True, tmp_path)
     _check_outputs(str(tmp_path), world, 1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Tensor sliced along one mode (BASELINE config 5)
+@pytest.mark.gpu
+@pytest.mark.parametrize("modes,C", [((14, 12, 10), 21), ((9, 8, 6, 10), 70), ((40, 18, 26), 300)])
+@pytest.mark.parametrize("variant", ["naive", "dmma"])
+def test_slab_partial_mttkrps_add_up(pkg, modes, C, variant):
+    """One GPU, ranks emulated one after the other: for every sliced mode s and every output mode n, the partial
+    MTTKRPs of the slabs add up to the MTTKRP of the whole tensor (n != s), or tile its rows (n == s)."""
+    import importlib
+    import oracle
+    d = importlib.import_module("cp_cals_b200.distributed")
+    rng = np.random.default_rng(sum(modes) + C)
+    X = rng.uniform(-1, 1, size=modes)
+    fs = [np.asfortranarray(rng.uniform(-1, 1, size=(i, C))) for i in modes]
+    want = [oracle.mttkrp(X, fs, n) for n in range(len(modes))]
+    v = pkg.MTTKRP_NAIVE if variant == "naive" else pkg.MTTKRP_DMMA
+    W = 3
+    for s in range(len(modes)):
+        cuts = [0] + [hi for _, hi in d.shard_slabs(modes[s], W)]
+        acc = [np.zeros_like(w) for w in want]
+        for r in range(W):
+            with pkg.Engine(0) as eng:
+                eng.comm_alloc(r, W, d.exchange_capacity(modes, C))
+                sl = [slice(None)] * len(modes)
+                sl[s] = slice(cuts[r], cuts[r + 1])
+                eng.set_tensor_slab(modes, s, cuts, X[tuple(sl)])
+                assert abs(eng.tensor_norm() - np.linalg.norm(X[tuple(sl)])) <= 1e-12 * np.linalg.norm(X)
+                for n in range(len(modes)):
+                    part, _ = eng.mttkrp(fs, n, variant=v)
+                    if n == s:  # only this slab's rows are produced, the rest stays zero
+                        outside = np.ones(modes[n], dtype=bool)
+                        outside[cuts[r]:cuts[r + 1]] = False
+                        assert not part[outside].any()
+                    acc[n] += part
+        for n in range(len(modes)):
+            e = np.linalg.norm(acc[n] - want[n]) / np.linalg.norm(want[n])
+            assert e <= 1e-12, "sliced mode %d, output mode %d: %.3e" % (s, n, e)
+
+
+@pytest.mark.gpu
+def test_single_slab_run_equals_plain_run(pkg):
+    import importlib
+    import caseio
+    from helpers import to_ktensors
+    d = importlib.import_module("cp_cals_b200.distributed")
+    rng = np.random.default_rng(77)
+    modes = (20, 16, 30)
+    X = rng.uniform(-1, 1, size=modes)
+    ms = caseio.random_models(rng, modes, [4, 2, 7, 1])
+    p = pkg.CalsParams(max_iterations=6, buffer_size=14, force_max_iter=True)
+    plain = to_ktensors(pkg, ms)
+    pkg.cp_cals(X, plain, p)
+    sliced = to_ktensors(pkg, ms)
+    rep = d.cp_cals_sliced(X, modes, 2, sliced, p)
+    assert rep.iter == 6
+    for a, b in zip(plain, sliced):
+        assert all(np.array_equal(x, y) for x, y in zip(a.factors, b.factors))
+        assert np.array_equal(a.lam, b.lam) and a.error == b.error
+
+
+def _sliced_worker(rank, world, port, out_dir):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import torch.distributed as dist
+    from conftest import load_package
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        pkg = load_package()
+        import importlib
+        d = importlib.import_module("cp_cals_b200.distributed")
+        X, modes, ranks, ms = _sliced_case()
+        for s in (2, 0):
+            lo, hi = d.shard_slabs(modes[s], world)[rank]
+            sl = [slice(None)] * len(modes)
+            sl[s] = slice(lo, hi)
+            kts = [pkg.Ktensor([F.copy() for F in m.factors]) for m in ms]
+            rep = d.cp_cals_sliced(np.asfortranarray(X[tuple(sl)]), modes, s, kts,
+                                   pkg.CalsParams(max_iterations=5, buffer_size=sum(ranks), force_max_iter=True),
+                                   device=rank)
+            np.savez(os.path.join(out_dir, "sliced_s%d_rank%d.npz" % (s, rank)), iter=rep.iter, x_norm=rep.X_norm,
+                     **{"m%d_f%d" % (i, n): F for i, k in enumerate(kts) for n, F in enumerate(k.factors)},
+                     **{"m%d_lam" % i: k.lam for i, k in enumerate(kts)},
+                     **{"m%d_st" % i: np.array([k.iters, k.error, k.fit]) for i, k in enumerate(kts)})
+    finally:
+        dist.destroy_process_group()
+
+
+def _sliced_case():
+    import caseio
+    rng = np.random.default_rng(5)
+    modes = (26, 30, 44)
+    X = rng.uniform(-1, 1, size=modes)
+    ranks = [3, 6, 1, 12, 5]
+    return X, modes, ranks, caseio.random_models(rng, modes, ranks)
+
+
+@pytest.mark.gpu
+def test_sliced_tensor_over_gpus_matches_oracle(tmp_path):
+    """Real exchange over NVLink peer memory: W processes, one GPU each, X sliced along the last and the first mode."""
+    import torch
+    import torch.multiprocessing as mp
+    import oracle
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    mp.spawn(_sliced_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    X, modes, ranks, ms = _sliced_case()
+    want = oracle.cp_cals(X, ms, max_iter=5, force_max_iter=True)
+    for s in (2, 0):
+        outs = [np.load(os.path.join(str(tmp_path), "sliced_s%d_rank%d.npz" % (s, r))) for r in range(world)]
+        for k in outs[0].files:  # replicated state: bit-identical on every GPU
+            for o in outs[1:]:
+                assert np.array_equal(outs[0][k], o[k]), k
+        assert int(outs[0]["iter"]) == want.iters
+        assert abs(float(outs[0]["x_norm"]) - want.x_norm) <= 1e-12 * want.x_norm
+        for i, w in enumerate(want.models):
+            for n in range(len(modes)):
+                a = outs[0]["m%d_f%d" % (i, n)]
+                assert np.linalg.norm(a - w.factors[n]) <= 1e-9 * np.linalg.norm(w.factors[n])
+            assert np.linalg.norm(outs[0]["m%d_lam" % i] - w.lam) <= 1e-9 * np.linalg.norm(w.lam)
+            st = outs[0]["m%d_st" % i]
+            assert int(st[0]) == w.iters and abs(st[2] - w.fit) <= 1e-9
