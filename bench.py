@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 CP-CALS hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4] [--strong]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1|2|3|4|5] [--strong]
 
 Metric (BASELINE.json): concurrent-ALS iterations per second summed over all models ("model-iterations/s").  The
 default workload is BASELINE config 2 (the largest configuration the metric is quoted on that fits one GPU): synthetic
@@ -48,6 +48,9 @@ CONFIGS = {
             ranks=[r for r in (3, 5, 7, 9) for _ in range(299)], als_iters=10, ref_iters=1, jk=True),
     4: dict(name="config 4: 80x80x80x80 tensor, 150 models (ranks 1..30 x5), buffer 2325", modes=(80, 80, 80, 80),
             ranks=[r for r in range(1, 31) for _ in range(5)], als_iters=4, ref_iters=1, jk=False),
+    5: dict(name="config 5: 1000x1000x1000 tensor sliced along mode 2 over the GPUs, 50 models (ranks 1..50), buffer "
+                 "1275, partial MTTKRPs combined over NVLink peer memory", modes=(1000, 1000, 1000),
+            ranks=list(range(1, 51)), als_iters=2, ref_iters=1, jk=False, sliced=2),
 }
 
 
@@ -194,6 +197,126 @@ def reference_arm(args, cfg, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_sliced(args, cfg, rank, world, local_rank):
+    """BASELINE config 5: ONE tensor sliced over the ranks (strong scaling), all models replicated."""
+    import importlib
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = load_pkg()
+    dmod = importlib.import_module("cp_cals_b200.distributed")
+    modes, s_mode, als_iters = cfg["modes"], cfg["sliced"], cfg["als_iters"]
+    steps = args.steps if args.steps is not None else 5
+    warmup = max(3, args.warmup if args.warmup is not None else 3)
+    lo, hi = dmod.shard_slabs(modes[s_mode], world)[rank]
+    shape = tuple((hi - lo) if n == s_mode else m for n, m in enumerate(modes))
+    # the slab of a seeded uniform(-1,1) tensor: slab r is drawn from its own stream so ranks generate in parallel
+    t = torch.empty(int(np.prod(shape)), dtype=torch.float64, pin_memory=True)
+    slab = t.numpy().reshape(shape, order="F")
+    rng = np.random.default_rng(5000 + rank)
+    chunk = 1 << 24
+    flat = t.numpy()
+    for o in range(0, flat.size, chunk):
+        flat[o:o + chunk] = rng.uniform(-1.0, 1.0, size=min(chunk, flat.size - o))
+    mrng = np.random.default_rng(77)  # the same models on every rank
+    models = []
+    for r in cfg["ranks"]:
+        fs = []
+        for i in modes:
+            F = mrng.uniform(-1.0, 1.0, size=(i, r))
+            fs.append(np.asfortranarray(F / np.linalg.norm(F, axis=0)))
+        models.append(fs)
+    C, n_models = sum(cfg["ranks"]), len(models)
+    params = pkg.CalsParams(max_iterations=als_iters, buffer_size=C, force_max_iter=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        v = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
+    eng = pkg.Engine(local_rank)
+    es = torch.cuda.ExternalStream(eng.stream_handle(), device=torch.device("cuda", local_rank))
+
+    def timed(fn, n):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record(es)
+        out = [fn() for _ in range(n)]
+        ev1.record(es)
+        barrier()
+        return ev0.elapsed_time(ev1), time.perf_counter() - t0, out
+
+    def e2e_step():
+        kts = [pkg.Ktensor(list(fs)) for fs in models]
+        return dmod.cp_cals_sliced(slab, modes, s_mode, kts, params, engine=eng, device=local_rank), kts
+
+    e2e_step()  # allocations, IPC mapping, upload (untimed)
+    for _ in range(warmup):
+        eng.rerun()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev_ms, wall, reps = timed(eng.rerun, steps)
+    clocks = sampler.stop()
+    ev_ms, wall = max_over_ranks(ev_ms), max_over_ranks(wall)
+    value = n_models * als_iters * steps / (ev_ms * 1e-3)
+    launches = sum(r.kernel_launches for r in reps)
+
+    eng.set_timing(1)
+    rep = eng.rerun()
+    eng.set_timing(0)
+    mt_ms = max_over_ranks(rep.mttkrp_ms) / rep.mttkrp_launches
+    flops_per_launch = 2.0 * float(np.prod(shape)) * C
+    peak, peak_src = fp64_peak()
+    ach = flops_per_launch / (mt_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "mttkrp_dmma_kernel (+ reduce + NVLink exchange_sum_kernel)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s per GPU", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "mttkrp_ms_per_launch": mt_ms, "flops_per_launch_per_gpu": flops_per_launch,
+                "mttkrp_share_of_step": rep.mttkrp_ms / (rep.mttkrp_ms + rep.update_ms)}
+
+    e2e_steps = 2
+    e2e_ms, e2e_wall, outs = timed(e2e_step, e2e_steps)
+    e2e_t = max(max_over_ranks(e2e_ms) * 1e-3, max_over_ranks(e2e_wall))
+    kts = outs[-1][1]
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ev_ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s, %d forced ALS iterations per model per step" % (cfg["name"], als_iters),
+                       "models": n_models, "sum_ranks": C, "slab_per_gpu": list(shape),
+                       "parallelism": "tensor sliced along mode %d over %d GPU(s), models replicated, one peer-memory "
+                                      "exchange per mode" % (s_mode, world),
+                       "l2": "inputs larger than L2 (%.1f GB of tensor per GPU)" % (np.prod(shape) * 16 / 1e9)},
+            "wall_ms_per_step": wall / steps * 1e3,
+            "timing": "CUDA events on the engine's stream around the K steps, max over ranks",
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "e2e": {"value": n_models * als_iters * e2e_steps / e2e_t, "unit": UNIT,
+                    "h2d_bytes_per_step": int(slab.nbytes + sum(F.nbytes for fs in models for F in fs)),
+                    "d2h_bytes_per_step": int(sum(F.nbytes for fs in models for F in fs) + 8 * C),
+                    "steps": e2e_steps, "ms_per_step": e2e_t / e2e_steps * 1e3,
+                    "mean_fit": float(np.mean([k.fit for k in kts]))},
+            "cpu_baseline": {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                             "sample": "not run: the reference materialises a 10 GB Khatri-Rao workspace for this "
+                                       "tensor (SURVEY 8d); config 2 carries the CPU baseline"},
+        }
+        print(json.dumps(line), flush=True)
+    dmod.release_sliced_engine(eng)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,7 +334,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
+        if cfg.get("sliced") is not None:
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "config 5 is not run through the CPU reference "
+                                  "(10 GB Khatri-Rao workspace); use --config 2"}), flush=True)
+            return
         reference_arm(args, cfg, rank)
+        return
+    if cfg.get("sliced") is not None:
+        run_sliced(args, cfg, rank, world, local_rank)
         return
 
     steps = args.steps if args.steps is not None else 10

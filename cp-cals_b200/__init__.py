@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "cals_b200_mttkrp", "cals_b200_device_info", "cals_b200_version", "cals_b200_fetch_iteration_cols",
     "cals_b200_host_alloc", "cals_b200_host_free", "cals_b200_stream",
     "cals_b200_comm_alloc", "cals_b200_comm_local_block", "cals_b200_comm_connect", "cals_b200_set_tensor_slab",
-    "cals_b200_set_tensor_norm",
+    "cals_b200_set_tensor_norm", "cals_b200_comm_disconnect",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
     L.cals_b200_comm_connect.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(i)]
     L.cals_b200_set_tensor_slab.argtypes = [vp, i, C.POINTER(u64), i, C.POINTER(u64), vp]
     L.cals_b200_set_tensor_norm.argtypes = [vp, dbl]
+    L.cals_b200_comm_disconnect.argtypes = [vp]
     _lib = L
     return L
 
@@ -253,6 +254,10 @@ class Engine:
         self._ck(self._L.cals_b200_comm_alloc(self._ctx, rank, world, capacity_doubles, h))
         self.comm_rank, self.comm_world = rank, world
         return h.raw
+
+    def comm_disconnect(self):
+        self._ck(self._L.cals_b200_comm_disconnect(self._ctx))
+        self._comm = None
 
     def comm_local_block(self) -> int:
         out = C.c_void_p()

@@ -440,13 +440,18 @@ void release_run(cals_b200_ctx *c) {
   c->run_sig.clear();
 }
 
-void release_comm(cals_b200_ctx *c) {
+void disconnect_peers(cals_b200_ctx *c) {
   for (int r = 0; r < CALS_MAX_PEERS; r++) {
     if (c->peer_block[r] && c->peer_is_ipc[r])
       cudaIpcCloseMemHandle(c->peer_block[r]);
     c->peer_block[r] = nullptr;
     c->peer_is_ipc[r] = false;
   }
+  c->comm_connected = false;
+}
+
+void release_comm(cals_b200_ctx *c) {
+  disconnect_peers(c);
   if (c->xblock)
     cudaFree(c->xblock);
   c->xblock = nullptr;
@@ -1107,6 +1112,17 @@ int cals_b200_comm_connect(cals_b200_ctx *c, const void *ipc_handles, void *cons
     }
   }
   c->comm_connected = true;
+  return 0;
+}
+
+int cals_b200_comm_disconnect(cals_b200_ctx *c) {
+  if (!c)
+    return 1;
+  cudaSetDevice(c->device);
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  disconnect_peers(c);
+  if (c->xblock)
+    c->peer_block[c->comm_rank] = c->xblock;
   return 0;
 }
 

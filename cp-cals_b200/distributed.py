@@ -159,11 +159,18 @@ def cp_cals_sliced(slab: np.ndarray, modes: Sequence[int], slice_mode: int, kten
     eng = engine or Engine(device)
     try:
         buffer_cols = min(params.buffer_size, sum(k.rank for k in ktensors))
-        handle = eng.comm_alloc(rank, world, exchange_capacity(modes, buffer_cols))
-        if world > 1:
-            handles = [None] * world
-            dist.all_gather_object(handles, handle, group=group)
-            eng.comm_connect_ipc(handles)
+        cap = exchange_capacity(modes, buffer_cols)
+        have = getattr(eng, "_comm", None)
+        if not (have and have[0] == rank and have[1] == world and have[2] >= cap):  # else: reuse the mapped blocks
+            if have and world > 1:
+                eng.comm_disconnect()
+                dist.barrier(group=group)
+            handle = eng.comm_alloc(rank, world, cap)
+            if world > 1:
+                handles = [None] * world
+                dist.all_gather_object(handles, handle, group=group)
+                eng.comm_connect_ipc(handles)
+            eng._comm = (rank, world, cap)
         eng.set_tensor_slab(modes, slice_mode, cuts, slab)
         sq = torch.tensor([eng.tensor_norm() ** 2], dtype=torch.float64,
                           device=torch.device("cuda", device) if world > 1 and dist.get_backend(group) == "nccl"
@@ -196,4 +203,17 @@ def cp_cals_sliced(slab: np.ndarray, modes: Sequence[int], slice_mode: int, kten
                           mttkrp_launches=rep.mttkrp_launches, kernel_launches=rep.kernel_launches)
     finally:
         if own:
-            eng.close()
+            release_sliced_engine(eng, group)
+
+
+def release_sliced_engine(eng, group=None):
+    """Tear-down order CUDA IPC asks for: every rank unmaps its peers' exchange blocks, all ranks synchronise, and
+    only then does anybody free its own block."""
+    import torch.distributed as dist
+    if getattr(eng, "_comm", None) and dist.is_initialized() and dist.get_world_size(group) > 1:
+        try:
+            eng.comm_disconnect()
+            dist.barrier(group=group)
+        except Exception:
+            pass
+    eng.close()

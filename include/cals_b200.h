@@ -86,6 +86,10 @@ int cals_b200_comm_local_block(cals_b200_ctx *ctx, void **block_dev_out);
  * peer_devices[r] = its CUDA ordinal. */
 int cals_b200_comm_connect(cals_b200_ctx *ctx, const void *ipc_handles, void *const *peer_blocks_dev,
                            const int *peer_devices);
+/* Unmap the peers' exchange blocks (own block stays).  Every rank calls this, then synchronises with the others,
+ * BEFORE any rank frees its block (cals_b200_comm_alloc again, or cals_b200_destroy): CUDA IPC does not allow the
+ * exporter to free memory that an importer still has mapped. */
+int cals_b200_comm_disconnect(cals_b200_ctx *ctx);
 int cals_b200_set_tensor_slab(cals_b200_ctx *ctx, int n_modes, const uint64_t *modes, int slice_mode,
                               const uint64_t *cuts, const double *host_slab);
 /* After set_tensor_slab, cals_b200_tensor_norm returns the norm of the local slab; the caller combines
