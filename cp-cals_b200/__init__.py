@@ -240,6 +240,7 @@ class Engine:
         Xf = np.asfortranarray(X, dtype=np.float64)
         modes = (C.c_uint64 * Xf.ndim)(*Xf.shape)
         self._ck(self._L.cals_b200_set_tensor(self._ctx, Xf.ndim, modes, Xf.ctypes.data))
+        self._keep_X = Xf  # the upload is asynchronous: keep the source alive until the next synchronising call
         self.modes = tuple(Xf.shape)
 
     def set_tensor_dev(self, dev_ptr: int, modes: Sequence[int]):
@@ -284,6 +285,7 @@ class Engine:
         m = (C.c_uint64 * len(modes))(*modes)
         cu = (C.c_uint64 * len(cuts))(*cuts)
         self._ck(self._L.cals_b200_set_tensor_slab(self._ctx, len(modes), m, slice_mode, cu, Sf.ctypes.data))
+        self._keep_X = Sf
         self.modes = tuple(modes)
 
     def set_tensor_norm(self, norm: float):
@@ -350,6 +352,17 @@ class Engine:
         self._ck(self._L.cals_b200_fetch_model(self._ctx, model_id, ptrs, lam.ctypes.data, C.byref(st)))
         return fs, lam, st
 
+    def fetch_all(self):
+        """All models of the last run with ONE call through the C ABI: [(factors, lam, stats), ...] in queue order."""
+        M, N = len(self._ranks), len(self.modes)
+        fs = [[np.empty((I, r), order="F") for I in self.modes] for r in self._ranks]
+        lams = [np.empty(r) for r in self._ranks]
+        fptr = (C.c_void_p * (M * N))(*[F.ctypes.data for row in fs for F in row])
+        lptr = (C.c_void_p * M)(*[l.ctypes.data for l in lams])
+        stats = (ModelStats * M)()
+        self._ck(self._L.cals_b200_fetch_all(self._ctx, fptr, lptr, stats))
+        return [(fs[m], lams[m], stats[m]) for m in range(M)]
+
     # -- hooks ---------------------------------------------------------------------------------------------------------------
     def mttkrp(self, factors: Sequence[np.ndarray], mode: int, variant: int = MTTKRP_DMMA, repeats: int = 1):
         """G = X_(mode) * KRP(factors except mode) over the concatenated columns.  Returns (G, ms_per_launch)."""
@@ -410,8 +423,7 @@ def cp_cals(X: np.ndarray, ktensors: Sequence[Ktensor], params: CalsParams, *, e
         for kt in ktensors:
             eng.enqueue(kt.factors, kt.jk_mode, kt.jk_fiber)
         rep = eng.run()
-        for i, kt in enumerate(ktensors):
-            fs, lam, st = eng.fetch(i)
+        for kt, (fs, lam, st) in zip(ktensors, eng.fetch_all()):
             kt.factors, kt.lam = fs, lam
             kt.iters, kt.error, kt.fit, kt.old_fit, kt.chol_info = st.iters, st.error, st.fit, st.old_fit, st.chol_info
         return CalsReport(n_modes=X.ndim, modes=tuple(X.shape), X_norm=rep.x_norm, iter=rep.iter,

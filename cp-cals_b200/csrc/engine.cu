@@ -31,9 +31,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-struct HostModel {
-  int rank, jk_mode, jk_fiber;
-  std::vector<double> factors; // concatenated I_n x rank blocks (dense, ld = I_n)
+struct HostModel { // the factors themselves go straight into the pinned input staging (ctx::h_in) at enqueue time
+  int rank, jk_mode, jk_fiber, home_col;
 };
 
 // Everything whose size depends on the number of buffer columns.
@@ -72,7 +71,10 @@ struct cals_b200_ctx {
   int ldX0 = 0, ldX1 = 0;
   double *jk_norms = nullptr; // dims[0]
   double *d_norm = nullptr;
-  double x_norm = 0.0;
+  double x_norm = 0.0;        // host copy of ||X||; valid only when x_norm_valid
+  bool x_norm_valid = false;  // false between an (asynchronous) set_tensor and the first synchronising call
+  bool x_norm_override = false; // cals_b200_set_tensor_norm: the host value wins over the device-computed one
+  double *h_norm = nullptr;   // pinned landing place of the device-computed norm
   bool have_tensor = false;
 
   // params
@@ -104,7 +106,11 @@ struct cals_b200_ctx {
   std::vector<void *> run_allocs;
   int run_cols = 0, run_total_cols = 0, run_models = 0;
 
-  // host mirrors of results: pinned staging buffers, reused from run to run
+  // pinned staging, reused from run to run: h_in = initial factors of the queued models (filled by enqueue_model, pitch
+  // ldF, one column block per model in queue order), h_home = fitted factors on the way back
+  double *h_in[CALS_MAX_MODES] = {};
+  size_t h_in_cap[CALS_MAX_MODES] = {};
+  int queued_cols = 0;
   double *h_home[CALS_MAX_MODES] = {};
   size_t h_home_cap[CALS_MAX_MODES] = {};
   double *h_lambda = nullptr;
@@ -556,13 +562,29 @@ int install_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const d
     }
     rowsumsq_partial_kernel<<<ctas, 256, 256 * 8, c->stream>>>(c->Xp, I0, c->ldX0, rest0, c->norm_partial);
     rowsumsq_final_kernel<<<1, 256, 0, c->stream>>>(c->norm_partial, ctas, I0, c->jk_norms, c->d_norm);
-    CU_TRY(c, cudaMemcpyAsync(&c->x_norm, c->d_norm, 8, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    // no synchronisation here: the upload and the layout kernels overlap with whatever the caller does next (queueing
+    // models); the host copy of the norm is picked up by the first call that synchronises anyway
+    if (!c->h_norm)
+      CU_TRY(c, cudaHostAlloc((void **)&c->h_norm, 64, cudaHostAllocDefault));
+    CU_TRY(c, cudaMemcpyAsync(c->h_norm, c->d_norm, 8, cudaMemcpyDeviceToHost, c->stream));
+    c->x_norm_valid = false;
+    c->x_norm_override = false;
   }
-  if (dense_owned)
+  if (dense_owned) {
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
     cudaFree(dense);
+  }
   CU_TRY(c, cudaGetLastError());
   c->have_tensor = true;
+  return 0;
+}
+
+int ensure_host_norm(cals_b200_ctx *c) {
+  if (!c->x_norm_valid) {
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    c->x_norm = *c->h_norm;
+    c->x_norm_valid = true;
+  }
   return 0;
 }
 
@@ -600,6 +622,8 @@ int prepare_run(cals_b200_ctx *c) {
       return fail(c, "model %d has rank %d > buffer_size %d: it can never be admitted", m, hm.rank, c->buffer_cols);
     ModelDesc &d = c->hdesc[m];
     d.rank = hm.rank;
+    if (hm.home_col != col)
+      return fail(c, "internal error: queue staging out of step");
     d.home_col = col;
     d.jk_mode = hm.jk_mode;
     d.jk_fiber = hm.jk_fiber;
@@ -630,26 +654,12 @@ int prepare_run(cals_b200_ctx *c) {
   if (ensure_dummy_state(c))
     return 1;
 
-  // pack the home matrices (pitch ldF) into pinned staging and upload
+  // upload the initial factors (already in the device layout, pitch ldF, in the pinned input staging)
   for (int n = 0; n < N; n++) {
-    const int rows = geo.dims[n], ld = geo.ldF[n];
-    const size_t count = (size_t)ld * c->total_cols;
+    const size_t count = (size_t)geo.ldF[n] * c->total_cols;
     if (pinned_reserve(c, &c->h_home[n], &c->h_home_cap[n], count))
       return 1;
-    double *h = c->h_home[n];
-    for (int m = 0; m < M; m++) {
-      const HostModel &hm = c->hmodels[m];
-      size_t off = 0;
-      for (int k = 0; k < n; k++)
-        off += (size_t)geo.dims[k] * hm.rank;
-      for (int j = 0; j < hm.rank; j++) {
-        double *dst = &h[(size_t)(c->hdesc[m].home_col + j) * ld];
-        memcpy(dst, &hm.factors[off + (size_t)j * rows], (size_t)rows * 8);
-        if (ld > rows)
-          dst[rows] = 0.0;
-      }
-    }
-    CU_TRY(c, cudaMemcpyAsync(c->bufs.fac.home[n], h, count * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(c->bufs.fac.home[n], c->h_in[n], count * 8, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(c->home0[n], c->bufs.fac.home[n], count * 8, cudaMemcpyDeviceToDevice, c->stream));
   }
   if (pinned_reserve(c, &c->h_lambda, &c->h_lambda_cap, (size_t)c->total_cols) ||
@@ -696,8 +706,10 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   st.max_iter = c->max_iter;
   st.buffer_cols = c->buffer_cols;
   st.tol = c->tol;
-  st.x_norm = c->x_norm;
+  st.x_norm = c->x_norm_valid ? c->x_norm : 0.0;
   CU_TRY(c, cudaMemcpyAsync(c->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s));
+  if (!c->x_norm_valid) // set_tensor has not been synchronised yet: take the norm from where the device computed it
+    CU_TRY(c, cudaMemcpyAsync(&c->d_st->x_norm, c->d_norm, 8, cudaMemcpyDeviceToDevice, s));
   c->h_flags[0] = c->h_flags[1] = c->h_flags[2] = 0;
 
   init_grams_kernel<<<dim3(M, N), 256, 0, s>>>(geo, b.fac, c->d_models, c->d_gram);
@@ -844,6 +856,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     rep->iter = st.global_iter;
     rep->n_ktensors = st.n_admitted;
     rep->ktensor_comp_sum = st.comp_sum;
+    if (ensure_host_norm(c))
+      return 1;
     rep->x_norm = c->x_norm;
     rep->total_time = std::chrono::duration<double>(t1 - t0).count();
     float ms = 0;
@@ -986,6 +1000,11 @@ int cals_b200_destroy(cals_b200_ctx *c) {
   for (auto &p : c->h_home)
     if (p)
       cudaFreeHost(p);
+  for (auto &p : c->h_in)
+    if (p)
+      cudaFreeHost(p);
+  if (c->h_norm)
+    cudaFreeHost(c->h_norm);
   if (c->h_lambda)
     cudaFreeHost(c->h_lambda);
   if (c->h_desc_pin)
@@ -1040,6 +1059,8 @@ int cals_b200_set_tensor_norm(cals_b200_ctx *c, double norm) {
   if (!(norm > 0.0))
     return fail(c, "the tensor norm must be positive");
   c->x_norm = norm;
+  c->x_norm_valid = true;
+  c->x_norm_override = true;
   return 0;
 }
 
@@ -1163,6 +1184,7 @@ int cals_b200_clear_models(cals_b200_ctx *c) {
     return 1;
   c->hmodels.clear();
   c->hdesc.clear();
+  c->queued_cols = 0;
   c->uploaded = false;
   c->results_fresh = false;
   return 0;
@@ -1187,17 +1209,35 @@ int cals_b200_enqueue_model(cals_b200_ctx *c, uint64_t rank, const double *const
   hm.rank = (int)rank;
   hm.jk_mode = jk_mode < 0 ? -1 : jk_mode;
   hm.jk_fiber = jk_mode < 0 ? 0 : (int)jk_fiber;
-  size_t total = 0;
+  hm.home_col = c->queued_cols;
   for (int n = 0; n < geo.n_modes; n++)
-    total += (size_t)geo.dims[n] * rank;
-  hm.factors.resize(total);
-  size_t off = 0;
-  for (int n = 0; n < geo.n_modes; n++) {
     if (!host_factors[n])
       return fail(c, "factor %d is null", n);
-    memcpy(&hm.factors[off], host_factors[n], (size_t)geo.dims[n] * rank * 8);
-    off += (size_t)geo.dims[n] * rank;
+  for (int n = 0; n < geo.n_modes; n++) {
+    const int rows = geo.dims[n], ld = geo.ldF[n];
+    const size_t need = (size_t)ld * (c->queued_cols + rank);
+    if (need > c->h_in_cap[n]) { // grow geometrically, keeping what is already queued
+      const size_t cap = std::max(need, std::max<size_t>(2 * c->h_in_cap[n], (size_t)ld * 256));
+      double *fresh = nullptr;
+      CU_TRY(c, cudaHostAlloc((void **)&fresh, cap * 8, cudaHostAllocDefault));
+      if (c->h_in[n]) {
+        CU_TRY(c, cudaStreamSynchronize(c->stream)); // an upload from the old block may still be in flight
+        memcpy(fresh, c->h_in[n], (size_t)ld * c->queued_cols * 8);
+        cudaFreeHost(c->h_in[n]);
+      }
+      c->h_in[n] = fresh;
+      c->h_in_cap[n] = cap;
+    }
+    double *dst = c->h_in[n] + (size_t)ld * c->queued_cols;
+    if (ld == rows)
+      memcpy(dst, host_factors[n], (size_t)rows * rank * 8);
+    else
+      for (uint64_t j = 0; j < rank; j++) {
+        memcpy(dst + j * ld, host_factors[n] + j * rows, (size_t)rows * 8);
+        dst[j * ld + rows] = 0.0;
+      }
   }
+  c->queued_cols += (int)rank;
   c->hmodels.push_back(std::move(hm));
   c->uploaded = false;
   if (model_id)
@@ -1257,6 +1297,9 @@ int cals_b200_tensor_norm(cals_b200_ctx *c, double *norm_out) {
     return fail(c, "null argument");
   if (!c->have_tensor)
     return fail(c, "no tensor set");
+  cudaSetDevice(c->device);
+  if (ensure_host_norm(c))
+    return 1;
   *norm_out = c->x_norm;
   return 0;
 }

@@ -190,8 +190,7 @@ def cp_cals_sliced(slab: np.ndarray, modes: Sequence[int], slice_mode: int, kten
         if world > 1:
             dist.barrier(group=group)  # every peer's exchange block is mapped before anyone starts to signal
         rep = eng.run()
-        for i, kt in enumerate(ktensors):
-            fs, lam, st = eng.fetch(i)
+        for kt, (fs, lam, st) in zip(ktensors, eng.fetch_all()):
             kt.factors, kt.lam = fs, lam
             kt.iters, kt.error, kt.fit, kt.old_fit, kt.chol_info = st.iters, st.error, st.fit, st.old_fit, st.chol_info
         if world > 1:

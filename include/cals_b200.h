@@ -63,7 +63,9 @@ const char *cals_b200_last_error(const cals_b200_ctx *ctx); /* ctx may be NULL: 
 
 /* ---- target tensor  (replaces X.allocate_cudata + send_to_device_async, reference src/cals.cpp:142-147) ------- */
 /* Uploads X (prod(modes) doubles, mode 0 fastest), builds the device layouts the kernels read, and computes
- * ||X|| (Tensor::norm, include/tensor.h:196) on the device. */
+ * ||X|| (Tensor::norm, include/tensor.h:196) on the device.  The call only ENQUEUES that work on the context's stream
+ * (so that queueing the models on the host overlaps with it): host_X must stay valid and unchanged until the next
+ * call that synchronises (cals_b200_run, cals_b200_tensor_norm, cals_b200_jk_norms, cals_b200_mttkrp). */
 int cals_b200_set_tensor(cals_b200_ctx *ctx, int n_modes, const uint64_t *modes, const double *host_X);
 /* Same with X already in device memory (dense, unpadded). */
 int cals_b200_set_tensor_dev(cals_b200_ctx *ctx, int n_modes, const uint64_t *modes, const double *X_dev);
