@@ -6,6 +6,7 @@
 #include <random>
 
 #include "cals.h"
+#include "multi_ktensor.h"
 #include "utils/error.h"
 
 #define REQUIRE(c)                                                                                                     \
@@ -179,6 +180,57 @@ int main() {
     for (int s : seen)
       REQUIRE(s == 1);
     REQUIRE(hi - lo <= 20);
+  }
+
+  // MultiKtensor: first-fit placement, BufferFull, detach on removal, stable compaction (reference
+  // src/multi_ktensor.cpp:14-39,41-130,132-163,188-264)
+  {
+    std::vector<dim_t> modes{4, 3, 5};
+    MultiKtensor mk(modes, 10);
+    REQUIRE(mk.get_factor(0).get_cols() == 0 && mk.get_leftmost_id() == 0);
+    std::vector<Ktensor> ms;
+    for (dim_t r : {3, 2, 4})
+      ms.emplace_back(r, modes);
+    for (Ktensor &m : ms)
+      m.fill(draw);
+    std::vector<Ktensor> orig(ms);
+    for (Ktensor &m : ms)
+      mk.add(m);
+    REQUIRE(mk.get_factor(1).get_cols() == 9 && mk.get_registry().size() == 3 && mk.get_leftmost_id() == 1);
+    REQUIRE(mk.get_registry().at(2).col == 3 && ms[1].get_iters() == 1);
+    // the models now live in the buffer: same values, storage inside the multi-factor
+    REQUIRE(ms[1].get_factor(2).get_data() == mk.get_factor(2).get_data() + 3 * 5);
+    REQUIRE(mk.get_factor(2)(4, 4) == orig[1].get_factor(2)(4, 1));
+    // Gramians of the incoming factors
+    REQUIRE(std::fabs(mk.get_registry().at(3).gramians[0](2, 2) - 1.0) < 1e-13);
+    Ktensor big(2, modes);
+    big.fill(draw);
+    bool full = false;
+    try {
+      mk.add(big); // only one free column
+    } catch (BufferFull &) {
+      full = true;
+    }
+    REQUIRE(full);
+    // write through the buffer, remove the middle model: it takes the value home, its columns are zeroed
+    mk.get_factor(0)(1, 3) = 42.0;
+    mk.remove(2);
+    REQUIRE(ms[1].get_factor(0)(1, 0) == 42.0 && ms[1].get_factor(0).get_data() != mk.get_factor(0).get_data() + 12);
+    REQUIRE(mk.get_factor(0)(1, 3) == 0.0 && mk.get_registry().count(2) == 0);
+    mk.add(big); // first fit: the hole left by the rank-2 model
+    REQUIRE(mk.get_registry().at(4).col == 3);
+    mk.remove(1);
+    REQUIRE(mk.get_leftmost_id() == 0 && mk.get_factor(0).get_cols() == 9);
+    mk.compress(); // [., ., ., big, big, m3 x4] -> [big, big, m3 x4]
+    REQUIRE(mk.get_factor(0).get_cols() == 6 && mk.get_registry().at(4).col == 0 && mk.get_registry().at(3).col == 2);
+    REQUIRE(mk.get_leftmost_id() == 4);
+    for (dim_t e = 0; e < ms[2].get_factor(1).get_n_elements(); e++)
+      REQUIRE(ms[2].get_factor(1)[e] == orig[2].get_factor(1)[e]);
+    REQUIRE(ms[2].get_factor(1).get_data() == mk.get_factor(1).get_data() + 2 * 3);
+    REQUIRE(mk.get_factor(1).get_data()[6 * 3] == 0.0); // vacated columns are clean
+    mk.remove(3);
+    mk.remove(4);
+    REQUIRE(mk.get_factor(0).get_cols() == 0 && mk.get_registry().empty());
   }
 
   set_threads(6);

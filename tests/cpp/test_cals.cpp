@@ -11,6 +11,7 @@
 
 #include "als.h"
 #include "cals.h"
+#include "multi_ktensor.h"
 
 using cals::Ktensor;
 using cals::Tensor;
@@ -222,6 +223,40 @@ TEST(Cals, ShardedModelSetEqualsSingleDevice) {
     EXPECT_NEAR(reconstruction_gap(one[p], two[p]), 0.0, 1e-9 * T.norm());
     EXPECT_NEAR(one[p].get_fit(), two[p].get_fit(), 1e-9);
     EXPECT_EQ(one[p].get_iters(), two[p].get_iters());
+  }
+}
+
+// The concurrent MTTKRP driven by hand, as the reference's MTTKRP benchmarks do (include/experiments/
+// bench_mttkrp_cals.h): models attached to a MultiKtensor, ONE mttkrp::mttkrp over the multi-factor == the MTTKRP of
+// every model on its own.
+TEST(Cals, MttkrpOverMultiKtensorEqualsPerModelMttkrp) {
+  Uniform u(21);
+  std::vector<dim_t> modes{18, 14, 11};
+  Tensor T(modes);
+  T.fill(u.source());
+  std::vector<dim_t> ranks{3, 5, 1, 4};
+  std::vector<Ktensor> models = random_models(ranks, modes, u);
+  for (dim_t mode = 0; mode < 3; mode++) {
+    std::vector<Ktensor> alone(models), together(models);
+    std::vector<cals::Matrix> ws;
+    cals::mttkrp::MttkrpParams mp;
+    for (Ktensor &k : alone)
+      cals::mttkrp::mttkrp(T, k, ws, mode, mp);
+    cals::MultiKtensor mk(modes, 16);
+    for (Ktensor &k : together)
+      mk.add(k);
+    cals::mttkrp::mttkrp(T, mk, ws, mode, mp);
+    EXPECT_EQ(mp.flops, 2ull * T.get_n_elements() * 13);
+    for (size_t p = 0; p < models.size(); p++) {
+      double worst = 0.0, scale = 0.0;
+      for (dim_t e = 0; e < alone[p].get_factor(mode).get_n_elements(); e++) {
+        worst = std::max(worst, std::fabs(alone[p].get_factor(mode)[e] - together[p].get_factor(mode)[e]));
+        scale = std::max(scale, std::fabs(alone[p].get_factor(mode)[e]));
+      }
+      EXPECT_LT(worst, 1e-12 * scale);
+    }
+    for (int id = 1; id <= 4; id++)
+      mk.remove(id);
   }
 }
 
