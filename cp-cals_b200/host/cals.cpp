@@ -125,6 +125,145 @@ RunResult run_on_device(int device, const Tensor &X, const std::vector<Ktensor *
   return out;
 }
 
+std::vector<dim_t> shard_slabs(dim_t extent, size_t n_parts) {
+  std::vector<dim_t> cuts{0};
+  for (size_t p = 1; p < n_parts; p++) {
+    dim_t c = static_cast<dim_t>(static_cast<double>(p) * extent / n_parts / 2.0 + 0.5) * 2; // even boundaries
+    cuts.push_back(std::min(std::max(c, cuts.back()), extent));
+  }
+  cuts.push_back(extent);
+  return cuts;
+}
+
+// Config 5: X sliced along `slice_mode` over the devices, all models on every device, one host thread per device.
+// Every device ends with the same (bit-identical) results; device 0's are written into the callers' Ktensors.
+static RunResult run_sliced(const std::vector<int> &devices, int slice_mode, const Tensor &X,
+                            const std::vector<Ktensor *> &models, const RunOptions &opt) {
+  const size_t W = devices.size();
+  const vector<dim_t> modes = X.get_modes();
+  const dim_t N = modes.size();
+  if (slice_mode < 0 || static_cast<dim_t>(slice_mode) >= N)
+    throw B200Error("cp_cals: slice_mode out of range");
+  for (size_t a = 0; a < W; a++)
+    for (size_t b = a + 1; b < W; b++)
+      if (devices[a] == devices[b])
+        throw B200Error("cp_cals: a sliced tensor needs distinct devices (ranks wait for each other on the GPU)");
+  const std::vector<dim_t> cuts = shard_slabs(modes[slice_mode], W);
+  for (size_t r = 0; r < W; r++)
+    if (cuts[r + 1] <= cuts[r])
+      throw B200Error("cp_cals: more devices than (pairs of) rows in the sliced mode");
+  dim_t sum_ranks = 0;
+  for (const Ktensor *kt : models) {
+    if (kt->is_jk())
+      throw B200Error("cp_cals: jackknife models are not supported on a sliced tensor");
+    sum_ranks += kt->get_components();
+  }
+  const dim_t buffer = std::max<dim_t>(std::min(opt.buffer_size, sum_ranks), 1);
+  dim_t max_ld = 0;
+  for (dim_t m : modes)
+    max_ld = std::max(max_ld, (m + 1) / 2 * 2);
+  std::vector<uint64_t> m64(modes.begin(), modes.end()), c64(cuts.begin(), cuts.end());
+
+  std::vector<EngineHandle *> eng(W);
+  std::vector<std::unique_lock<std::mutex>> locks;
+  for (size_t r = 0; r < W; r++) {
+    eng[r] = &engine_for_device(devices[r]);
+    locks.emplace_back(eng[r]->mu);
+    eng[r]->resident_data = nullptr;
+  }
+  // exchange blocks + peer mapping (one process drives all GPUs: plain peer pointers)
+  std::vector<void *> blocks(W);
+  for (size_t r = 0; r < W; r++) {
+    check(*eng[r], cals_b200_comm_alloc(eng[r]->ctx, (int)r, (int)W, max_ld * buffer, nullptr), "cals_b200_comm_alloc");
+    check(*eng[r], cals_b200_comm_local_block(eng[r]->ctx, &blocks[r]), "cals_b200_comm_local_block");
+  }
+  for (size_t r = 0; r < W; r++)
+    check(*eng[r], cals_b200_comm_connect(eng[r]->ctx, nullptr, blocks.data(), devices.data()),
+          "cals_b200_comm_connect");
+
+  // slabs: contiguous for the last mode, gathered otherwise
+  dim_t below = 1, above = 1;
+  for (dim_t k = 0; k < (dim_t)slice_mode; k++)
+    below *= modes[k];
+  for (dim_t k = slice_mode + 1; k < N; k++)
+    above *= modes[k];
+  std::vector<std::vector<double>> slab_store(W);
+  double sumsq = 0.0;
+  for (size_t r = 0; r < W; r++) {
+    const dim_t ext = cuts[r + 1] - cuts[r];
+    const double *src = X.get_data() + below * cuts[r];
+    if (above > 1) {
+      slab_store[r].resize(below * ext * above);
+      for (dim_t u = 0; u < above; u++)
+        std::copy(src + u * below * modes[slice_mode], src + u * below * modes[slice_mode] + below * ext,
+                  slab_store[r].data() + u * below * ext);
+      src = slab_store[r].data();
+    }
+    check(*eng[r], cals_b200_set_tensor_slab(eng[r]->ctx, (int)N, m64.data(), slice_mode, c64.data(), src),
+          "cals_b200_set_tensor_slab");
+  }
+  for (size_t r = 0; r < W; r++) {
+    double nrm = 0.0;
+    check(*eng[r], cals_b200_tensor_norm(eng[r]->ctx, &nrm), "cals_b200_tensor_norm");
+    sumsq += nrm * nrm;
+  }
+  const unsigned flags = (opt.force_max_iter ? CALS_B200_FORCE_MAX_ITER : 0u) |
+                         (opt.always_evict_first ? CALS_B200_ALWAYS_EVICT_FIRST : 0u);
+  std::vector<const double *> in(N);
+  for (size_t r = 0; r < W; r++) {
+    check(*eng[r], cals_b200_set_tensor_norm(eng[r]->ctx, std::sqrt(sumsq)), "cals_b200_set_tensor_norm");
+    check(*eng[r], cals_b200_configure(eng[r]->ctx, buffer, opt.max_iterations, opt.tol, flags), "cals_b200_configure");
+    check(*eng[r], cals_b200_set_timing(eng[r]->ctx, opt.timing), "cals_b200_set_timing");
+    check(*eng[r], cals_b200_clear_models(eng[r]->ctx), "cals_b200_clear_models");
+    for (Ktensor *kt : models) {
+      for (dim_t n = 0; n < N; n++)
+        in[n] = kt->get_factor(n).get_data();
+      check(*eng[r], cals_b200_enqueue_model(eng[r]->ctx, kt->get_components(), in.data(), -1, 0, nullptr),
+            "cals_b200_enqueue_model");
+    }
+  }
+  // the loops of all devices run side by side (they meet in every exchange)
+  std::vector<cals_b200_report> reps(W);
+  std::vector<std::string> errors(W);
+  std::vector<std::thread> workers;
+  for (size_t r = 0; r < W; r++)
+    workers.emplace_back([&, r] {
+      if (cals_b200_run(eng[r]->ctx, &reps[r]) != 0)
+        errors[r] = cals_b200_last_error(eng[r]->ctx);
+    });
+  for (auto &w : workers)
+    w.join();
+  for (size_t r = 0; r < W; r++)
+    if (!errors[r].empty())
+      throw B200Error("cp_cals (sliced) on device " + std::to_string(devices[r]) + ": " + errors[r]);
+
+  RunResult out;
+  out.rep = reps[0];
+  const size_t M = models.size();
+  std::vector<double *> fptr(M * N), lptr(M);
+  std::vector<cals_b200_model_stats> stats(M);
+  for (size_t m = 0; m < M; m++) {
+    for (dim_t n = 0; n < N; n++)
+      fptr[m * N + n] = models[m]->get_factor(n).get_data();
+    lptr[m] = models[m]->get_lambda().data();
+  }
+  check(*eng[0], cals_b200_fetch_all(eng[0]->ctx, fptr.data(), lptr.data(), stats.data()), "cals_b200_fetch_all");
+  for (size_t m = 0; m < M; m++) {
+    models[m]->set_iters(static_cast<dim_t>(stats[m].iters));
+    models[m]->set_approximation_error(stats[m].error);
+    models[m]->set_fit(stats[m].fit, stats[m].old_fit);
+  }
+  uint64_t n_it = 0;
+  check(*eng[0], cals_b200_fetch_iteration_cols(eng[0]->ctx, nullptr, 0, &n_it), "cals_b200_fetch_iteration_cols");
+  std::vector<uint32_t> c32(n_it);
+  if (n_it)
+    check(*eng[0], cals_b200_fetch_iteration_cols(eng[0]->ctx, c32.data(), n_it, &n_it), "fetch_iteration_cols");
+  out.cols.assign(c32.begin(), c32.end());
+  for (size_t r = 0; r < W; r++) // leave no peer mapping behind: the next call may use other devices
+    check(*eng[r], cals_b200_comm_disconnect(eng[r]->ctx), "cals_b200_comm_disconnect");
+  return out;
+}
+
 std::vector<std::vector<size_t>> shard_models(const std::vector<dim_t> &ranks, size_t n_parts) {
   std::vector<std::vector<size_t>> parts(std::max<size_t>(n_parts, 1));
   std::vector<dim_t> load(parts.size(), 0);
@@ -193,7 +332,10 @@ CalsReport cp_cals(const Tensor &X, KtensorQueue &kt_queue, CalsParams &cals_par
   rep.n_devices = static_cast<int>(devices.size());
 
   std::vector<detail::RunResult> results(devices.size());
-  if (devices.size() == 1) {
+  if (cals_params.slice_mode >= 0 && devices.size() > 1) {
+    results.resize(1);
+    results[0] = detail::run_sliced(devices, cals_params.slice_mode, X, models, opt);
+  } else if (devices.size() == 1) {
     results[0] = detail::run_on_device(devices[0], X, models, opt);
   } else {
     std::vector<dim_t> ranks(models.size());

@@ -104,6 +104,10 @@ struct CalsParams {
 
   // extensions
   std::vector<int> devices{}; // CUDA ordinals to shard the model set over (X replicated); empty = {0}
+  // >= 0: instead of sharding the models, slice X along this mode over `devices` (a tensor too large for one GPU,
+  // BASELINE config 5): every device holds a slab of X and all models; partial MTTKRPs are combined over NVLink peer
+  // memory by the engine's exchange kernel.  -1 (default): replicate X, shard the models.
+  int slice_mode{-1};
   int timing{0};              // 1: bracket MTTKRP / update kernels with CUDA events (fills mttkrp_ms / update_ms)
 
   void print() const;

@@ -260,6 +260,44 @@ TEST(Cals, MttkrpOverMultiKtensorEqualsPerModelMttkrp) {
   }
 }
 
+// CalsParams::slice_mode: X sliced over two GPUs (needs two devices; skipped otherwise).
+TEST(Cals, SlicedTensorOverTwoDevicesEqualsSingleDevice) {
+  cals::Tensor probe(std::vector<dim_t>{4, 4, 4});
+  probe.zero();
+  Uniform u(31);
+  const std::vector<dim_t> modes{22, 26, 31};
+  Tensor T(modes);
+  T.fill(u.source());
+  std::vector<dim_t> ranks{2, 6, 3, 9};
+  std::vector<Ktensor> start = random_models(ranks, modes, u);
+  std::vector<Ktensor> one(start);
+  cals::CalsParams cp;
+  cp.max_iterations = 6;
+  cp.force_max_iter = true;
+  cp.buffer_size = 20;
+  auto q1 = queue_of(one);
+  cals::cp_cals(T, q1, cp);
+  for (int s : {2, 1}) {
+    std::vector<Ktensor> two(start);
+    cp.devices = {0, 1};
+    cp.slice_mode = s;
+    auto q2 = queue_of(two);
+    try {
+      cals::cp_cals(T, q2, cp);
+    } catch (const cals::B200Error &e) {
+      if (std::string(e.what()).find("out of range") != std::string::npos) {
+        std::cout << "[  SKIPPED ] needs two GPUs: " << e.what() << std::endl;
+        return;
+      }
+      throw;
+    }
+    for (size_t p = 0; p < ranks.size(); p++) {
+      EXPECT_NEAR(reconstruction_gap(one[p], two[p]), 0.0, 1e-9 * T.norm());
+      EXPECT_NEAR(one[p].get_fit(), two[p].get_fit(), 1e-9);
+    }
+  }
+}
+
 TEST(Cals, ReportDescribesTheRun) {
   Uniform u(3);
   const std::vector<dim_t> modes{16, 10, 12};
