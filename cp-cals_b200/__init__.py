@@ -22,6 +22,7 @@ LIB_PATH = os.environ.get("CALS_B200_LIB", os.path.join(HERE, "libcals_b200.so")
 
 FORCE_MAX_ITER = 1
 ALWAYS_EVICT_FIRST = 2
+NNLS = 4
 MTTKRP_DMMA = 0
 MTTKRP_NAIVE = 1
 
@@ -34,7 +35,8 @@ ABI_SYMBOLS = [
     "cals_b200_mttkrp", "cals_b200_device_info", "cals_b200_version", "cals_b200_fetch_iteration_cols",
     "cals_b200_host_alloc", "cals_b200_host_free", "cals_b200_stream",
     "cals_b200_comm_alloc", "cals_b200_comm_local_block", "cals_b200_comm_connect", "cals_b200_set_tensor_slab",
-    "cals_b200_set_tensor_norm", "cals_b200_comm_disconnect",
+    "cals_b200_set_tensor_norm", "cals_b200_comm_disconnect", "cals_b200_set_model_active_set",
+    "cals_b200_fetch_model_active_set",
 ]
 
 
@@ -102,6 +104,8 @@ def lib():
     L.cals_b200_set_tensor_slab.argtypes = [vp, i, C.POINTER(u64), i, C.POINTER(u64), vp]
     L.cals_b200_set_tensor_norm.argtypes = [vp, dbl]
     L.cals_b200_comm_disconnect.argtypes = [vp]
+    L.cals_b200_set_model_active_set.argtypes = [vp, i, C.POINTER(vp)]
+    L.cals_b200_fetch_model_active_set.argtypes = [vp, i, C.POINTER(vp)]
     _lib = L
     return L
 
@@ -120,6 +124,7 @@ class Ktensor:
     fit: float = 0.0
     old_fit: float = 0.0
     chol_info: int = 0
+    active_set: Optional[List[np.ndarray]] = None  # NNLS: per mode (I_n, R) bool, None = all constraints active
 
     @property
     def rank(self) -> int:
@@ -303,8 +308,9 @@ class Engine:
 
     # -- parameters ----------------------------------------------------------------------------------------------------
     def configure(self, buffer_cols: int, max_iterations: int, tol: float, force_max_iter=False,
-                  always_evict_first=False):
-        flags = (FORCE_MAX_ITER if force_max_iter else 0) | (ALWAYS_EVICT_FIRST if always_evict_first else 0)
+                  always_evict_first=False, nnls=False):
+        flags = ((FORCE_MAX_ITER if force_max_iter else 0) | (ALWAYS_EVICT_FIRST if always_evict_first else 0) |
+                 (NNLS if nnls else 0))
         self._ck(self._L.cals_b200_configure(self._ctx, buffer_cols, max_iterations, tol, flags))
 
     def set_timing(self, level: int):
@@ -352,6 +358,19 @@ class Engine:
         self._ck(self._L.cals_b200_fetch_model(self._ctx, model_id, ptrs, lam.ctypes.data, C.byref(st)))
         return fs, lam, st
 
+    def set_active_set(self, model_id: int, active: Sequence[np.ndarray]):
+        """active[n]: (I_n, R) bool/uint8, True = entry constrained to zero (Ktensor::active_set of the reference)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint8) for a in active]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        self._ck(self._L.cals_b200_set_model_active_set(self._ctx, model_id, ptrs))
+
+    def fetch_active_set(self, model_id: int):
+        R = self._ranks[model_id]
+        arrs = [np.empty((I, R), dtype=np.uint8) for I in self.modes]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        self._ck(self._L.cals_b200_fetch_model_active_set(self._ctx, model_id, ptrs))
+        return [a.astype(bool) for a in arrs]
+
     def fetch_all(self):
         """All models of the last run with ONE call through the C ABI: [(factors, lam, stats), ...] in queue order."""
         M, N = len(self._ranks), len(self.modes)
@@ -398,8 +417,8 @@ class Engine:
 
 # ---------------------------------------------------------------------------------------------------------------------
 def _check_params(params: CalsParams):
-    if params.update_method != "unconstrained":
-        raise CalsB200Error("update_method %r is not on the B200 path (only 'unconstrained'; NNLS is out of scope)"
+    if params.update_method not in ("unconstrained", "nnls"):
+        raise CalsB200Error("unknown update_method %r (reference include/utils/update.h:8: unconstrained | nnls)"
                             % (params.update_method,))
     if params.line_search:
         raise CalsB200Error("line search is not on the B200 path (reference default is off, include/cals.h:153)")
@@ -415,17 +434,24 @@ def cp_cals(X: np.ndarray, ktensors: Sequence[Ktensor], params: CalsParams, *, e
     try:
         if own or eng.modes is None or X is not None:
             eng.set_tensor(X)
+        nnls = params.update_method == "nnls"
         eng.configure(params.buffer_size, params.max_iterations, params.tol, params.force_max_iter,
-                      params.always_evict_first)
+                      params.always_evict_first, nnls)
         eng.set_timing(timing)
         eng.set_mttkrp_variant(mttkrp_variant)
         eng.clear_models()
         for kt in ktensors:
             eng.enqueue(kt.factors, kt.jk_mode, kt.jk_fiber)
+        if nnls:  # active sets persist in the Ktensor across calls (reference include/ktensor.h:36)
+            for i, kt in enumerate(ktensors):
+                if kt.active_set is not None:
+                    eng.set_active_set(i, kt.active_set)
         rep = eng.run()
-        for kt, (fs, lam, st) in zip(ktensors, eng.fetch_all()):
+        for i, (kt, (fs, lam, st)) in enumerate(zip(ktensors, eng.fetch_all())):
             kt.factors, kt.lam = fs, lam
             kt.iters, kt.error, kt.fit, kt.old_fit, kt.chol_info = st.iters, st.error, st.fit, st.old_fit, st.chol_info
+            if nnls:
+                kt.active_set = eng.fetch_active_set(i)
         return CalsReport(n_modes=X.ndim, modes=tuple(X.shape), X_norm=rep.x_norm, iter=rep.iter,
                           max_iter=params.max_iterations, buffer_size=params.buffer_size, n_ktensors=rep.n_ktensors,
                           ktensor_comp_sum=rep.ktensor_comp_sum, tol=params.tol, total_time=rep.total_time,

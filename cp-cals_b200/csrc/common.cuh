@@ -20,6 +20,7 @@ struct ModelDesc {
   int jk_mode; // -1: regular
   int jk_fiber;
   long long gram_off; // doubles; n_modes matrices of rank*rank, mode-major
+  long long act_off;  // bytes into the active-set pool (NNLS): per mode an I_n x rank block, row-major
   int state;
   int col;
   int iters;

@@ -100,6 +100,9 @@ struct cals_b200_ctx {
   SchedState *d_st = nullptr;
   int *d_live = nullptr, *d_live_tmp = nullptr, *d_gather = nullptr, *d_evict = nullptr;
   double *d_gram = nullptr, *d_lambda = nullptr;
+  unsigned char *d_active = nullptr;       // NNLS active sets of all queued models (ModelDesc::act_off)
+  std::vector<unsigned char> h_active;     // host image: all 1 unless set through cals_b200_set_model_active_set
+  long long active_bytes = 0;
   int *h_flags = nullptr, *d_flags = nullptr;
   unsigned *d_iter_cols = nullptr; // [ITER_LOG_CAP]
   unsigned long long last_global_iter = 0;
@@ -442,6 +445,7 @@ void release_run(cals_b200_ctx *c) {
   c->d_models = nullptr;
   c->d_live = c->d_live_tmp = c->d_gather = c->d_evict = nullptr;
   c->d_gram = c->d_lambda = nullptr;
+  c->d_active = nullptr;
   c->uploaded = false;
   c->run_sig.clear();
 }
@@ -615,7 +619,9 @@ int prepare_run(cals_b200_ctx *c) {
 
   c->hdesc.assign(M, ModelDesc{});
   int col = 0, max_rank = 0;
-  long long goff = 0;
+  long long goff = 0, aoff = 0, sum_rows = 0;
+  for (int n = 0; n < N; n++)
+    sum_rows += geo.dims[n];
   for (int m = 0; m < M; m++) {
     const HostModel &hm = c->hmodels[m];
     if (hm.rank > c->buffer_cols)
@@ -628,14 +634,19 @@ int prepare_run(cals_b200_ctx *c) {
     d.jk_mode = hm.jk_mode;
     d.jk_fiber = hm.jk_fiber;
     d.gram_off = goff;
+    d.act_off = aoff;
     d.state = MODEL_QUEUED;
     col += hm.rank;
     goff += (long long)N * hm.rank * hm.rank;
+    aoff += sum_rows * hm.rank;
     max_rank = std::max(max_rank, hm.rank);
   }
   c->total_cols = col;
   c->max_rank = max_rank;
   c->gram_doubles = goff;
+  c->active_bytes = aoff;
+  if ((long long)c->h_active.size() != aoff)
+    c->h_active.assign((size_t)aoff, 1); // fresh models: every constraint active (reference include/ktensor.h:66)
 
   if (!reuse) {
     if (alloc_buffers(c, c->bufs, c->buffer_cols, true, c->total_cols))
@@ -645,6 +656,7 @@ int prepare_run(cals_b200_ctx *c) {
         dev_alloc(c, &c->d_gather, (size_t)c->buffer_cols, c->run_allocs) ||
         dev_alloc(c, &c->d_evict, (size_t)c->buffer_cols, c->run_allocs) ||
         dev_alloc(c, &c->d_gram, (size_t)goff, c->run_allocs) ||
+        dev_alloc(c, &c->d_active, (size_t)aoff, c->run_allocs) ||
         dev_alloc(c, &c->d_lambda, (size_t)c->total_cols, c->run_allocs))
       return 1;
     for (int n = 0; n < N; n++)
@@ -712,6 +724,9 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     CU_TRY(c, cudaMemcpyAsync(&c->d_st->x_norm, c->d_norm, 8, cudaMemcpyDeviceToDevice, s));
   c->h_flags[0] = c->h_flags[1] = c->h_flags[2] = 0;
 
+  if ((c->flags & CALS_B200_NNLS) && c->active_bytes > 0)
+    CU_TRY(c, cudaMemcpyAsync(c->d_active, c->h_active.data(), (size_t)c->active_bytes, cudaMemcpyHostToDevice, s));
+
   init_grams_kernel<<<dim3(M, N), 256, 0, s>>>(geo, b.fac, c->d_models, c->d_gram);
 
   SchedParams sp{c->d_st,    c->d_models, c->d_live, c->d_live_tmp,  c->d_gather,
@@ -729,8 +744,18 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     u.rows = geo.dims[n];
     u.ld = geo.ldF[n];
     const int R = c->max_rank;
-    const size_t fixed = ((size_t)2 * R * R + 2 * R + 32) * 8;
+    size_t fixed = ((size_t)2 * R * R + 2 * R + 32) * 8;
     const size_t budget = 200 * 1024;
+    u.nnls = (c->flags & CALS_B200_NNLS) ? 1 : 0;
+    u.nnls_warps = 0;
+    if (u.nnls) { // per working warp: 5R + R*R doubles and 2R + 1 ints of scratch
+      const size_t per_warp = ((size_t)5 * R + (size_t)R * R + (size_t)(2 * R + 2) / 2 + 1) * 8;
+      int nw = UPDATE_THREADS / 32;
+      while (nw > 1 && fixed + nw * per_warp + (size_t)33 * R * 8 > budget)
+        nw >>= 1;
+      u.nnls_warps = nw;
+      fixed += nw * per_warp;
+    }
     if (fixed + (size_t)33 * R * 8 > budget)
       return fail(c, "rank %d too large for the shared-memory update kernel", R);
     int cr = round_up_int(u.rows, 32);
@@ -748,6 +773,10 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     u.models = c->d_models;
     u.live = c->d_live;
     u.st = c->d_st;
+    u.act_pool = c->d_active;
+    u.rows_before = 0;
+    for (int k = 0; k < n; k++)
+      u.rows_before += geo.dims[k];
     up_smem[n] = fixed + (size_t)(cr + 1) * R * 8;
   }
   {
@@ -755,7 +784,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     for (int n = 0; n < N; n++)
       mx = std::max(mx, up_smem[n]);
     if (mx > c->update_attr_smem) {
-      CU_TRY(c, cudaFuncSetAttribute(model_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+      CU_TRY(c, cudaFuncSetAttribute(model_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+      CU_TRY(c, cudaFuncSetAttribute(model_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
       c->update_attr_smem = mx;
     }
   }
@@ -821,7 +851,10 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
         timed.push_back({ev_next + 1, 1});
         ev_next += 2;
       }
-      model_update_kernel<<<max_live, UPDATE_THREADS, up_smem[n], s>>>(up[n]);
+      if (up[n].nnls)
+        model_update_kernel<true><<<max_live, UPDATE_THREADS, up_smem[n], s>>>(up[n]);
+      else
+        model_update_kernel<false><<<max_live, UPDATE_THREADS, up_smem[n], s>>>(up[n]);
       launches++;
       if (c->timing) {
         cudaEventRecord(get_event(c, ev_next), s);
@@ -1184,6 +1217,7 @@ int cals_b200_clear_models(cals_b200_ctx *c) {
     return 1;
   c->hmodels.clear();
   c->hdesc.clear();
+  c->h_active.clear();
   c->queued_cols = 0;
   c->uploaded = false;
   c->results_fresh = false;
@@ -1289,6 +1323,57 @@ int cals_b200_fetch_all(cals_b200_ctx *c, double *const *factors_out, double *co
   for (int m = 0; m < (int)c->hdesc.size(); m++)
     copy_model_out(c, m, factors_out ? factors_out + (size_t)m * N : nullptr, lambda_out ? lambda_out[m] : nullptr,
                    stats ? stats + m : nullptr);
+  return 0;
+}
+
+// Layout shared by both calls: active[n] -> I_n x rank bytes, row-major (byte [row * rank + col]), 1 = constrained.
+static long long model_act_offset(cals_b200_ctx *c, int model_id, long long *sum_rows_out) {
+  long long sum_rows = 0, off = 0;
+  for (int n = 0; n < c->geo.n_modes; n++)
+    sum_rows += c->geo.dims[n];
+  for (int m = 0; m < model_id; m++)
+    off += sum_rows * c->hmodels[m].rank;
+  *sum_rows_out = sum_rows;
+  return off;
+}
+
+int cals_b200_set_model_active_set(cals_b200_ctx *c, int model_id, const uint8_t *const *active) {
+  if (!c || !active)
+    return fail(c, "null argument");
+  if (model_id < 0 || model_id >= (int)c->hmodels.size())
+    return fail(c, "model id %d out of range", model_id);
+  long long sum_rows = 0, total = 0;
+  const long long off = model_act_offset(c, model_id, &sum_rows);
+  for (auto &hm : c->hmodels)
+    total += sum_rows * hm.rank;
+  if ((long long)c->h_active.size() != total) { // models queued since the last sizing: extend with "all active"
+    c->h_active.resize((size_t)total, 1);
+  }
+  long long o = off;
+  for (int n = 0; n < c->geo.n_modes; n++) {
+    const long long cnt = (long long)c->geo.dims[n] * c->hmodels[model_id].rank;
+    if (!active[n])
+      return fail(c, "active set of mode %d is null", n);
+    memcpy(&c->h_active[(size_t)o], active[n], (size_t)cnt);
+    o += cnt;
+  }
+  return 0;
+}
+
+int cals_b200_fetch_model_active_set(cals_b200_ctx *c, int model_id, uint8_t *const *active_out) {
+  if (!c || !active_out)
+    return fail(c, "null argument");
+  if (model_id < 0 || model_id >= (int)c->hdesc.size() || !c->uploaded || !c->d_active)
+    return fail(c, "no run to fetch the active set of model %d from", model_id);
+  cudaSetDevice(c->device);
+  long long sum_rows = 0;
+  long long o = model_act_offset(c, model_id, &sum_rows);
+  for (int n = 0; n < c->geo.n_modes; n++) {
+    const long long cnt = (long long)c->geo.dims[n] * c->hmodels[model_id].rank;
+    if (active_out[n])
+      CU_TRY(c, cudaMemcpy(active_out[n], c->d_active + o, (size_t)cnt, cudaMemcpyDeviceToHost));
+    o += cnt;
+  }
   return 0;
 }
 

@@ -39,6 +39,11 @@ struct UpdateParams {
   ModelDesc *models;
   const int *live;
   SchedState *st;
+  // non-negative update (update_method == NNLS)
+  int nnls;                 // 0: Cholesky solve, 1: row-wise active-set NNLS
+  int nnls_warps;           // warps of the CTA that work on rows (each owns a scratch block in shared memory)
+  int rows_before;          // sum of the extents of the modes below this one (offset into a model's active sets)
+  unsigned char *act_pool;  // per model: for every mode an I_n x R block, row-major, 1 = constrained to zero
 };
 
 __device__ __forceinline__ double block_sum(double v, double *scratch) {
@@ -66,6 +71,242 @@ __device__ __forceinline__ double block_sum(double v, double *scratch) {
   return t;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Row-wise active-set NNLS: update::update_factor_non_negative_constrained (reference src/utils/update.cpp:61-176),
+// one warp per factor row, everything in shared memory.  Scratch per warp (doubles): y d w s sp [5R], Gp [R*R];
+// ints: act [R], map [R+1].
+struct NnlsScratch {
+  double *y, *d, *w, *s, *sp, *Gp;
+  int *act, *map;
+};
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Solve H_pp x = y_p for the passive set (dposv('L'), reference src/utils/update.cpp:18-46).  Returns the size of the
+// passive set, or -1 when the Cholesky meets a non-positive pivot (CholFail).
+__device__ int nnls_solve_passive(const double *H, int R, const NnlsScratch &q, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    int p = 0;
+    for (int i = 0; i < R; i++)
+      if (!q.act[i])
+        q.map[p++] = i;
+    q.map[R] = p;
+  }
+  __syncwarp();
+  const int p = q.map[R];
+  double *Gp = q.Gp, *sp = q.sp;
+  for (int e = lane; e < p * p; e += 32) {
+    const int a = e % p, b = e / p;
+    Gp[a + b * p] = H[q.map[a] + q.map[b] * R];
+  }
+  for (int a = lane; a < p; a += 32)
+    sp[a] = q.y[q.map[a]];
+  __syncwarp();
+  for (int j = 0; j < p; j++) {
+    const double dj = Gp[j + j * p];
+    if (!(dj > 0.0))
+      return -1; // warp-uniform: every lane read the same value
+    const double sd = sqrt(dj);
+    __syncwarp();
+    if (lane == 0)
+      Gp[j + j * p] = sd;
+    for (int i = j + 1 + lane; i < p; i += 32)
+      Gp[i + j * p] /= sd;
+    __syncwarp();
+    const int t = p - j - 1;
+    for (int e = lane; e < t * t; e += 32) {
+      const int i = j + 1 + e % t, k = j + 1 + e / t;
+      if (k <= i)
+        Gp[i + k * p] -= Gp[i + j * p] * Gp[k + j * p];
+    }
+    __syncwarp();
+  }
+  for (int j = 0; j < p; j++) { // L z = y_p
+    const double z = sp[j] / Gp[j + j * p];
+    __syncwarp();
+    if (lane == 0)
+      sp[j] = z;
+    for (int i = j + 1 + lane; i < p; i += 32)
+      sp[i] -= Gp[i + j * p] * z;
+    __syncwarp();
+  }
+  for (int j = p - 1; j >= 0; j--) { // L^T x = z
+    const double x = sp[j] / Gp[j + j * p];
+    __syncwarp();
+    if (lane == 0)
+      sp[j] = x;
+    for (int i = lane; i < j; i += 32)
+      sp[i] -= Gp[j + i * p] * x;
+    __syncwarp();
+  }
+  return p;
+}
+
+__device__ __forceinline__ void nnls_scatter(double *dst, int R, int p, const NnlsScratch &q, int lane) {
+  for (int i = lane; i < R; i += 32)
+    dst[i] = 0.0;
+  __syncwarp();
+  for (int a = lane; a < p; a += 32)
+    dst[q.map[a]] = q.sp[a];
+  __syncwarp();
+}
+__device__ __forceinline__ double nnls_min_sp(int p, const NnlsScratch &q, int lane) {
+  double m = 1.7976931348623157e308;
+  for (int a = lane; a < p; a += 32)
+    m = fmin(m, q.sp[a]);
+  return warp_min(m);
+}
+__device__ __forceinline__ int nnls_count_passive(int R, const NnlsScratch &q, int lane) {
+  int n = 0;
+  for (int i = lane; i < R; i += 32)
+    n += !q.act[i];
+  return warp_sum_int(n);
+}
+__device__ __forceinline__ void nnls_multipliers(const double *H, int R, const NnlsScratch &q, int lane) {
+  for (int i = lane; i < R; i += 32) { // w = y - H d   (reference src/utils/update.cpp:49-57)
+    double t = 0.0;
+    for (int j = 0; j < R; j++)
+      t += H[i + j * R] * q.d[j];
+    q.w[i] = q.y[i] - t;
+  }
+  __syncwarp();
+}
+
+// One row: y = the row of the MTTKRP result in S (pitch `pitch`), result written back to S, active set updated in
+// `arow` (global memory).  Returns 1 when a passive-block Cholesky failed inside the main loop or an iteration cap was
+// hit (the reference has no caps; they only guard the GPU against a non-terminating corner case).
+__device__ int nnls_row(const double *H, int R, double tol, double *Srow, int pitch, unsigned char *arow,
+                        const NnlsScratch &q, int lane) {
+  int any = 0;
+  for (int i = lane; i < R; i += 32) {
+    const double yi = Srow[i * pitch];
+    int a = arow[i];
+    if (yi > 0.0)
+      a = 0;
+    q.y[i] = yi;
+    q.d[i] = 0.0;
+    q.act[i] = a;
+    any |= !a;
+  }
+  any = __any_sync(0xffffffffu, any);
+  __syncwarp();
+  int p = 0;
+  if (any) { // warm start from the previous active set (reference :88-117)
+    p = nnls_solve_passive(H, R, q, lane);
+    bool failed = p < 0;
+    for (int guard = 0; !failed; guard++) {
+      nnls_scatter(q.d, R, p, q, lane);
+      if (!(nnls_min_sp(p, q, lane) <= tol))
+        break;
+      for (int i = lane; i < R; i += 32)
+        if (q.d[i] <= tol) {
+          q.d[i] = 0.0;
+          q.act[i] = 1;
+        }
+      __syncwarp();
+      if (nnls_count_passive(R, q, lane) == 0 || guard > 2 * R) {
+        failed = true;
+        break;
+      }
+      p = nnls_solve_passive(H, R, q, lane);
+      failed = p < 0;
+    }
+    if (failed) {
+      for (int i = lane; i < R; i += 32) {
+        q.act[i] = 1;
+        q.d[i] = 0.0;
+      }
+      __syncwarp();
+    }
+  }
+  nnls_multipliers(H, R, q, lane);
+  int trouble = 0;
+  for (int outer = 0;; outer++) { // main loop (reference :122-170)
+    double best = -1.7976931348623157e308;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < R; i += 32)
+      if (q.act[i] && q.w[i] > best) { // strictly greater: the first index of the maximum within this lane's sequence
+        best = q.w[i];
+        bi = i;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    if (bi == 0x7fffffff || !(best > tol))
+      break;
+    if (outer > 3 * R) {
+      trouble = 1;
+      break;
+    }
+    if (lane == 0)
+      q.act[bi] = 0;
+    p = nnls_solve_passive(H, R, q, lane);
+    if (p < 0) {
+      trouble = 1;
+      break;
+    }
+    bool bad = false;
+    for (int inner = 0; nnls_min_sp(p, q, lane) <= tol; inner++) { // inner loop (reference :131-155)
+      nnls_scatter(q.s, R, p, q, lane);
+      double alpha = 1.7976931348623157e308;
+      for (int i = lane; i < R; i += 32)
+        if (!q.act[i] && q.s[i] <= tol)
+          alpha = fmin(alpha, q.d[i] / (q.d[i] - q.s[i]));
+      alpha = warp_min(alpha);
+      for (int i = lane; i < R; i += 32) {
+        const double di = q.d[i] + alpha * (q.s[i] - q.d[i]);
+        q.d[i] = di;
+        if (fabs(di) < tol && !q.act[i]) {
+          q.act[i] = 1;
+          q.d[i] = 0.0;
+        }
+      }
+      __syncwarp();
+      if (nnls_count_passive(R, q, lane) == 0 || inner > 3 * R) {
+        bad = true;
+        break;
+      }
+      p = nnls_solve_passive(H, R, q, lane);
+      if (p < 0) {
+        bad = true;
+        break;
+      }
+    }
+    if (bad) {
+      trouble = 1;
+      break;
+    }
+    nnls_scatter(q.d, R, p, q, lane);
+    nnls_multipliers(H, R, q, lane);
+  }
+  for (int i = lane; i < R; i += 32) {
+    Srow[i * pitch] = q.d[i];
+    arow[i] = (unsigned char)q.act[i];
+  }
+  __syncwarp();
+  return trouble;
+}
+
+template <bool NNLS>
 __global__ void __launch_bounds__(UPDATE_THREADS)
 model_update_kernel(const UpdateParams p) {
   SchedState *st = p.st;
@@ -85,6 +326,8 @@ model_update_kernel(const UpdateParams p) {
   double *red = cstat + 2 * R;     // 32
   double *S = red + 32;            // chunk_rows x R, pitch chunk_pitch
   const int pitch = p.chunk_pitch, CR = p.chunk_rows;
+  // NNLS scratch (only allocated when p.nnls): per working warp 5R + R*R doubles and 2R + 1 ints, behind S
+  double *nn_base = S + (size_t)pitch * p.max_rank;
 
   double *grams = p.gram_pool + md.gram_off;
   const double *Gm = p.G + (size_t)col * ld;
@@ -106,9 +349,30 @@ model_update_kernel(const UpdateParams p) {
     for (int e = tid; e < R; e += nthr)
       cstat[e] = 0.0;
 
-  // ---- Cholesky, right-looking, in shared memory ----
+  // ---- Cholesky, right-looking, in shared memory (unconstrained update only; NNLS needs H itself) ----
   int chol_fail = 0;
-  for (int j = 0; j < R; j++) {
+  double nnls_tol = 0.0;
+  if (NNLS) { // tol = 10 * eps * ||H||_1 * R   (reference src/utils/update.cpp:65-66; one_norm = max column sum)
+    double mx = -1.0;
+    for (int j = tid; j < R; j += nthr) {
+      double cs = 0.0;
+      for (int i = 0; i < R; i++)
+        cs += fabs(Hs[i + j * R]);
+      mx = fmax(mx, cs);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0)
+      red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int wv = 1; wv < (nthr >> 5); wv++)
+      mx = fmax(mx, red[wv]);
+    nnls_tol = 10 * 2.2204e-16 * mx * (double)R;
+    __syncthreads();
+  }
+  for (int j = 0; j < (NNLS ? 0 : R); j++) {
     __syncthreads();
     const double d = Hs[j + j * R];
     if (!(d > 0.0))
@@ -143,27 +407,52 @@ model_update_kernel(const UpdateParams p) {
       S[rr + j * pitch] = Gm[(size_t)j * ld + r0 + rr];
     }
     __syncthreads();
-    for (int rr = tid; rr < nr; rr += nthr) {
-      double *row = S + rr;
-      // y L^T = g   (forward, right-looking)
-      for (int j = 0; j < R; j++) {
-        const double y = row[j * pitch] / Hs[j + j * R];
-        row[j * pitch] = y;
-        for (int k = j + 1; k < R; k++)
-          row[k * pitch] -= y * Hs[k + j * R];
+    if (NNLS) { // warp per row, active sets warm-started from the previous iteration
+      const int warp = tid >> 5, lane = tid & 31;
+      if (warp < p.nnls_warps) {
+        const size_t per_warp = (size_t)5 * R + (size_t)R * R + (size_t)(2 * R + 2) / 2 + 1; // doubles
+        double *wb = nn_base + per_warp * warp;
+        NnlsScratch q;
+        q.y = wb;
+        q.d = wb + R;
+        q.w = wb + 2 * R;
+        q.s = wb + 3 * R;
+        q.sp = wb + 4 * R;
+        q.Gp = wb + 5 * R;
+        q.act = reinterpret_cast<int *>(wb + 5 * R + (size_t)R * R);
+        q.map = q.act + R;
+        unsigned char *act = p.act_pool + md.act_off + (size_t)p.rows_before * R;
+        int trouble = 0;
+        for (int rr = warp; rr < nr; rr += p.nnls_warps)
+          trouble += nnls_row(Hs, R, nnls_tol, S + rr, pitch, act + (size_t)(r0 + rr) * R, q, lane);
+        if (trouble && lane == 0)
+          chol_fail = 1;
       }
-      // x L = y     (backward, right-looking)
-      for (int j = R - 1; j >= 0; j--) {
-        const double x = row[j * pitch] / Hs[j + j * R];
-        row[j * pitch] = x;
-        for (int k = 0; k < j; k++)
-          row[k * pitch] -= x * Hs[j + k * R];
+    } else {
+      for (int rr = tid; rr < nr; rr += nthr) {
+        double *row = S + rr;
+        // y L^T = g   (forward, right-looking)
+        for (int j = 0; j < R; j++) {
+          const double y = row[j * pitch] / Hs[j + j * R];
+          row[j * pitch] = y;
+          for (int k = j + 1; k < R; k++)
+            row[k * pitch] -= y * Hs[k + j * R];
+        }
+        // x L = y     (backward, right-looking)
+        for (int j = R - 1; j >= 0; j--) {
+          const double x = row[j * pitch] / Hs[j + j * R];
+          row[j * pitch] = x;
+          for (int k = 0; k < j; k++)
+            row[k * pitch] -= x * Hs[j + k * R];
+        }
       }
-      if (jk_here && r0 + rr == jk_row)
-        for (int j = 0; j < R; j++)
-          row[j * pitch] *= 0.0;
     }
     __syncthreads();
+    if (jk_here && jk_row >= r0 && jk_row < r0 + nr) { // Ktensor::set_jk_fiber(0.0)
+      for (int j = tid; j < R; j += nthr)
+        S[(jk_row - r0) + j * pitch] *= 0.0;
+      __syncthreads();
+    }
     // column statistics: warp per column
     {
       const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
@@ -257,7 +546,7 @@ model_update_kernel(const UpdateParams p) {
   __syncthreads();
   for (int e = tid; e < R * R; e += nthr)
     grams[(size_t)n * R * R + e] = Gs[e];
-  if (tid == 0 && chol_fail)
+  if (__syncthreads_or(chol_fail) && tid == 0)
     md.chol_info += 1;
 
   if (!last_mode)

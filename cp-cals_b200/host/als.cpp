@@ -16,8 +16,8 @@
 namespace cals {
 
 static AlsReport run_single(const Tensor &X, Ktensor &ktensor, AlsParams &p, bool may_skip_upload) {
-  if (p.update_method != update::UNCONSTRAINED)
-    throw B200Error("cp_als: update method 'nnls' is not on the B200 path; there is no CPU fallback");
+  if (p.update_method != update::UNCONSTRAINED && p.update_method != update::NNLS)
+    throw B200Error("cp_als: unknown update method");
   if (p.line_search)
     throw B200Error("cp_als: line search is not on the B200 path; there is no CPU fallback");
   if (X.get_n_modes() < 3)
@@ -46,6 +46,7 @@ static AlsReport run_single(const Tensor &X, Ktensor &ktensor, AlsParams &p, boo
   opt.max_iterations = p.max_iterations;
   opt.tol = p.tol;
   opt.force_max_iter = p.force_max_iter;
+  opt.nnls = p.update_method == update::NNLS;
   opt.skip_upload_if_resident = may_skip_upload;
   std::vector<Ktensor *> one{&ktensor};
   const detail::RunResult r = detail::run_on_device(p.device, X, one, opt);

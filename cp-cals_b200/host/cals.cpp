@@ -72,7 +72,8 @@ RunResult run_on_device(int device, const Tensor &X, const std::vector<Ktensor *
     return out;
   upload_tensor(e, X, opt.skip_upload_if_resident);
   const unsigned flags = (opt.force_max_iter ? CALS_B200_FORCE_MAX_ITER : 0u) |
-                         (opt.always_evict_first ? CALS_B200_ALWAYS_EVICT_FIRST : 0u);
+                         (opt.always_evict_first ? CALS_B200_ALWAYS_EVICT_FIRST : 0u) |
+                         (opt.nnls ? CALS_B200_NNLS : 0u);
   // A buffer wider than the whole queue behaves exactly like one that just holds it (everything is admitted at once),
   // so the device buffers are sized by what can actually be resident.
   dim_t sum_ranks = 0;
@@ -99,6 +100,29 @@ RunResult run_on_device(int device, const Tensor &X, const std::vector<Ktensor *
                                   kt->is_jk() ? (int64_t)kt->get_jk_fiber() : 0, &id),
           "cals_b200_enqueue_model");
   }
+  if (opt.nnls) { // warm-start active sets live in the Ktensor (reference include/ktensor.h:36); fresh ones are all-true
+    std::vector<std::vector<uint8_t>> bytes(N);
+    std::vector<const uint8_t *> ptrs(N);
+    for (size_t m = 0; m < models.size(); m++) {
+      Ktensor *kt = models[m];
+      bool fresh = true;
+      for (dim_t n = 0; n < N && fresh; n++)
+        for (const auto &row : kt->get_active_set(n))
+          for (bool a : row)
+            fresh = fresh && a;
+      if (fresh)
+        continue;
+      for (dim_t n = 0; n < N; n++) {
+        const auto &as = kt->get_active_set(n);
+        bytes[n].assign(as.size() * kt->get_components(), 1);
+        for (size_t r = 0; r < as.size(); r++)
+          for (size_t c = 0; c < as[r].size(); c++)
+            bytes[n][r * kt->get_components() + c] = as[r][c] ? 1 : 0;
+        ptrs[n] = bytes[n].data();
+      }
+      check(e, cals_b200_set_model_active_set(e.ctx, (int)m, ptrs.data()), "cals_b200_set_model_active_set");
+    }
+  }
   check(e, cals_b200_run(e.ctx, &out.rep), "cals_b200_run");
 
   // results straight into the callers' storage (Ktensor::detach of the reference, src/ktensor.cpp:127-135)
@@ -115,6 +139,24 @@ RunResult run_on_device(int device, const Tensor &X, const std::vector<Ktensor *
     models[m]->set_iters(static_cast<dim_t>(stats[m].iters));
     models[m]->set_approximation_error(stats[m].error);
     models[m]->set_fit(stats[m].fit, stats[m].old_fit);
+  }
+  if (opt.nnls) {
+    std::vector<std::vector<uint8_t>> bytes(N);
+    std::vector<uint8_t *> ptrs(N);
+    for (size_t m = 0; m < M; m++) {
+      Ktensor *kt = models[m];
+      for (dim_t n = 0; n < N; n++) {
+        bytes[n].resize(kt->get_factor(n).get_rows() * kt->get_components());
+        ptrs[n] = bytes[n].data();
+      }
+      check(e, cals_b200_fetch_model_active_set(e.ctx, (int)m, ptrs.data()), "cals_b200_fetch_model_active_set");
+      for (dim_t n = 0; n < N; n++) {
+        auto &as = kt->get_active_set(n);
+        for (size_t r = 0; r < as.size(); r++)
+          for (size_t c = 0; c < as[r].size(); c++)
+            as[r][c] = bytes[n][r * kt->get_components() + c] != 0;
+      }
+    }
   }
   uint64_t n_it = 0;
   check(e, cals_b200_fetch_iteration_cols(e.ctx, nullptr, 0, &n_it), "cals_b200_fetch_iteration_cols");
@@ -208,7 +250,8 @@ static RunResult run_sliced(const std::vector<int> &devices, int slice_mode, con
     sumsq += nrm * nrm;
   }
   const unsigned flags = (opt.force_max_iter ? CALS_B200_FORCE_MAX_ITER : 0u) |
-                         (opt.always_evict_first ? CALS_B200_ALWAYS_EVICT_FIRST : 0u);
+                         (opt.always_evict_first ? CALS_B200_ALWAYS_EVICT_FIRST : 0u) |
+                         (opt.nnls ? CALS_B200_NNLS : 0u);
   std::vector<const double *> in(N);
   for (size_t r = 0; r < W; r++) {
     check(*eng[r], cals_b200_set_tensor_norm(eng[r]->ctx, std::sqrt(sumsq)), "cals_b200_set_tensor_norm");
@@ -282,9 +325,8 @@ std::vector<std::vector<size_t>> shard_models(const std::vector<dim_t> &ranks, s
 
 // ---------------------------------------------------------------------------------------------------------------------
 static void reject_unsupported(update::UPDATE_METHOD um, bool line_search, const char *who) {
-  if (um != update::UNCONSTRAINED)
-    throw B200Error(std::string(who) + ": update method '" + update::update_method_names[um] +
-                    "' is not on the B200 path (only 'unconstrained'); there is no CPU fallback");
+  if (um != update::UNCONSTRAINED && um != update::NNLS)
+    throw B200Error(std::string(who) + ": unknown update method");
   if (line_search)
     throw B200Error(std::string(who) + ": line search is not on the B200 path; there is no CPU fallback");
 }
@@ -326,6 +368,7 @@ CalsReport cp_cals(const Tensor &X, KtensorQueue &kt_queue, CalsParams &cals_par
   opt.tol = cals_params.tol;
   opt.force_max_iter = cals_params.force_max_iter;
   opt.always_evict_first = cals_params.always_evict_first;
+  opt.nnls = cals_params.update_method == update::NNLS;
   opt.timing = cals_params.timing;
 
   std::vector<int> devices = cals_params.devices.empty() ? std::vector<int>{0} : cals_params.devices;

@@ -37,6 +37,7 @@ struct RunOptions {
   double tol{1e-7};
   bool force_max_iter{false};
   bool always_evict_first{false};
+  bool nnls{false}; // update_method == NNLS
   int timing{0};
   bool skip_upload_if_resident{false};
 };

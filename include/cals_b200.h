@@ -28,6 +28,9 @@ typedef struct cals_b200_ctx cals_b200_ctx;
 /* flags for cals_b200_configure (CalsParams::force_max_iter / always_evict_first, reference include/cals.h:158-159) */
 #define CALS_B200_FORCE_MAX_ITER 1u
 #define CALS_B200_ALWAYS_EVICT_FIRST 2u
+/* CalsParams::update_method == NNLS (reference include/utils/update.h:8, src/utils/update.cpp:61-176): non-negative
+ * factors by a row-wise active-set solve instead of the Cholesky solve */
+#define CALS_B200_NNLS 4u
 
 /* MTTKRP kernel variants (test hook / tuning knob; the product default is CALS_B200_MTTKRP_DMMA) */
 #define CALS_B200_MTTKRP_DMMA 0  /* TMA + mbarrier pipeline, FP64 tensor-core mma.sync, stream-K partials */
@@ -124,6 +127,12 @@ int cals_b200_fetch_model(cals_b200_ctx *ctx, int model_id, double *const *facto
 /* All models at once: factors_out[model*n_modes + n]; lambda_out[model]; stats[model]. Any pointer may be NULL. */
 int cals_b200_fetch_all(cals_b200_ctx *ctx, double *const *factors_out, double *const *lambda_out,
                         cals_b200_model_stats *stats);
+
+/* ---- NNLS active sets (Ktensor::active_set, reference include/ktensor.h:36; they persist across calls there) ---- */
+/* active[n] / active_out[n] -> I_n x rank bytes, row-major (byte [row * rank + col]); 1 = the entry is constrained
+ * to zero.  Models start with every constraint active unless set here after enqueueing; fetch after a run. */
+int cals_b200_set_model_active_set(cals_b200_ctx *ctx, int model_id, const uint8_t *const *active);
+int cals_b200_fetch_model_active_set(cals_b200_ctx *ctx, int model_id, uint8_t *const *active_out);
 
 /* ---- single-operation hooks (parity tests against the oracle; also the reference's unit seams) ----------------- */
 int cals_b200_tensor_norm(cals_b200_ctx *ctx, double *norm_out);

@@ -1,5 +1,6 @@
-// Factor-update options (reference include/utils/update.h:6-20).  Only UNCONSTRAINED exists on the B200 path
-// (batched Cholesky solve inside model_update_kernel, cp-cals_b200/csrc/update.cuh); NNLS is rejected loudly.
+// Factor-update options (reference include/utils/update.h:6-20).  Both run inside model_update_kernel
+// (cp-cals_b200/csrc/update.cuh): UNCONSTRAINED = batched Cholesky solve, NNLS = row-wise active-set solve with the
+// active sets kept in Ktensor::active_set between calls, as in the reference (src/utils/update.cpp:61-176).
 #ifndef CALS_B200_UTILS_UPDATE_H
 #define CALS_B200_UTILS_UPDATE_H
 

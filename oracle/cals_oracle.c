@@ -33,6 +33,9 @@ typedef struct {
   double fit;       /* out */
   double old_fit;   /* out */
   int64_t chol_fail; /* out: number of non-positive Cholesky pivots met (reference only logs dpotrf info) */
+  unsigned char *active; /* NNLS only, in/out, may be NULL (= all constraints active, a fresh Ktensor): per mode an
+                          * I_n x R block, row-major [row * R + col], 1 = constrained to zero (reference
+                          * include/ktensor.h:36 active_set) */
 } cals_oracle_model;
 
 typedef struct {
@@ -198,6 +201,173 @@ static void solve_in_place(double *F, int64_t rows, int64_t R, const double *Lm)
   }
 }
 
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * update::update_factor_non_negative_constrained (src/utils/update.cpp:61-176): row-wise active-set NNLS
+ * (Bro & de Jong's fast NNLS on the normal equations), warm-started from the active set of the previous iteration.
+ * F holds the MTTKRP result G on entry (rows x R, ld = rows), H is the Hadamard product of the other Gramians
+ * (R x R, NOT factored), active is rows x R row-major.  dposv('L') (src/utils/update.cpp:40) is restated as an
+ * unblocked Cholesky + two triangular solves.  Returns the number of rows on which a Cholesky of a passive block
+ * failed inside the main loop (the reference would terminate on the uncaught CholFail there). */
+static int nnls_solve_passive(const double *H, int64_t R, const double *y, const unsigned char *act, double *Gp,
+                              double *sp, int64_t *map, int64_t *p_out) {
+  int64_t p = 0;
+  for (int64_t i = 0; i < R; i++)
+    if (!act[i])
+      map[p++] = i;
+  *p_out = p;
+  for (int64_t a = 0; a < p; a++) {
+    sp[a] = y[map[a]];
+    for (int64_t b = 0; b < p; b++)
+      Gp[a + b * p] = H[map[a] + map[b] * R];
+  }
+  if (cholesky_lower(Gp, p) != 0)
+    return 1; /* CholFail (src/utils/update.cpp:43-44) */
+  for (int64_t j = 0; j < p; j++) { /* L z = y_p */
+    double t = sp[j];
+    for (int64_t k = 0; k < j; k++)
+      t -= Gp[j + k * p] * sp[k];
+    sp[j] = t / Gp[j + j * p];
+  }
+  for (int64_t j = p - 1; j >= 0; j--) { /* L^T x = z */
+    double t = sp[j];
+    for (int64_t k = j + 1; k < p; k++)
+      t -= Gp[k + j * p] * sp[k];
+    sp[j] = t / Gp[j + j * p];
+  }
+  return 0;
+}
+
+static double vec_min(const double *v, int64_t n) {
+  double m = v[0];
+  for (int64_t i = 1; i < n; i++)
+    if (v[i] < m)
+      m = v[i];
+  return m;
+}
+
+static int64_t nnls_update(double *F, int64_t rows, int64_t R, const double *H, unsigned char *active) {
+  /* tol = 10 * eps * ||H||_1 * n  (src/utils/update.cpp:65-66; one_norm = max column sum, include/matrix.h:113-121) */
+  double one_norm = -1.0e308;
+  for (int64_t c = 0; c < R; c++) {
+    double t = 0.0;
+    for (int64_t r = 0; r < R; r++)
+      t += fabs(H[r + c * R]);
+    if (t > one_norm)
+      one_norm = t;
+  }
+  const double tol = 10 * 2.2204e-16 * one_norm * (double)R;
+  double *y = (double *)malloc(sizeof(double) * (size_t)(5 * R + R * R));
+  double *d = y + R, *w = d + R, *s = w + R, *sp = s + R, *Gp = sp + R;
+  int64_t *map = (int64_t *)malloc(sizeof(int64_t) * (size_t)R);
+  int64_t failures = 0;
+  for (int64_t row = 0; row < rows; row++) {
+    unsigned char *act = active + row * R;
+    int64_t p = 0;
+    int any_passive = 0;
+    for (int64_t i = 0; i < R; i++) {
+      d[i] = 0.0;
+      y[i] = F[row + rows * i];
+      if (y[i] > 0)
+        act[i] = 0;
+      any_passive |= !act[i];
+    }
+    if (any_passive) { /* warm start from the previous active set (:88-117) */
+      int failed = nnls_solve_passive(H, R, y, act, Gp, sp, map, &p);
+      while (!failed) {
+        for (int64_t a = 0, i = 0; i < R; i++)
+          d[i] = act[i] ? 0.0 : sp[a++];
+        if (!(vec_min(sp, p) <= tol))
+          break;
+        int64_t left = 0;
+        for (int64_t i = 0; i < R; i++) {
+          if (d[i] <= tol) {
+            d[i] = 0.0;
+            act[i] = 1;
+          }
+          left += !act[i];
+        }
+        if (left == 0) { /* ZeroPassiveSet */
+          failed = 1;
+          break;
+        }
+        failed = nnls_solve_passive(H, R, y, act, Gp, sp, map, &p);
+      }
+      if (failed) { /* catch block (:112-115) */
+        for (int64_t i = 0; i < R; i++) {
+          act[i] = 1;
+          d[i] = 0.0;
+        }
+      }
+    }
+    /* w = y - H d  (:119, :50-57) */
+    for (int64_t i = 0; i < R; i++) {
+      double t = 0.0;
+      for (int64_t j = 0; j < R; j++)
+        t += H[i + j * R] * d[j];
+      w[i] = y[i] - t;
+    }
+    for (;;) { /* main loop (:122-170) */
+      int64_t m = -1;
+      double best = -1.0e308;
+      for (int64_t i = 0; i < R; i++)
+        if (act[i] && w[i] > best) { /* Tensor::max_id: first index of the maximum among the active ones */
+          best = w[i];
+          m = i;
+        }
+      if (m < 0 || !(best > tol))
+        break;
+      act[m] = 0;
+      if (nnls_solve_passive(H, R, y, act, Gp, sp, map, &p)) {
+        failures++;
+        break;
+      }
+      int bad = 0;
+      while (vec_min(sp, p) <= tol) { /* inner loop (:131-155) */
+        for (int64_t a = 0, i = 0; i < R; i++)
+          s[i] = act[i] ? 0.0 : sp[a++];
+        double alpha = 1.7976931348623157e308;
+        for (int64_t i = 0; i < R; i++)
+          if (!act[i] && s[i] <= tol) {
+            double t = d[i] / (d[i] - s[i]);
+            if (t < alpha)
+              alpha = t;
+          }
+        int64_t left = 0;
+        for (int64_t i = 0; i < R; i++) {
+          d[i] = d[i] + alpha * (s[i] - d[i]);
+          if (fabs(d[i]) < tol && !act[i]) {
+            act[i] = 1;
+            d[i] = 0.0;
+          }
+          left += !act[i];
+        }
+        if (left == 0 || nnls_solve_passive(H, R, y, act, Gp, sp, map, &p)) {
+          bad = 1;
+          break;
+        }
+      }
+      if (bad) {
+        failures++;
+        break;
+      }
+      for (int64_t a = 0, i = 0; i < R; i++)
+        d[i] = act[i] ? 0.0 : sp[a++];
+      for (int64_t i = 0; i < R; i++) {
+        double t = 0.0;
+        for (int64_t j = 0; j < R; j++)
+          t += H[i + j * R] * d[j];
+        w[i] = y[i] - t;
+      }
+    }
+    for (int64_t i = 0; i < R; i++)
+      F[row + rows * i] = d[i];
+  }
+  free(y);
+  free(map);
+  return failures;
+}
+
 /* Ktensor::normalize(mode, iteration) (src/ktensor.cpp:66-83). */
 static void normalize_mode(double *F, int64_t rows, int64_t R, int64_t iteration, double *lambda) {
   for (int64_t c = 0; c < R; c++) {
@@ -247,7 +417,8 @@ static double fast_error(double x_norm, const double *lambda, const double *F_la
 /* ---------------------------------------------------------------------------------------------------------------
  * cals::cp_cals (src/cals.cpp:19-395) with the MultiKtensor buffer bookkeeping (src/multi_ktensor.cpp).
  *
- * flags: bit0 force_max_iter, bit1 always_evict_first.  Models are consumed FIFO from models[0..n_models).
+ * flags: bit0 force_max_iter, bit1 always_evict_first, bit2 update_method == NNLS.  Models are consumed FIFO from
+ * models[0..n_models).
  * Because models never interact numerically, the buffer only decides WHEN a model runs (global iteration count,
  * admission order); it is restated through the occupancy vector exactly as the reference keeps it. */
 typedef struct {
@@ -256,6 +427,8 @@ typedef struct {
   double **grams; /* n_modes matrices R x R */
   double *G;      /* scratch: max_rows x R  (MTTKRP result for the current mode) */
   double *G_last;
+  unsigned char *active; /* NNLS: the model's active sets (caller's buffer, or owned when the caller passed none) */
+  int own_active;
 } live_entry;
 
 int cals_oracle_cp_cals(int n_modes, const int64_t *modes, const double *X, int64_t n_models,
@@ -263,8 +436,10 @@ int cals_oracle_cp_cals(int n_modes, const int64_t *modes, const double *X, int6
                         cals_oracle_report *rep) {
   if (n_modes > 16)
     return -1;
-  const int force_max_iter = flags & 1, always_evict_first = flags & 2;
-  int64_t nX = 1, max_rows = 0;
+  const int force_max_iter = flags & 1, always_evict_first = flags & 2, nnls = flags & 4;
+  int64_t nX = 1, max_rows = 0, sum_rows = 0;
+  for (int n = 0; n < n_modes; n++)
+    sum_rows += modes[n];
   for (int n = 0; n < n_modes; n++) {
     nX *= modes[n];
     if (modes[n] > max_rows)
@@ -319,6 +494,13 @@ int cals_oracle_cp_cals(int n_modes, const int64_t *modes, const double *X, int6
         gramian(mm->factors + off, modes[n], R, le->grams[n]);
         off += modes[n] * R;
       }
+      le->active = mm->active;
+      le->own_active = 0;
+      if (nnls && !le->active) { /* fresh Ktensor: every constraint active (include/ktensor.h:66) */
+        le->active = (unsigned char *)malloc((size_t)(sum_rows * R));
+        memset(le->active, 1, (size_t)(sum_rows * R));
+        le->own_active = 1;
+      }
       mm->iters = 1; /* multi_ktensor.cpp:96 */
       if (mm->jk_mode >= 0 && !x_norms_jk) { /* cals.cpp:198-200 */
         x_norms_jk = (double *)malloc(sizeof(double) * (size_t)modes[0]);
@@ -357,9 +539,16 @@ int cals_oracle_cp_cals(int n_modes, const int64_t *modes, const double *X, int6
         double *F = mm->factors + foff[n];
         memcpy(F, le->G, sizeof(double) * (size_t)(rows * R)); /* G overwrites factor n (mttkrp.cpp:327,613) */
         hadamard_but_one(le->grams, n_modes, n, R);                 /* cals.cpp:242 */
-        if (cholesky_lower(le->grams[n], R) != 0)                   /* update.cpp:183-185 */
-          mm->chol_fail++;
-        solve_in_place(F, rows, R, le->grams[n]);                   /* update.cpp:187-190 */
+        if (nnls) {                                                 /* cals.cpp:247-248 */
+          int64_t aoff = 0;
+          for (int k = 0; k < n; k++)
+            aoff += modes[k] * R;
+          mm->chol_fail += nnls_update(F, rows, R, le->grams[n], le->active + aoff);
+        } else {
+          if (cholesky_lower(le->grams[n], R) != 0)                 /* update.cpp:183-185 */
+            mm->chol_fail++;
+          solve_in_place(F, rows, R, le->grams[n]);                 /* update.cpp:187-190 */
+        }
         if (mm->jk_mode == n)                                       /* cals.cpp:250-251, ktensor.h:316-325 */
           for (int64_t c = 0; c < R; c++)
             F[mm->jk_fiber + c * rows] *= 0.0;
@@ -407,6 +596,8 @@ int cals_oracle_cp_cals(int n_modes, const int64_t *modes, const double *X, int6
         free(le->grams);
         free(le->G);
         free(le->G_last);
+        if (le->own_active)
+          free(le->active);
         le->live = 0;
         n_live--;
       }

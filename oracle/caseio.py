@@ -75,11 +75,11 @@ def ref_available() -> bool:
 
 
 def write_case(path, X, models, *, max_iter, tol=1e-7, buffer_size=None, force_max_iter=False,
-               always_evict_first=False, threads=1, algo=ALGO_CALS, mttkrp_method=METHOD_AUTO):
+               always_evict_first=False, threads=1, algo=ALGO_CALS, mttkrp_method=METHOD_AUTO, nnls=False):
     modes = list(X.shape)
     if buffer_size is None:
         buffer_size = sum(m.rank for m in models)
-    flags = (1 if force_max_iter else 0) | (2 if always_evict_first else 0)
+    flags = (1 if force_max_iter else 0) | (2 if always_evict_first else 0) | (4 if nnls else 0)
     with open(path, "wb") as f:
         f.write(b"CALSIN01")
         f.write(struct.pack("<q", len(modes)))

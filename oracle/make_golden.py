@@ -88,5 +88,28 @@ def main():
     pack("evict_first_3d", X, ms, caseio.run_reference(X, ms, **p), **p)
 
 
+def main_nnls():
+    """Fixtures for update_method == NNLS (reference src/utils/update.cpp:61-176), added after the first set: own
+    random stream so that the earlier fixtures stay byte-identical.  `python oracle/make_golden.py nnls`"""
+    rng = np.random.default_rng(20261019)
+    # non-negative low-rank target + noise, queueing (buffer < sum of ranks), forced iterations
+    modes = (14, 12, 10)
+    gen = [rng.uniform(0, 1, size=(i, 4)) for i in modes]
+    X = caseio.ktensor_to_tensor(gen, np.ones(4)) + 0.02 * rng.standard_normal(modes)
+    ms = caseio.random_models(rng, modes, [3, 5, 2, 7, 4, 1])
+    p = dict(max_iter=8, tol=1e-7, buffer_size=12, force_max_iter=True, nnls=True)
+    pack("nnls_3d_queue", X, ms, caseio.run_reference(X, ms, **p), **p)
+    # four modes, tol-based stopping
+    modes4 = (6, 5, 4, 7)
+    gen = [rng.uniform(0, 1, size=(i, 3)) for i in modes4]
+    X4 = caseio.ktensor_to_tensor(gen, np.ones(3)) + 0.01 * rng.standard_normal(modes4)
+    ms = caseio.random_models(rng, modes4, [2, 4, 3])
+    p = dict(max_iter=30, tol=1e-6, buffer_size=9, force_max_iter=False, nnls=True)
+    pack("nnls_4d_tol", X4, ms, caseio.run_reference(X4, ms, **p), **p)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "nnls":
+        main_nnls()
+    else:
+        main()

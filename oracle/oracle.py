@@ -18,7 +18,7 @@ class _Model(C.Structure):
     _fields_ = [("rank", C.c_int64), ("jk_mode", C.c_int64), ("jk_fiber", C.c_int64),
                 ("factors", C.POINTER(C.c_double)), ("lam", C.POINTER(C.c_double)),
                 ("iters", C.c_int64), ("error", C.c_double), ("fit", C.c_double), ("old_fit", C.c_double),
-                ("chol_fail", C.c_int64)]
+                ("chol_fail", C.c_int64), ("active", C.POINTER(C.c_ubyte))]
 
 
 class _Report(C.Structure):
@@ -95,7 +95,8 @@ class OracleResult:
         self.x_norm = 0.0
 
 
-def cp_cals(X, models, *, max_iter, tol=1e-7, buffer_size=None, force_max_iter=False, always_evict_first=False):
+def cp_cals(X, models, *, max_iter, tol=1e-7, buffer_size=None, force_max_iter=False, always_evict_first=False,
+            nnls=False):
     """Run the oracle's cp_cals.  `models` is a list of caseio.Model (inputs untouched); returns OracleResult whose
     .models are new caseio.Model objects with factors/lam/iters/error/fit/old_fit filled."""
     from caseio import Model  # same directory
@@ -116,7 +117,7 @@ def cp_cals(X, models, *, max_iter, tol=1e-7, buffer_size=None, force_max_iter=F
         arr[i].factors = flat.ctypes.data_as(C.POINTER(C.c_double))
         arr[i].lam = lam.ctypes.data_as(C.POINTER(C.c_double))
     rep = _Report()
-    flags = (1 if force_max_iter else 0) | (2 if always_evict_first else 0)
+    flags = (1 if force_max_iter else 0) | (2 if always_evict_first else 0) | (4 if nnls else 0)
     rc = lib().cals_oracle_cp_cals(Xf.ndim, m.ctypes.data, Xf.ctypes.data, len(models), arr, max_iter, tol,
                                    buffer_size, flags, C.byref(rep))
     if rc != 0:

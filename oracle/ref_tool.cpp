@@ -128,7 +128,7 @@ int main(int argc, char **argv) {
   }
   fclose(fi);
 
-  const bool force_max_iter = flags & 1, always_evict_first = flags & 2;
+  const bool force_max_iter = flags & 1, always_evict_first = flags & 2, nnls = flags & 4;
 
   double seconds = 0.0;
   int64_t rep_iter = 0, rep_n_ktensors = 0, rep_comp_sum = 0;
@@ -144,6 +144,8 @@ int main(int argc, char **argv) {
     p.buffer_size = (dim_t)buffer_size;
     p.force_max_iter = force_max_iter;
     p.always_evict_first = always_evict_first;
+    if (nnls)
+      p.update_method = cals::update::UPDATE_METHOD::NNLS;
     cals::KtensorQueue q;
     for (auto &m : models)
       q.emplace(m);
@@ -159,6 +161,8 @@ int main(int argc, char **argv) {
     p.tol = tol;
     p.force_max_iter = force_max_iter;
     p.suppress_lut_warning = true;
+    if (nnls)
+      p.update_method = cals::update::UPDATE_METHOD::NNLS;
     for (auto &m : models) {
       auto rep = cals::cp_als(X, m, p);
       seconds += rep.total_time;

