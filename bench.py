@@ -326,6 +326,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--strong", action="store_true", help="N > 1: shard ONE model set over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nnls", action="store_true", help="measurement aid: update_method = NNLS instead of the Cholesky solve")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
 
@@ -384,7 +385,7 @@ def main():
 
     eng = pkg.Engine(local_rank)
     eng.set_tensor(X)
-    eng.configure(C, als_iters, 1e-7, force_max_iter=True)
+    eng.configure(C, als_iters, 1e-7, force_max_iter=True, nnls=args.nnls)
     eng.clear_models()
     for fs, j in zip(models, jk):
         eng.enqueue(fs, j[0], j[1])
@@ -459,7 +460,8 @@ def main():
             keep.append(t)
             row.append(v)
         pinned_models.append(row)
-    params = pkg.CalsParams(max_iterations=als_iters, buffer_size=C, force_max_iter=True)
+    params = pkg.CalsParams(max_iterations=als_iters, buffer_size=C, force_max_iter=True,
+                            update_method="nnls" if args.nnls else "unconstrained")
     h2d = X.nbytes + sum(F.nbytes for fs in models for F in fs)
     d2h = sum(F.nbytes for fs in models for F in fs) + 8 * C + n_models * 40
 
@@ -491,7 +493,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ev_ms / steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s, %d forced ALS iterations per model per step" % (cfg["name"], als_iters),
+            "config": {"workload": "%s, %d forced ALS iterations per model per step%s"
+                                   % (cfg["name"], als_iters, ", NNLS update" if args.nnls else ""),
                        "models_per_gpu": n_models, "sum_ranks_per_gpu": C, "als_iters_per_step": als_iters,
                        "parallelism": "model set sharded over %d GPU(s) (%s), tensor replicated, no data-path "
                                       "collective" % (world, "one set split" if args.strong else "one full set per GPU"),

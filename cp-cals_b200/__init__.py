@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "cals_b200_host_alloc", "cals_b200_host_free", "cals_b200_stream",
     "cals_b200_comm_alloc", "cals_b200_comm_local_block", "cals_b200_comm_connect", "cals_b200_set_tensor_slab",
     "cals_b200_set_tensor_norm", "cals_b200_comm_disconnect", "cals_b200_set_model_active_set",
-    "cals_b200_fetch_model_active_set",
+    "cals_b200_fetch_model_active_set", "cals_b200_set_line_search", "cals_b200_line_search_counts",
 ]
 
 
@@ -104,6 +104,8 @@ def lib():
     L.cals_b200_set_tensor_slab.argtypes = [vp, i, C.POINTER(u64), i, C.POINTER(u64), vp]
     L.cals_b200_set_tensor_norm.argtypes = [vp, dbl]
     L.cals_b200_comm_disconnect.argtypes = [vp]
+    L.cals_b200_set_line_search.argtypes = [vp, i, i, i, dbl]
+    L.cals_b200_line_search_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.cals_b200_set_model_active_set.argtypes = [vp, i, C.POINTER(vp)]
     L.cals_b200_fetch_model_active_set.argtypes = [vp, i, C.POINTER(vp)]
     _lib = L
@@ -183,6 +185,7 @@ class CalsParams:
     line_search: bool = False
     line_search_interval: int = 5
     line_search_step: float = 0.0
+    line_search_method: str = "no-error-checking"  # | "error-checking-serial" (include/utils/line_search.h:10-11)
     force_max_iter: bool = False
     always_evict_first: bool = False
 
@@ -206,6 +209,8 @@ class CalsReport:
     update_ms: float = 0.0
     mttkrp_launches: int = 0
     kernel_launches: int = 0
+    ls_performed: int = 0
+    ls_failed: int = 0
 
 
 class Engine:
@@ -313,6 +318,15 @@ class Engine:
                  (NNLS if nnls else 0))
         self._ck(self._L.cals_b200_configure(self._ctx, buffer_cols, max_iterations, tol, flags))
 
+    def set_line_search(self, enabled: bool, method: int = 0, interval: int = 5, step: float = 0.0):
+        """method 0 = no error checking, 1 = error checking (serial) -- reference include/utils/line_search.h:8."""
+        self._ck(self._L.cals_b200_set_line_search(self._ctx, 1 if enabled else 0, method, interval, step))
+
+    def line_search_counts(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.cals_b200_line_search_counts(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_timing(self, level: int):
         self._ck(self._L.cals_b200_set_timing(self._ctx, level))
 
@@ -416,12 +430,16 @@ class Engine:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+LS_METHODS = {"no-error-checking": 0, "error-checking-serial": 1}
+
+
 def _check_params(params: CalsParams):
     if params.update_method not in ("unconstrained", "nnls"):
         raise CalsB200Error("unknown update_method %r (reference include/utils/update.h:8: unconstrained | nnls)"
                             % (params.update_method,))
-    if params.line_search:
-        raise CalsB200Error("line search is not on the B200 path (reference default is off, include/cals.h:153)")
+    if params.line_search and params.line_search_method not in LS_METHODS:
+        raise CalsB200Error("line search method %r is not available (%s)" % (params.line_search_method,
+                                                                             " | ".join(LS_METHODS)))
 
 
 def cp_cals(X: np.ndarray, ktensors: Sequence[Ktensor], params: CalsParams, *, engine: Optional[Engine] = None,
@@ -437,6 +455,8 @@ def cp_cals(X: np.ndarray, ktensors: Sequence[Ktensor], params: CalsParams, *, e
         nnls = params.update_method == "nnls"
         eng.configure(params.buffer_size, params.max_iterations, params.tol, params.force_max_iter,
                       params.always_evict_first, nnls)
+        eng.set_line_search(params.line_search, LS_METHODS.get(params.line_search_method, 0),
+                            params.line_search_interval, params.line_search_step)
         eng.set_timing(timing)
         eng.set_mttkrp_variant(mttkrp_variant)
         eng.clear_models()
@@ -452,11 +472,13 @@ def cp_cals(X: np.ndarray, ktensors: Sequence[Ktensor], params: CalsParams, *, e
             kt.iters, kt.error, kt.fit, kt.old_fit, kt.chol_info = st.iters, st.error, st.fit, st.old_fit, st.chol_info
             if nnls:
                 kt.active_set = eng.fetch_active_set(i)
+        lsp, lsf = eng.line_search_counts()
         return CalsReport(n_modes=X.ndim, modes=tuple(X.shape), X_norm=rep.x_norm, iter=rep.iter,
                           max_iter=params.max_iterations, buffer_size=params.buffer_size, n_ktensors=rep.n_ktensors,
                           ktensor_comp_sum=rep.ktensor_comp_sum, tol=params.tol, total_time=rep.total_time,
                           device_ms=rep.device_ms, mttkrp_ms=rep.mttkrp_ms, update_ms=rep.update_ms,
-                          mttkrp_launches=rep.mttkrp_launches, kernel_launches=rep.kernel_launches)
+                          mttkrp_launches=rep.mttkrp_launches, kernel_launches=rep.kernel_launches,
+                          ls_performed=lsp, ls_failed=lsf)
     finally:
         if own:
             eng.close()

@@ -26,6 +26,12 @@ struct ModelDesc {
   int iters;
   int chol_info;
   double error, fit, old_fit;
+  // line search (RegistryEntry::ls_params of the reference, include/multi_ktensor.h:20, include/utils/line_search.h:15-34)
+  int ls_iter;         // iterations since the last extrapolation
+  int ls_updated_last; // NO_ERROR_CHECKING: the previous iteration extrapolated
+  int ls_trial;        // ERROR_CHECKING: a trial model of this iteration waits for its explicit error
+  int b_iters;         // backup_ktensor: scalars (its factors / lambda live in the ls_backup matrices)
+  double b_error, b_fit, b_old_fit;
 };
 
 struct SchedState {
@@ -47,7 +53,28 @@ struct SchedState {
   unsigned long long n_admitted;
   unsigned long long comp_sum;
   unsigned long long col_iter_sum; // sum over executed iterations of the active column count C
+  // line search (CalsParams::line_search*, reference include/cals.h:153-156)
+  int ls_enabled, ls_method, ls_interval, ls_pad_;
+  double ls_step; // 0: cbrt(model iteration), reference src/cals.cpp:317-318
+  unsigned long long ls_performed, ls_failed;
 };
+
+// eviction predicate + iteration counter (reference src/cals.cpp:336-347); called by exactly one thread per model
+__device__ __forceinline__ void decide_eviction(ModelDesc &md, SchedState *st) {
+  if (st->flags & 2u) // always_evict_first: the scheduler evicts the leftmost model
+    return;
+  const int iters = md.iters;
+  bool evict;
+  if (st->flags & 1u)
+    evict = iters >= st->max_iter;
+  else
+    evict = (fabs(md.old_fit - md.fit) < st->tol) || (iters >= st->max_iter);
+  if (evict) {
+    md.state = MODEL_EVICT;
+    atomicAdd(&st->n_evict, 1);
+  } else
+    md.iters = iters + 1;
+}
 
 // Geometry shared by all kernels: extents and leading dimensions.
 struct Geom {

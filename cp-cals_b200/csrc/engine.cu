@@ -16,6 +16,7 @@
 #include "../../include/cals_b200.h"
 #include "comm.cuh"
 #include "common.cuh"
+#include "ls.cuh"
 #include "mttkrp.cuh"
 #include "prep.cuh"
 #include "sched.cuh"
@@ -100,6 +101,12 @@ struct cals_b200_ctx {
   SchedState *d_st = nullptr;
   int *d_live = nullptr, *d_live_tmp = nullptr, *d_gather = nullptr, *d_evict = nullptr;
   double *d_gram = nullptr, *d_lambda = nullptr;
+  // line search (CalsParams::line_search*, reference include/cals.h:153-156)
+  int ls_enabled = 0, ls_method = 0, ls_interval = 5;
+  double ls_step = 0.0;
+  double *ls_prev[CALS_MAX_MODES] = {}, *ls_backup[CALS_MAX_MODES] = {};
+  double *ls_prev_lambda = nullptr, *ls_backup_lambda = nullptr, *ls_partial = nullptr;
+  unsigned long long last_ls_performed = 0, last_ls_failed = 0;
   unsigned char *d_active = nullptr;       // NNLS active sets of all queued models (ModelDesc::act_off)
   std::vector<unsigned char> h_active;     // host image: all 1 unless set through cals_b200_set_model_active_set
   long long active_bytes = 0;
@@ -192,6 +199,7 @@ void free_all(std::vector<void *> &v) {
 // ---------------------------------------------------------------------------------------------------------------
 // tile configuration
 constexpr int WN_FIXED = 4;
+constexpr int LS_CHUNKS = 48; // CTAs per trial model in the explicit-error kernel
 
 int wm_max() {
   static int v = 0;
@@ -446,6 +454,9 @@ void release_run(cals_b200_ctx *c) {
   c->d_live = c->d_live_tmp = c->d_gather = c->d_evict = nullptr;
   c->d_gram = c->d_lambda = nullptr;
   c->d_active = nullptr;
+  for (int n = 0; n < CALS_MAX_MODES; n++)
+    c->ls_prev[n] = c->ls_backup[n] = nullptr;
+  c->ls_prev_lambda = c->ls_backup_lambda = c->ls_partial = nullptr;
   c->uploaded = false;
   c->run_sig.clear();
 }
@@ -611,6 +622,7 @@ int prepare_run(cals_b200_ctx *c) {
     sig.push_back(c->roff[n]);
   }
   sig.push_back(c->buffer_cols);
+  sig.push_back(c->ls_enabled ? 1 + c->ls_method : 0);
   for (int m = 0; m < M; m++)
     sig.push_back(c->hmodels[m].rank);
   const bool reuse = !c->run_sig.empty() && sig == c->run_sig && c->d_models && c->bufs.cols == c->buffer_cols;
@@ -662,6 +674,18 @@ int prepare_run(cals_b200_ctx *c) {
     for (int n = 0; n < N; n++)
       if (dev_alloc(c, &c->home0[n], (size_t)geo.ldF[n] * c->total_cols, c->run_allocs))
         return 1;
+    if (c->ls_enabled) {
+      for (int n = 0; n < N; n++) {
+        if (dev_alloc(c, &c->ls_prev[n], (size_t)geo.ldF[n] * c->total_cols, c->run_allocs))
+          return 1;
+        if (c->ls_method == 0 && dev_alloc(c, &c->ls_backup[n], (size_t)geo.ldF[n] * c->total_cols, c->run_allocs))
+          return 1;
+      }
+      if (dev_alloc(c, &c->ls_prev_lambda, (size_t)c->total_cols, c->run_allocs) ||
+          dev_alloc(c, &c->ls_backup_lambda, (size_t)c->total_cols, c->run_allocs) ||
+          dev_alloc(c, &c->ls_partial, (size_t)std::min(M, c->buffer_cols) * LS_CHUNKS, c->run_allocs))
+        return 1;
+    }
   }
   if (ensure_dummy_state(c))
     return 1;
@@ -709,6 +733,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     d.iters = 0;
     d.chol_info = 0;
     d.error = d.fit = d.old_fit = 0.0;
+    d.ls_iter = d.ls_updated_last = d.ls_trial = d.b_iters = 0;
+    d.b_error = d.b_fit = d.b_old_fit = 0.0;
   }
   memcpy(c->h_desc_pin, c->hdesc.data(), (size_t)M * sizeof(ModelDesc));
   CU_TRY(c, cudaMemcpyAsync(c->d_models, c->h_desc_pin, (size_t)M * sizeof(ModelDesc), cudaMemcpyHostToDevice, s));
@@ -718,6 +744,10 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   st.max_iter = c->max_iter;
   st.buffer_cols = c->buffer_cols;
   st.tol = c->tol;
+  st.ls_enabled = c->ls_enabled;
+  st.ls_method = c->ls_method;
+  st.ls_interval = c->ls_interval;
+  st.ls_step = c->ls_step;
   st.x_norm = c->x_norm_valid ? c->x_norm : 0.0;
   CU_TRY(c, cudaMemcpyAsync(c->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s));
   if (!c->x_norm_valid) // set_tensor has not been synchronised yet: take the norm from where the device computed it
@@ -817,6 +847,32 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     cp.spin_limit = 40000000000ll; // ~20 s at 1.97 GHz: a peer that has not arrived by then is gone
   }
 
+  LsParams lp{};
+  if (c->ls_enabled) {
+    if (c->slice_mode >= 0 && c->comm_world > 1 && c->ls_method != 0)
+      return fail(c, "line search with error checking needs the whole tensor on one GPU");
+    if (c->flags & CALS_B200_NNLS)
+      return fail(c, "line search together with the NNLS update is not supported");
+    lp.geo = geo;
+    lp.fac = b.fac;
+    for (int n = 0; n < N; n++) {
+      lp.prev[n] = c->ls_prev[n];
+      lp.backup[n] = c->ls_backup[n];
+    }
+    lp.prev_lambda = c->ls_prev_lambda;
+    lp.backup_lambda = c->ls_backup_lambda;
+    lp.lambda_home = c->d_lambda;
+    lp.gram_pool = c->d_gram;
+    lp.models = c->d_models;
+    lp.live = c->d_live;
+    lp.st = c->d_st;
+    lp.X = c->Xp;
+    lp.ldX0 = c->ldX0;
+    lp.rest0 = c->nX / c->xd[0];
+    lp.partial = c->ls_partial;
+    lp.chunks = LS_CHUNKS;
+  }
+
   const int RA = 4; // host run-ahead in CALS iterations
   cudaEvent_t ring[RA];
   for (int i = 0; i < RA; i++)
@@ -833,6 +889,10 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     sched_kernel<<<1, 32, 0, s>>>(sp);
     move_kernel<<<move_grid, 256, 0, s>>>(geo, b.fac, c->d_st, c->d_gather, c->d_evict);
     launches += 2;
+    if (c->ls_enabled) {
+      ls_snapshot_kernel<<<max_live, 256, 0, s>>>(lp);
+      launches++;
+    }
     for (int n = 0; n < N; n++) {
       if (c->timing) {
         timed.push_back({ev_next, 0});
@@ -861,6 +921,15 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
         ev_next += 1;
       }
     }
+    if (c->ls_enabled) {
+      ls_main_kernel<<<max_live, 256, 0, s>>>(lp);
+      launches++;
+      if (c->ls_method != 0) {
+        ls_explicit_error_kernel<<<dim3(max_live, LS_CHUNKS), 256, (size_t)(c->max_rank + 32) * 8, s>>>(lp);
+        ls_decide_kernel<<<max_live, 256, 0, s>>>(lp);
+        launches += 2;
+      }
+    }
     CU_TRY(c, cudaEventRecord(ring[it % RA], s));
     if (it >= RA - 1)
       CU_TRY(c, cudaEventSynchronize(ring[(it + 1) % RA]));
@@ -878,6 +947,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   // scalars back
   CU_TRY(c, cudaMemcpy(&st, c->d_st, sizeof st, cudaMemcpyDeviceToHost));
   c->last_global_iter = st.global_iter;
+  c->last_ls_performed = st.ls_performed;
+  c->last_ls_failed = st.ls_failed;
   if (exchange) {
     c->seq_base += st.global_iter * (unsigned long long)N; // the next run's first exchange continues the sequence
     if (st.comm_error)
@@ -1193,6 +1264,35 @@ int cals_b200_configure(cals_b200_ctx *c, uint64_t buffer_cols, uint64_t max_ite
   c->max_iter = (int)max_iterations;
   c->tol = tol;
   c->flags = flags;
+  return 0;
+}
+
+int cals_b200_set_line_search(cals_b200_ctx *c, int enabled, int method, int interval, double step) {
+  if (!c)
+    return 1;
+  if (enabled) {
+    if (method != 0 && method != 1)
+      return fail(c, "line search method %d is not available (0 = no error checking, 1 = error checking, serial)",
+                  method);
+    if (interval < 2)
+      return fail(c, "line search interval must be at least 2");
+  }
+  if ((enabled != 0) != (c->ls_enabled != 0) || method != c->ls_method)
+    c->uploaded = false;
+  c->ls_enabled = enabled ? 1 : 0;
+  c->ls_method = method;
+  c->ls_interval = interval;
+  c->ls_step = step;
+  return 0;
+}
+
+int cals_b200_line_search_counts(cals_b200_ctx *c, uint64_t *performed, uint64_t *failed) {
+  if (!c)
+    return 1;
+  if (performed)
+    *performed = c->last_ls_performed;
+  if (failed)
+    *failed = c->last_ls_failed;
   return 0;
 }
 

@@ -573,18 +573,8 @@ model_update_kernel(const UpdateParams p) {
     md.error = err;
     md.old_fit = old_fit;
     md.fit = fit;
-    if (!(st->flags & 2u)) {
-      bool evict;
-      if (st->flags & 1u)
-        evict = iters >= st->max_iter;
-      else
-        evict = (fabs(old_fit - fit) < st->tol) || (iters >= st->max_iter);
-      if (evict) {
-        md.state = MODEL_EVICT;
-        atomicAdd(&st->n_evict, 1);
-      } else
-        md.iters = iters + 1;
-    }
+    if (!st->ls_enabled) // with line search the decision is taken after the extrapolation step (ls.cuh)
+      decide_eviction(md, st);
   }
 }
 

@@ -183,6 +183,7 @@ def cp_cals_sliced(slab: np.ndarray, modes: Sequence[int], slice_mode: int, kten
             total = float(sq.item())
         eng.set_tensor_norm(total ** 0.5)
         eng.configure(buffer_cols, params.max_iterations, params.tol, params.force_max_iter, params.always_evict_first)
+        eng.set_line_search(False)
         eng.set_timing(timing)
         eng.clear_models()
         for kt in ktensors:

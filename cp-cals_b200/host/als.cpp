@@ -18,8 +18,8 @@ namespace cals {
 static AlsReport run_single(const Tensor &X, Ktensor &ktensor, AlsParams &p, bool may_skip_upload) {
   if (p.update_method != update::UNCONSTRAINED && p.update_method != update::NNLS)
     throw B200Error("cp_als: unknown update method");
-  if (p.line_search)
-    throw B200Error("cp_als: line search is not on the B200 path; there is no CPU fallback");
+  if (p.line_search && p.line_search_method != ls::NO_ERROR_CHECKING && p.line_search_method != ls::ERROR_CHECKING_SERIAL)
+    throw B200Error("cp_als: this line search method is not on the B200 path; there is no CPU fallback");
   if (X.get_n_modes() < 3)
     throw B200Error("cp_als: tensors need at least 3 modes (the reference asserts the same, src/als.cpp:51)");
 
@@ -47,6 +47,10 @@ static AlsReport run_single(const Tensor &X, Ktensor &ktensor, AlsParams &p, boo
   opt.tol = p.tol;
   opt.force_max_iter = p.force_max_iter;
   opt.nnls = p.update_method == update::NNLS;
+  opt.line_search = p.line_search;
+  opt.ls_method = static_cast<int>(p.line_search_method);
+  opt.ls_interval = p.line_search_interval;
+  opt.ls_step = p.line_search_step;
   opt.skip_upload_if_resident = may_skip_upload;
   std::vector<Ktensor *> one{&ktensor};
   const detail::RunResult r = detail::run_on_device(p.device, X, one, opt);
@@ -54,6 +58,8 @@ static AlsReport run_single(const Tensor &X, Ktensor &ktensor, AlsParams &p, boo
 
   rep.X_norm = r.rep.x_norm;
   rep.iter = r.rep.iter;
+  rep.ls_performed = r.ls_performed;
+  rep.ls_failed = r.ls_failed;
   rep.total_time = total.get_time();
   rep.flops_per_iteration = 2ull * rep.n_modes * X.get_n_elements() * ktensor.get_components();
   const dim_t its = std::max<dim_t>(rep.iter, 1);

@@ -81,6 +81,8 @@ RunResult run_on_device(int device, const Tensor &X, const std::vector<Ktensor *
     sum_ranks += kt->get_components();
   const dim_t buffer = std::max<dim_t>(std::min(opt.buffer_size, sum_ranks), 1);
   check(e, cals_b200_configure(e.ctx, buffer, opt.max_iterations, opt.tol, flags), "cals_b200_configure");
+  check(e, cals_b200_set_line_search(e.ctx, opt.line_search, opt.ls_method, opt.ls_interval, opt.ls_step),
+        "cals_b200_set_line_search");
   check(e, cals_b200_set_timing(e.ctx, opt.timing), "cals_b200_set_timing");
   check(e, cals_b200_clear_models(e.ctx), "cals_b200_clear_models");
 
@@ -124,6 +126,7 @@ RunResult run_on_device(int device, const Tensor &X, const std::vector<Ktensor *
     }
   }
   check(e, cals_b200_run(e.ctx, &out.rep), "cals_b200_run");
+  check(e, cals_b200_line_search_counts(e.ctx, &out.ls_performed, &out.ls_failed), "cals_b200_line_search_counts");
 
   // results straight into the callers' storage (Ktensor::detach of the reference, src/ktensor.cpp:127-135)
   const size_t M = models.size();
@@ -256,6 +259,8 @@ static RunResult run_sliced(const std::vector<int> &devices, int slice_mode, con
   for (size_t r = 0; r < W; r++) {
     check(*eng[r], cals_b200_set_tensor_norm(eng[r]->ctx, std::sqrt(sumsq)), "cals_b200_set_tensor_norm");
     check(*eng[r], cals_b200_configure(eng[r]->ctx, buffer, opt.max_iterations, opt.tol, flags), "cals_b200_configure");
+    check(*eng[r], cals_b200_set_line_search(eng[r]->ctx, opt.line_search, opt.ls_method, opt.ls_interval, opt.ls_step),
+          "cals_b200_set_line_search");
     check(*eng[r], cals_b200_set_timing(eng[r]->ctx, opt.timing), "cals_b200_set_timing");
     check(*eng[r], cals_b200_clear_models(eng[r]->ctx), "cals_b200_clear_models");
     for (Ktensor *kt : models) {
@@ -324,15 +329,17 @@ std::vector<std::vector<size_t>> shard_models(const std::vector<dim_t> &ranks, s
 } // namespace detail
 
 // ---------------------------------------------------------------------------------------------------------------------
-static void reject_unsupported(update::UPDATE_METHOD um, bool line_search, const char *who) {
+static void reject_unsupported(update::UPDATE_METHOD um, bool line_search, ls::LS_METHOD lm, const char *who) {
   if (um != update::UNCONSTRAINED && um != update::NNLS)
     throw B200Error(std::string(who) + ": unknown update method");
-  if (line_search)
-    throw B200Error(std::string(who) + ": line search is not on the B200 path; there is no CPU fallback");
+  if (line_search && lm != ls::NO_ERROR_CHECKING && lm != ls::ERROR_CHECKING_SERIAL)
+    throw B200Error(std::string(who) + ": line search method '" + ls::ls_method_names[lm] +
+                    "' is not on the B200 path (the reference's own dispatcher ignores it too, "
+                    "src/utils/line_search.cpp:228-259); there is no CPU fallback");
 }
 
 CalsReport cp_cals(const Tensor &X, KtensorQueue &kt_queue, CalsParams &cals_params) {
-  reject_unsupported(cals_params.update_method, cals_params.line_search, "cp_cals");
+  reject_unsupported(cals_params.update_method, cals_params.line_search, cals_params.line_search_method, "cp_cals");
   if (X.get_n_modes() < 3)
     throw B200Error("cp_cals: tensors need at least 3 modes (the reference asserts the same, src/cals.cpp:52)");
 
@@ -369,6 +376,10 @@ CalsReport cp_cals(const Tensor &X, KtensorQueue &kt_queue, CalsParams &cals_par
   opt.force_max_iter = cals_params.force_max_iter;
   opt.always_evict_first = cals_params.always_evict_first;
   opt.nnls = cals_params.update_method == update::NNLS;
+  opt.line_search = cals_params.line_search;
+  opt.ls_method = static_cast<int>(cals_params.line_search_method);
+  opt.ls_interval = cals_params.line_search_interval;
+  opt.ls_step = cals_params.line_search_step;
   opt.timing = cals_params.timing;
 
   std::vector<int> devices = cals_params.devices.empty() ? std::vector<int>{0} : cals_params.devices;
@@ -418,6 +429,8 @@ CalsReport cp_cals(const Tensor &X, KtensorQueue &kt_queue, CalsParams &cals_par
     rep.update_ms = std::max(rep.update_ms, r.rep.update_ms);
     rep.kernel_launches += r.rep.kernel_launches;
     rep.mttkrp_flops += r.rep.mttkrp_flops;
+    rep.ls_performed += r.ls_performed;
+    rep.ls_failed += r.ls_failed;
   }
   if (models.empty())
     rep.X_norm = X.norm();

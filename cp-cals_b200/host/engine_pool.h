@@ -38,6 +38,10 @@ struct RunOptions {
   bool force_max_iter{false};
   bool always_evict_first{false};
   bool nnls{false}; // update_method == NNLS
+  bool line_search{false};
+  int ls_method{0};
+  int ls_interval{5};
+  double ls_step{0.0};
   int timing{0};
   bool skip_upload_if_resident{false};
 };
@@ -45,6 +49,7 @@ struct RunOptions {
 struct RunResult {
   cals_b200_report rep{};
   std::vector<dim_t> cols; // active columns per global iteration
+  uint64_t ls_performed{0}, ls_failed{0};
 };
 
 // Fit `models` (FIFO order) to X on one device; every Ktensor is overwritten with its result.

@@ -104,6 +104,12 @@ int cals_b200_set_tensor_norm(cals_b200_ctx *ctx, double norm);
 /* ---- parameters (CalsParams, reference include/cals.h:138-159) ------------------------------------------------ */
 int cals_b200_configure(cals_b200_ctx *ctx, uint64_t buffer_cols, uint64_t max_iterations, double tol,
                         unsigned flags);
+/* CalsParams::line_search / line_search_method / line_search_interval / line_search_step (reference include/cals.h:
+ * 153-156, src/utils/line_search.cpp).  method 0 = NO_ERROR_CHECKING, 1 = ERROR_CHECKING_SERIAL; step 0 = cbrt of the
+ * model's iteration count (src/cals.cpp:317-318); interval >= 2.  Off by default, as in the reference. */
+int cals_b200_set_line_search(cals_b200_ctx *ctx, int enabled, int method, int interval, double step);
+/* CalsReport::ls_performed / ls_failed of the last run (reference include/cals.h:52-53). */
+int cals_b200_line_search_counts(cals_b200_ctx *ctx, uint64_t *performed, uint64_t *failed);
 /* 0: no per-kernel timing (default).  1: bracket MTTKRP / update kernels with CUDA events (adds syncs at the end). */
 int cals_b200_set_timing(cals_b200_ctx *ctx, int level);
 int cals_b200_set_mttkrp_variant(cals_b200_ctx *ctx, int variant);

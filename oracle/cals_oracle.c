@@ -43,7 +43,18 @@ typedef struct {
   int64_t n_ktensors;    /* CalsReport::n_ktensors */
   int64_t ktensor_comp_sum;
   double x_norm;
+  int64_t ls_performed; /* CalsReport::ls_performed / ls_failed (include/cals.h:52-53) */
+  int64_t ls_failed;
 } cals_oracle_report;
+
+/* Line-search options (reference include/utils/line_search.h:8-39, CalsParams include/cals.h:153-156).
+ * method: 0 NO_ERROR_CHECKING, 1 ERROR_CHECKING_SERIAL.  step == 0 -> cbrt(model iteration) (src/cals.cpp:317-318). */
+typedef struct {
+  int enabled;
+  int method;
+  int interval;
+  double step;
+} cals_oracle_ls;
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Tensor::norm  (include/tensor.h:196, cblas_dnrm2 over all elements), called at src/cals.cpp:36. */
@@ -414,6 +425,104 @@ static double fast_error(double x_norm, const double *lambda, const double *F_la
   return sqrt(fmax(x_norm * x_norm + term2 - 2.0 * term3, 0.0));
 }
 
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Line search (src/utils/line_search.cpp).  A model's state is (factors, lambda, error, fit, old_fit, iters); the
+ * reference keeps two extra Ktensors per live model: prev_ktensor (snapshot taken `interval-1` iterations after the
+ * last extrapolation, src/cals.cpp:203-212) and backup_ktensor (NO_ERROR_CHECKING only: state right before an
+ * extrapolation, to return to if the error went up). */
+typedef struct {
+  double *factors, *lambda; /* same layout as cals_oracle_model */
+  double error, fit, old_fit;
+  int64_t iters;
+} ls_snapshot;
+
+static void snapshot_take(ls_snapshot *s, const cals_oracle_model *m, int64_t n_fac) { /* Ktensor::copy, ktensor.cpp:162-179 */
+  memcpy(s->factors, m->factors, sizeof(double) * (size_t)n_fac);
+  memcpy(s->lambda, m->lambda, sizeof(double) * (size_t)m->rank);
+  s->error = m->error;
+  s->fit = m->fit;
+  s->old_fit = m->old_fit;
+  s->iters = m->iters;
+}
+static void snapshot_restore(const ls_snapshot *s, cals_oracle_model *m, int64_t n_fac) {
+  memcpy(m->factors, s->factors, sizeof(double) * (size_t)n_fac);
+  memcpy(m->lambda, s->lambda, sizeof(double) * (size_t)m->rank);
+  m->error = s->error;
+  m->fit = s->fit;
+  m->old_fit = s->old_fit;
+  m->iters = s->iters;
+}
+/* Ktensor::denormalize (src/ktensor.cpp:101-107) */
+static void denormalize(double *factors, const double *lambda, int64_t rows0, int64_t R) {
+  for (int64_t c = 0; c < R; c++)
+    for (int64_t r = 0; r < rows0; r++)
+      factors[r + c * rows0] *= lambda[c];
+}
+/* Ktensor::normalize() (src/ktensor.cpp:85-99): every column to unit 2-norm, lambda = product of the norms */
+static void normalize_all(int n_modes, const int64_t *modes, int64_t R, double *factors, double *lambda) {
+  for (int64_t c = 0; c < R; c++)
+    lambda[c] = 1.0;
+  int64_t off = 0;
+  for (int n = 0; n < n_modes; n++) {
+    double *F = factors + off;
+    for (int64_t c = 0; c < R; c++) {
+      double s = 0.0;
+      for (int64_t r = 0; r < modes[n]; r++)
+        s += F[r + c * modes[n]] * F[r + c * modes[n]];
+      double nrm = sqrt(s), inv = 1.0 / nrm;
+      for (int64_t r = 0; r < modes[n]; r++)
+        F[r + c * modes[n]] *= inv;
+      lambda[c] *= nrm;
+    }
+    off += modes[n] * R;
+  }
+}
+static void all_gramians(int n_modes, const int64_t *modes, int64_t R, const double *factors, double *const *grams) {
+  int64_t off = 0;
+  for (int n = 0; n < n_modes; n++) {
+    gramian(factors + off, modes[n], R, grams[n]);
+    off += modes[n] * R;
+  }
+}
+/* error::compute_error (src/utils/error.cpp:7-31; 3 modes there, any N here): ||X - [[lambda; factors]]||_F by explicit
+ * reconstruction. */
+static double explicit_error(int n_modes, const int64_t *modes, const double *X, int64_t R, const double *factors,
+                             const double *lambda) {
+  int64_t nX = 1, foff[17];
+  foff[0] = 0;
+  for (int n = 0; n < n_modes; n++) {
+    nX *= modes[n];
+    foff[n + 1] = foff[n] + modes[n] * R;
+  }
+  int64_t idx[16] = {0};
+  double *w = (double *)malloc(sizeof(double) * (size_t)R);
+  double acc = 0.0;
+  const int64_t I0 = modes[0];
+  for (int64_t o = 0; o < nX / I0; o++) {
+    for (int64_t r = 0; r < R; r++) {
+      double p = lambda[r];
+      for (int n = 1; n < n_modes; n++)
+        p *= factors[foff[n] + idx[n] + r * modes[n]];
+      w[r] = p;
+    }
+    for (int64_t i = 0; i < I0; i++) {
+      double m = 0.0;
+      for (int64_t r = 0; r < R; r++)
+        m += w[r] * factors[i + r * I0];
+      double dlt = X[o * I0 + i] - m;
+      acc += dlt * dlt;
+    }
+    for (int n = 1; n < n_modes; n++) {
+      if (++idx[n] < modes[n])
+        break;
+      idx[n] = 0;
+    }
+  }
+  free(w);
+  return sqrt(acc);
+}
+
 /* ---------------------------------------------------------------------------------------------------------------
  * cals::cp_cals (src/cals.cpp:19-395) with the MultiKtensor buffer bookkeeping (src/multi_ktensor.cpp).
  *
@@ -429,13 +538,28 @@ typedef struct {
   double *G_last;
   unsigned char *active; /* NNLS: the model's active sets (caller's buffer, or owned when the caller passed none) */
   int own_active;
+  /* line search (RegistryEntry::ls_params, include/multi_ktensor.h:20) */
+  int ls_iter, ls_updated_last;
+  ls_snapshot prev, backup;
 } live_entry;
+
+int cals_oracle_cp_cals_ls(int n_modes, const int64_t *modes, const double *X, int64_t n_models,
+                           cals_oracle_model *models, int64_t max_iter, double tol, int64_t buffer_size, int flags,
+                           const cals_oracle_ls *lsp, cals_oracle_report *rep);
 
 int cals_oracle_cp_cals(int n_modes, const int64_t *modes, const double *X, int64_t n_models,
                         cals_oracle_model *models, int64_t max_iter, double tol, int64_t buffer_size, int flags,
                         cals_oracle_report *rep) {
+  cals_oracle_ls off = {0, 0, 0, 0.0};
+  return cals_oracle_cp_cals_ls(n_modes, modes, X, n_models, models, max_iter, tol, buffer_size, flags, &off, rep);
+}
+
+int cals_oracle_cp_cals_ls(int n_modes, const int64_t *modes, const double *X, int64_t n_models,
+                           cals_oracle_model *models, int64_t max_iter, double tol, int64_t buffer_size, int flags,
+                           const cals_oracle_ls *lsp, cals_oracle_report *rep) {
   if (n_modes > 16)
     return -1;
+  const cals_oracle_ls ls = *lsp;
   const int force_max_iter = flags & 1, always_evict_first = flags & 2, nnls = flags & 4;
   int64_t nX = 1, max_rows = 0, sum_rows = 0;
   for (int n = 0; n < n_modes; n++)
@@ -455,6 +579,8 @@ int cals_oracle_cp_cals(int n_modes, const int64_t *modes, const double *X, int6
   rep->n_ktensors = 0;
   rep->ktensor_comp_sum = 0;
   rep->x_norm = x_norm;
+  rep->ls_performed = 0;
+  rep->ls_failed = 0;
   for (int64_t m = 0; m < n_models; m++) {
     models[m].iters = 0;
     models[m].error = 0.0;
@@ -501,6 +627,17 @@ int cals_oracle_cp_cals(int n_modes, const int64_t *modes, const double *X, int6
         memset(le->active, 1, (size_t)(sum_rows * R));
         le->own_active = 1;
       }
+      le->ls_iter = 0;
+      le->ls_updated_last = 0;
+      if (ls.enabled) { /* multi_ktensor.cpp:103-111 */
+        ls_snapshot *snaps[2] = {&le->prev, &le->backup};
+        for (int k = 0; k < 2; k++) {
+          snaps[k]->factors = (double *)calloc((size_t)(sum_rows * R), sizeof(double));
+          snaps[k]->lambda = (double *)calloc((size_t)R, sizeof(double));
+          snaps[k]->error = snaps[k]->fit = snaps[k]->old_fit = 0.0;
+          snaps[k]->iters = 0;
+        }
+      }
       mm->iters = 1; /* multi_ktensor.cpp:96 */
       if (mm->jk_mode >= 0 && !x_norms_jk) { /* cals.cpp:198-200 */
         x_norms_jk = (double *)malloc(sizeof(double) * (size_t)modes[0]);
@@ -511,6 +648,12 @@ int cals_oracle_cp_cals(int n_modes, const int64_t *modes, const double *X, int6
       n_live++;
       next++;
     }
+
+    /* line search: time to remember the model as it is now? (cals.cpp:203-212) */
+    if (ls.enabled)
+      for (int64_t m = 0; m < n_models; m++)
+        if (live[m].live && live[m].ls_iter == ls.interval - 1)
+          snapshot_take(&live[m].prev, &models[m], sum_rows * models[m].rank);
 
     /* modes loop (cals.cpp:220-276); per model the concatenated MTTKRP is its own columns' MTTKRP.
      * Models are independent (the reference runs them under `omp parallel for`, cals.cpp:239,281). */
@@ -564,6 +707,71 @@ int cals_oracle_cp_cals(int n_modes, const int64_t *modes, const double *X, int6
                              n_modes);
       mm->old_fit = mm->fit; /* ktensor.h:178-183: fit uses the GLOBAL norm, also for jk models (cals.cpp:302) */
       mm->fit = 1.0 - fabs(mm->error) / x_norm;
+
+      /* line search (cals.cpp:309-333, line_search.cpp:219-268) */
+      if (ls.enabled && !(ls.method == 0 && mm->iters >= max_iter)) {
+        const int64_t n_fac = sum_rows * R;
+        const double step = ls.step == 0.0 ? cbrt((double)mm->iters) : ls.step;
+        int extrapolated = 0, reversed = 0;
+        le->ls_iter++;
+        if (ls.method == 0) {
+          if (le->ls_updated_last) {
+            le->ls_updated_last = 0;
+            if (le->backup.error < mm->error) { /* the extrapolation made it worse: go back */
+              reversed = 1;
+              le->ls_iter = 0;
+              snapshot_restore(&le->backup, mm, n_fac);
+              all_gramians(n_modes, modes, R, mm->factors, le->grams);
+            }
+          }
+          if (le->ls_iter == ls.interval) {
+            extrapolated = 1;
+            le->ls_iter = 0;
+            le->ls_updated_last = 1;
+            snapshot_take(&le->backup, mm, n_fac);
+            /* line_search_no_error_checking (line_search.cpp:23-68) */
+            denormalize(mm->factors, mm->lambda, modes[0], R);
+            denormalize(le->prev.factors, le->prev.lambda, modes[0], R);
+            for (int64_t e = 0; e < n_fac; e++)
+              mm->factors[e] += step * (mm->factors[e] - le->prev.factors[e]);
+            normalize_all(n_modes, modes, R, mm->factors, mm->lambda);
+            mm->error = 1.7976931348623157e308;
+            mm->old_fit = mm->fit;
+            mm->fit = 1.0 - fabs(mm->error) / 1.0;
+            all_gramians(n_modes, modes, R, mm->factors, le->grams);
+          }
+        } else if (le->ls_iter == ls.interval) { /* ERROR_CHECKING_SERIAL: line_search_error_checking (:84-150) */
+          extrapolated = 1;
+          le->ls_iter = 0;
+          double *lsf = le->prev.factors; /* the snapshot doubles as the trial model (ls_ktensor) */
+          for (int64_t e = 0; e < n_fac; e++)
+            lsf[e] = mm->factors[e] + step * (mm->factors[e] - lsf[e]);
+          memcpy(le->prev.lambda, mm->lambda, sizeof(double) * (size_t)R);
+          /* compute_error: denormalize, ||X - M||, normalize() (error.cpp:13,28) */
+          denormalize(lsf, le->prev.lambda, modes[0], R);
+          double ones[64];
+          double *one_l = R <= 64 ? ones : (double *)malloc(sizeof(double) * (size_t)R);
+          for (int64_t c = 0; c < R; c++)
+            one_l[c] = 1.0;
+          const double e_new = explicit_error(n_modes, modes, X, R, lsf, one_l);
+          if (one_l != ones)
+            free(one_l);
+          normalize_all(n_modes, modes, R, lsf, le->prev.lambda);
+          reversed = 1;
+          if (e_new < mm->error) {
+            reversed = 0;
+            memcpy(mm->factors, lsf, sizeof(double) * (size_t)n_fac); /* factors only: lambda stays (:130-131) */
+            all_gramians(n_modes, modes, R, mm->factors, le->grams);
+            mm->error = e_new;
+            mm->old_fit = mm->fit;
+            mm->fit = 1.0 - fabs(mm->error) / x_norm;
+          }
+        }
+#pragma omp atomic
+        rep->ls_performed += extrapolated;
+#pragma omp atomic
+        rep->ls_failed += reversed;
+      }
     }
 
     /* eviction (cals.cpp:336-358) in registry (= admission) order */
@@ -598,6 +806,12 @@ int cals_oracle_cp_cals(int n_modes, const int64_t *modes, const double *X, int6
         free(le->G_last);
         if (le->own_active)
           free(le->active);
+        if (ls.enabled) {
+          free(le->prev.factors);
+          free(le->prev.lambda);
+          free(le->backup.factors);
+          free(le->backup.lambda);
+        }
         le->live = 0;
         n_live--;
       }

@@ -75,16 +75,19 @@ def ref_available() -> bool:
 
 
 def write_case(path, X, models, *, max_iter, tol=1e-7, buffer_size=None, force_max_iter=False,
-               always_evict_first=False, threads=1, algo=ALGO_CALS, mttkrp_method=METHOD_AUTO, nnls=False):
+               always_evict_first=False, threads=1, algo=ALGO_CALS, mttkrp_method=METHOD_AUTO, nnls=False,
+               line_search=False, ls_method=0, ls_interval=5, ls_step=0.0):
     modes = list(X.shape)
     if buffer_size is None:
         buffer_size = sum(m.rank for m in models)
-    flags = (1 if force_max_iter else 0) | (2 if always_evict_first else 0) | (4 if nnls else 0)
+    flags = ((1 if force_max_iter else 0) | (2 if always_evict_first else 0) | (4 if nnls else 0) |
+             (8 if line_search else 0))
     with open(path, "wb") as f:
         f.write(b"CALSIN01")
         f.write(struct.pack("<q", len(modes)))
         f.write(struct.pack("<%dq" % len(modes), *modes))
         f.write(struct.pack("<qqdqqqqq", len(models), max_iter, tol, buffer_size, flags, threads, algo, mttkrp_method))
+        f.write(struct.pack("<qqd", ls_method, ls_interval, ls_step))
         for m in models:
             f.write(struct.pack("<qqq", m.rank, m.jk_mode, m.jk_fiber))
         f.write(np.asfortranarray(X, dtype=np.float64).tobytes(order="F"))

@@ -108,8 +108,27 @@ def main_nnls():
     pack("nnls_4d_tol", X4, ms, caseio.run_reference(X4, ms, **p), **p)
 
 
+def main_ls():
+    """Fixtures for line search (reference src/utils/line_search.cpp), own random stream.
+    `python oracle/make_golden.py ls`.  Forced iteration counts on noisy tensors that are still far from converged:
+    the accept / go-back decisions compare errors, and on a converged model those differ only in the last bits."""
+    rng = np.random.default_rng(20261020)
+    modes = (18, 17, 16)
+    gen = [rng.uniform(-1, 1, size=(i, 4)) for i in modes]
+    X = caseio.ktensor_to_tensor(gen, np.ones(4)) + 0.05 * rng.standard_normal(modes)
+    ms = caseio.random_models(rng, modes, [5, 5, 3, 6])
+    p = dict(max_iter=14, tol=1e-6, buffer_size=11, force_max_iter=True, line_search=True, ls_method=0, ls_interval=4,
+             ls_step=1.2)
+    pack("ls_noerr_3d_queue", X, ms, caseio.run_reference(X, ms, **p), **p)
+    p = dict(max_iter=13, tol=1e-6, buffer_size=19, force_max_iter=True, line_search=True, ls_method=1, ls_interval=5,
+             ls_step=0.0)
+    pack("ls_errcheck_3d", X, ms, caseio.run_reference(X, ms, **p), **p)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "nnls":
+    if len(sys.argv) > 1 and sys.argv[1] == "ls":
+        main_ls()
+    elif len(sys.argv) > 1 and sys.argv[1] == "nnls":
         main_nnls()
     else:
         main()

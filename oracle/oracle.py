@@ -23,7 +23,11 @@ class _Model(C.Structure):
 
 class _Report(C.Structure):
     _fields_ = [("iter", C.c_int64), ("n_ktensors", C.c_int64), ("ktensor_comp_sum", C.c_int64),
-                ("x_norm", C.c_double)]
+                ("x_norm", C.c_double), ("ls_performed", C.c_int64), ("ls_failed", C.c_int64)]
+
+
+class _Ls(C.Structure):
+    _fields_ = [("enabled", C.c_int), ("method", C.c_int), ("interval", C.c_int), ("step", C.c_double)]
 
 
 _lib = None
@@ -47,6 +51,9 @@ def lib():
         _lib.cals_oracle_cp_cals.restype = C.c_int
         _lib.cals_oracle_cp_cals.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Model), C.c_int64,
                                              C.c_double, C.c_int64, C.c_int, C.POINTER(_Report)]
+        _lib.cals_oracle_cp_cals_ls.restype = C.c_int
+        _lib.cals_oracle_cp_cals_ls.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(_Model), C.c_int64,
+                                                C.c_double, C.c_int64, C.c_int, C.POINTER(_Ls), C.POINTER(_Report)]
         _lib.cals_oracle_denormalize_normalize.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     return _lib
 
@@ -96,7 +103,7 @@ class OracleResult:
 
 
 def cp_cals(X, models, *, max_iter, tol=1e-7, buffer_size=None, force_max_iter=False, always_evict_first=False,
-            nnls=False):
+            nnls=False, line_search=False, ls_method=0, ls_interval=5, ls_step=0.0):
     """Run the oracle's cp_cals.  `models` is a list of caseio.Model (inputs untouched); returns OracleResult whose
     .models are new caseio.Model objects with factors/lam/iters/error/fit/old_fit filled."""
     from caseio import Model  # same directory
@@ -118,12 +125,14 @@ def cp_cals(X, models, *, max_iter, tol=1e-7, buffer_size=None, force_max_iter=F
         arr[i].lam = lam.ctypes.data_as(C.POINTER(C.c_double))
     rep = _Report()
     flags = (1 if force_max_iter else 0) | (2 if always_evict_first else 0) | (4 if nnls else 0)
-    rc = lib().cals_oracle_cp_cals(Xf.ndim, m.ctypes.data, Xf.ctypes.data, len(models), arr, max_iter, tol,
-                                   buffer_size, flags, C.byref(rep))
+    ls = _Ls(1 if line_search else 0, ls_method, ls_interval, ls_step)
+    rc = lib().cals_oracle_cp_cals_ls(Xf.ndim, m.ctypes.data, Xf.ctypes.data, len(models), arr, max_iter, tol,
+                                      buffer_size, flags, C.byref(ls), C.byref(rep))
     if rc != 0:
         raise RuntimeError("oracle cp_cals failed rc=%d" % rc)
     res = OracleResult()
     res.iters, res.n_ktensors, res.comp_sum, res.x_norm = rep.iter, rep.n_ktensors, rep.ktensor_comp_sum, rep.x_norm
+    res.ls_performed, res.ls_failed = rep.ls_performed, rep.ls_failed
     for i, mm in enumerate(models):
         flat, lam = keep[i]
         fs, off = [], 0

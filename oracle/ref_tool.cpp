@@ -96,6 +96,11 @@ int main(int argc, char **argv) {
   rd(fi, &threads, 1);
   rd(fi, &algo, 1);
   rd(fi, &mttkrp_method, 1);
+  int64_t ls_method, ls_interval;
+  double ls_step;
+  rd(fi, &ls_method, 1);
+  rd(fi, &ls_interval, 1);
+  rd(fi, &ls_step, 1);
   std::vector<ModelSpec> specs(n_models);
   for (auto &s : specs) {
     rd(fi, &s.rank, 1);
@@ -128,7 +133,7 @@ int main(int argc, char **argv) {
   }
   fclose(fi);
 
-  const bool force_max_iter = flags & 1, always_evict_first = flags & 2, nnls = flags & 4;
+  const bool force_max_iter = flags & 1, always_evict_first = flags & 2, nnls = flags & 4, line_search = flags & 8;
 
   double seconds = 0.0;
   int64_t rep_iter = 0, rep_n_ktensors = 0, rep_comp_sum = 0;
@@ -146,6 +151,12 @@ int main(int argc, char **argv) {
     p.always_evict_first = always_evict_first;
     if (nnls)
       p.update_method = cals::update::UPDATE_METHOD::NNLS;
+    if (line_search) {
+      p.line_search = true;
+      p.line_search_method = (cals::ls::LS_METHOD)ls_method;
+      p.line_search_interval = (int)ls_interval;
+      p.line_search_step = ls_step;
+    }
     cals::KtensorQueue q;
     for (auto &m : models)
       q.emplace(m);
@@ -163,6 +174,12 @@ int main(int argc, char **argv) {
     p.suppress_lut_warning = true;
     if (nnls)
       p.update_method = cals::update::UPDATE_METHOD::NNLS;
+    if (line_search) {
+      p.line_search = true;
+      p.line_search_method = (cals::ls::LS_METHOD)ls_method;
+      p.line_search_interval = (int)ls_interval;
+      p.line_search_step = ls_step;
+    }
     for (auto &m : models) {
       auto rep = cals::cp_als(X, m, p);
       seconds += rep.total_time;

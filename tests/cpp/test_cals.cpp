@@ -96,6 +96,53 @@ TEST(Cals, QueueOfModelsEqualsOneByOneAls) {
   }
 }
 
+// reference CalsLineSearchTests.LineSearchCorrectness (tests/cals/test_cals.cpp:88-179), both methods: with line search
+// switched on, the queue of models through cp_cals equals cp_als model by model.
+static void line_search_case(cals::ls::LS_METHOD method) {
+  std::vector<dim_t> ranks;
+  for (dim_t r = 1; r <= 12; r++)
+    ranks.insert(ranks.end(), 6, r);
+  std::mt19937 order(9);
+  std::shuffle(ranks.begin(), ranks.end(), order);
+  Uniform u(0);
+  Ktensor P(10, {13, 12, 11});
+  P.fill(u.source());
+  Tensor T = P.to_tensor();
+  std::vector<Ktensor> start = random_models(ranks, T.get_modes(), u);
+  std::vector<Ktensor> by_cals(start), by_als(start);
+
+  cals::CalsParams cp;
+  cp.max_iterations = 1000;
+  cp.tol = 1e-5;
+  cp.buffer_size = 30;
+  cp.line_search = true;
+  cp.line_search_interval = 10;
+  cp.line_search_step = 0;
+  cp.line_search_method = method;
+  cals::AlsParams ap;
+  ap.max_iterations = cp.max_iterations;
+  ap.tol = cp.tol;
+  ap.line_search = true;
+  ap.line_search_interval = cp.line_search_interval;
+  ap.line_search_step = cp.line_search_step;
+  ap.line_search_method = method;
+  ap.suppress_lut_warning = true;
+
+  auto q = queue_of(by_cals);
+  const cals::CalsReport rep = cals::cp_cals(T, q, cp);
+  dim_t als_performed = 0;
+  for (Ktensor &k : by_als)
+    als_performed += cals::cp_als(T, k, ap).ls_performed;
+  EXPECT_GT(rep.ls_performed, (dim_t)0);
+  EXPECT_EQ(rep.ls_performed, als_performed);
+  for (size_t p = 0; p < ranks.size(); p++) {
+    EXPECT_NEAR(reconstruction_gap(by_als[p], by_cals[p]), 0.0, kModelTol);
+    EXPECT_EQ(by_als[p].get_iters(), by_cals[p].get_iters());
+  }
+}
+TEST(Cals, LineSearchWithoutErrorCheckingEqualsOneByOneAls) { line_search_case(cals::ls::NO_ERROR_CHECKING); }
+TEST(Cals, LineSearchWithErrorCheckingEqualsOneByOneAls) { line_search_case(cals::ls::ERROR_CHECKING_SERIAL); }
+
 // reference CalsJackknifingTests.LogicCorrectness (tests/cals/test_cals.cpp:181-297): a model flagged "leave sample i
 // out" inside cp_cals must equal cp_als on the tensor with row i of mode 0 deleted.
 TEST(Cals, FlaggedModelsEqualAlsOnRowDeletedTensors) {
@@ -336,6 +383,7 @@ TEST(Cals, OptionsOutsideThePathAreRejectedLoudly) {
   auto q = queue_of(models);
   bool thrown = false;
   cp.line_search = true;
+  cp.line_search_method = cals::ls::ERROR_CHECKING_PARALLEL; // not dispatched by the reference either
   try {
     cals::cp_cals(T, q, cp);
   } catch (const cals::B200Error &) {

@@ -79,7 +79,8 @@ def test_python_ktensor_host_logic(pkg):
     p = pkg.CalsParams()
     assert (p.max_iterations, p.tol, p.buffer_size, p.force_max_iter) == (200, 1e-7, 4200, False)
     with pytest.raises(pkg.CalsB200Error):
-        pkg._check_params(pkg.CalsParams(line_search=True))
+        pkg._check_params(pkg.CalsParams(line_search=True, line_search_method="error-checking-parallel"))
+    pkg._check_params(pkg.CalsParams(line_search=True))
     with pytest.raises(pkg.CalsB200Error):
         pkg._check_params(pkg.CalsParams(update_method="simplex"))
     pkg._check_params(pkg.CalsParams(update_method="nnls"))

@@ -115,6 +115,23 @@ def test_nnls_active_sets_persist_across_calls(pkg):
             assert F.min() >= 0.0
 
 
+@pytest.mark.parametrize("name", ["ls_noerr_3d_queue", "ls_errcheck_3d"])
+def test_cp_cals_line_search_matches_golden(pkg, name):
+    """Line search on the device (csrc/ls.cuh) against the reference's outputs, both methods."""
+    X, ins, refs, params, report = load_golden(name)
+    kts = to_ktensors(pkg, ins)
+    method = {0: "no-error-checking", 1: "error-checking-serial"}[params["ls_method"]]
+    p = pkg.CalsParams(max_iterations=params["max_iter"], tol=params["tol"], buffer_size=params["buffer_size"],
+                       force_max_iter=True, line_search=True, line_search_method=method,
+                       line_search_interval=params["ls_interval"], line_search_step=params["ls_step"])
+    rep = pkg.cp_cals(X, kts, p)
+    want = oracle.cp_cals(X, ins, **params)
+    assert rep.iter == report["iter"] == want.iters
+    assert (rep.ls_performed, rep.ls_failed) == (want.ls_performed, want.ls_failed)
+    assert rep.ls_performed > 0
+    assert_models_close(kts, refs, report["x_norm"], rtol=1e-8, what=name)
+
+
 def test_cp_cals_queue_tol_golden(pkg):
     """tol-based stopping with queueing/eviction/compaction (buffer 14 < sum of ranks).  Stopping can flip by one
     iteration through rounding (the fast error is a cancellation), so iteration counts are compared leniently and

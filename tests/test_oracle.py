@@ -13,7 +13,7 @@ import oracle
 from helpers import RTOL, assert_models_close, load_golden
 
 GOLDEN_CASES = ["forced_3d_k1", "forced_3d_k2", "forced_3d_k5", "queue_tol_3d", "forced_4d_queue", "jackknife_3d",
-                "evict_first_3d", "nnls_3d_queue", "nnls_4d_tol"]
+                "evict_first_3d", "nnls_3d_queue", "nnls_4d_tol", "ls_noerr_3d_queue", "ls_errcheck_3d"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
