@@ -326,6 +326,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--strong", action="store_true", help="N > 1: shard ONE model set over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-of", type=int, default=0, help="tuning aid on ONE GPU: run only the first shard of an "
+                    "N-way --strong split (what each GPU of an N-GPU job gets)")
     ap.add_argument("--nnls", action="store_true", help="measurement aid: update_method = NNLS instead of the Cholesky solve")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -367,6 +369,10 @@ def main():
     if args.strong and world > 1:
         mine = dmod.shard_models([fs[0].shape[1] for fs in models], world)[rank]
         models, jk = [models[i] for i in mine], [jk[i] for i in mine]
+    if args.shard_of > 1 and world == 1:
+        mine = dmod.shard_models([fs[0].shape[1] for fs in models], args.shard_of)[0]
+        models, jk = [models[i] for i in mine], [jk[i] for i in mine]
+        total_models = len(models)
     nX = X.size
     C = sum(fs[0].shape[1] for fs in models)
     n_models = len(models)
