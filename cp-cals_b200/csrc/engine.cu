@@ -365,12 +365,16 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
     tile_elems = std::max(tile_elems, (size_t)tile_m(b.wm[n]) * TILE_N);
     if (dev_alloc(c, &b.plans.plan[n], (size_t)plan_capacity(c->sm_count, pairs_max), b.allocs))
       return 1;
-    b.plans.In[n] = c->xd[n];
-    b.plans.WM[n] = b.wm[n];
+    b.plans.shape[n].In = c->xd[n];
+    b.plans.shape[n].WM = b.wm[n];
+    b.plans.shape[n].Ip = b.mg[n].Ip;
+    b.plans.shape[n].Iq = b.mg[n].outer_dim[0];
+    b.plans.shape[n].S = b.mg[n].S;
     const long long tp = (long long)b.mg[n].P_tiles * b.mg[n].S * b.mg[n].QC;
     if (tp * pairs_max > 0x7fffffffLL)
       return fail(c, "tensor too large for 32-bit chunk indices");
-    b.plans.Tp[n] = (int)tp;
+    if (tp != plan_tp(b.plans.shape[n]))
+      return fail(c, "internal error: chunk count mismatch");
   }
   b.ws_tiles = tiles;
   if (dev_alloc(c, &b.ws, tiles * tile_elems, b.allocs))

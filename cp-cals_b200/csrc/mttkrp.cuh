@@ -177,8 +177,62 @@ __host__ __device__ inline PlanView plan_view(const int *plan, int G) {
   return v;
 }
 
-// Builds the plan for one mode.  O(G + pairs) integer steps, single thread.
-__host__ __device__ inline void mttkrp_make_plan(int *plan, int In, int WM, int C, int Tp, int G) {
+// Shape of one mode's chunk space: a chunk is (K tile pt, slow outer index sl, chunk qc of OC fastest-outer indices),
+// qc fastest; Tp = P_tiles * S * QC chunks per (m,n) pair.
+struct PlanShape {
+  int In, WM; // rows of G on this device, tallest m-tile in m8 groups
+  int Ip;     // extent of the contiguous (K) mode  -> P_tiles = ceil(Ip / KT), the last tile may hold fewer K8 groups
+  int Iq;     // extent of the fastest outer mode   -> QC = ceil(Iq / OC), the last chunk may hold fewer stages
+  int S;      // product of the slower outer extents
+};
+__host__ __device__ inline int plan_p_tiles(const PlanShape &sh) { return (sh.Ip + KT - 1) / KT; }
+__host__ __device__ inline int plan_qc(const PlanShape &sh) { return (sh.Iq + OC - 1) / OC; }
+__host__ __device__ inline long long plan_tp(const PlanShape &sh) {
+  return (long long)plan_p_tiles(sh) * sh.S * plan_qc(sh);
+}
+
+// Cost model (unit: one DMMA issue slot of one warp).  A stage (one outer index) costs groups * 2*nm*nn DMMAs plus
+// PLAN_STAGE_COST of barrier / weight bookkeeping; a chunk adds PLAN_FIXED_COST.  Chunks of a pair are NOT equally
+// expensive: the last chunk of every OC-run holds Iq - (QC-1)*OC stages and the last K tile ceil(tail/8) groups, which
+// is what unbalanced ragged shapes (299 x 301 x 41) under the old equal-weight split.
+constexpr int PLAN_STAGE_COST = 4;
+struct PairCost {
+  long long stage_full, stage_tail; // cost of one stage in a full / in the last K tile
+  int P_tiles, QC, S, Iq;
+  __host__ __device__ long long row(bool tail_k) const { // all QC chunks of one (pt, sl)
+    return (long long)Iq * (tail_k ? stage_tail : stage_full) + (long long)QC * PLAN_FIXED_COST;
+  }
+  __host__ __device__ long long prefix(long long k) const { // cost of the first k chunks of the pair
+    const long long per_pt = (long long)S * QC;
+    const long long pt = k / per_pt, rem = k - pt * per_pt;
+    const long long sl = rem / QC, qc = rem - sl * QC;
+    const bool tail = (pt >= P_tiles - 1);
+    const long long full_pts = pt < P_tiles - 1 ? pt : P_tiles - 1;
+    long long c = full_pts * S * row(false);
+    if (pt >= P_tiles) // k == Tp
+      return c + (long long)S * row(true);
+    c += sl * row(tail);
+    c += qc * ((long long)OC * (tail ? stage_tail : stage_full) + PLAN_FIXED_COST); // chunks before qc are full ones
+    return c;
+  }
+};
+__host__ __device__ inline PairCost plan_pair_cost(const PlanShape &sh, int nm, int nn) {
+  PairCost pc;
+  const int P_tiles = plan_p_tiles(sh);
+  const int tail_groups = (sh.Ip - (P_tiles - 1) * KT + 7) / 8;
+  pc.stage_full = (long long)(KT / 8) * 2 * nm * nn + PLAN_STAGE_COST;
+  pc.stage_tail = (long long)tail_groups * 2 * nm * nn + PLAN_STAGE_COST;
+  pc.P_tiles = P_tiles;
+  pc.QC = plan_qc(sh);
+  pc.S = sh.S;
+  pc.Iq = sh.Iq;
+  return pc;
+}
+
+// Builds the plan for one mode.  O((G + pairs) * log Tp) integer steps, single thread.
+__host__ __device__ inline void mttkrp_make_plan(int *plan, const PlanShape &sh, int C, int G) {
+  const int In = sh.In, WM = sh.WM;
+  const int Tp = (int)plan_tp(sh);
   const int In8 = (In + 7) / 8, NO = (C + 63) / 64;
   const int m_tiles = (In8 + WM - 1) / WM;
   const int n_tiles = (NO + OCT_TILE - 1) / OCT_TILE;
@@ -186,11 +240,16 @@ __host__ __device__ inline void mttkrp_make_plan(int *plan, int In, int WM, int 
   const long long total = (long long)pairs * Tp;
   const int G_eff = (int)(total < (long long)G ? total : (long long)G);
   int *cta_lo = plan + PLAN_HDR, *cta_seg0 = plan + PLAN_HDR + (G + 1), *pair_seg0 = plan + PLAN_HDR + (G + 1) + G;
-  // total weight: sum over pairs of Tp * (2*nm*nn + fixed);  sum_mt nm = In8, sum_nt nn = NO
-  const long long W = (long long)Tp * (2LL * In8 * NO + (long long)PLAN_FIXED_COST * pairs);
+  // total weight
+  long long W = 0;
+  for (int pi = 0; pi < pairs; pi++) {
+    const int nt = pi / m_tiles, mt = pi - nt * m_tiles;
+    W += plan_pair_cost(sh, plan_wm(mt, In8, m_tiles), plan_nn(nt, NO, n_tiles)).prefix(Tp);
+  }
 
   int pi = 0, k = 0, seg = 0;
   long long cw = 0, done = 0;
+  PairCost pc = plan_pair_cost(sh, plan_wm(0, In8, m_tiles), plan_nn(0, NO, n_tiles));
   for (int b = 0; b < G_eff; b++) {
     cta_lo[b] = (int)done;
     cta_seg0[b] = seg;
@@ -198,11 +257,23 @@ __host__ __device__ inline void mttkrp_make_plan(int *plan, int In, int WM, int 
     const long long must_leave = G_eff - b - 1;
     long long taken = 0;
     while (pi < pairs) {
-      const int nt = pi / m_tiles, mt = pi - nt * m_tiles;
-      const long long w = 2LL * plan_wm(mt, In8, m_tiles) * plan_nn(nt, NO, n_tiles) + PLAN_FIXED_COST;
       const long long r = Tp - k;
       const long long avail = total - done - must_leave;
-      long long want = (cw + r * w <= target) ? r : (target - cw) / w;
+      const long long base = pc.prefix(k);
+      long long want;
+      if (cw + (pc.prefix(Tp) - base) <= target)
+        want = r;
+      else { // largest want with cw + cost(k .. k+want) <= target
+        long long lo = 0, hi = r;
+        while (lo < hi) {
+          const long long mid = (lo + hi + 1) / 2;
+          if (cw + (pc.prefix(k + mid) - base) <= target)
+            lo = mid;
+          else
+            hi = mid - 1;
+        }
+        want = lo;
+      }
       if (taken == 0 && want <= 0)
         want = 1;
       if (want > r)
@@ -214,13 +285,17 @@ __host__ __device__ inline void mttkrp_make_plan(int *plan, int In, int WM, int 
       if (k == 0)
         pair_seg0[pi] = seg;
       seg++;
+      cw += pc.prefix(k + want) - base;
       k += (int)want;
-      cw += want * w;
       done += want;
       taken += want;
       if (k == Tp) {
         pi++;
         k = 0;
+        if (pi < pairs) {
+          const int nt = pi / m_tiles, mt = pi - nt * m_tiles;
+          pc = plan_pair_cost(sh, plan_wm(mt, In8, m_tiles), plan_nn(nt, NO, n_tiles));
+        }
       } else
         break;
     }
@@ -243,14 +318,14 @@ __host__ __device__ inline void mttkrp_make_plan(int *plan, int In, int WM, int 
 // One thread per mode builds its plan (test hook path; the run loop plans inside sched_kernel).
 struct PlanArgs {
   int n_modes;
-  int In[CALS_MAX_MODES], WM[CALS_MAX_MODES], Tp[CALS_MAX_MODES];
+  PlanShape shape[CALS_MAX_MODES];
   int *plan[CALS_MAX_MODES];
   int G;
 };
 __global__ void mttkrp_plan_kernel(const PlanArgs a, int C) {
   const int n = threadIdx.x;
   if (n < a.n_modes && a.plan[n])
-    mttkrp_make_plan(a.plan[n], a.In[n], a.WM[n], C, a.Tp[n], a.G);
+    mttkrp_make_plan(a.plan[n], a.shape[n], C, a.G);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -502,7 +577,12 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
     const int sl = lc % g.S, pt = lc / g.S;
     // number of valid m8 row groups / n8 column groups of this pair (CTA-uniform)
     const int nm = plan_wm(mt, pv.In8, m_tiles);
-    const int nn = plan_nn(nt, pv.NO, n_tiles);
+    int nn = plan_nn(nt, pv.NO, n_tiles);
+    // Only the last octet of the last n-tile can reach beyond C; a warp whose n8 group there starts at or beyond C has
+    // nothing to compute for it (the factor tile is zero-filled).  Warps w and w+4 share an SM sub-partition, so
+    // dropping the groups of the upper warps shortens the tile for every sub-partition alike.
+    if (64 * (plan_oct_start(nt, pv.NO, n_tiles) + nn - 1) + warp * 8 >= C)
+      nn -= 1;
     if (pair != prev_pair) {
       if (prev_pair >= 0)
         flush();
@@ -554,7 +634,8 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
       for (int j = 0; j < WN; j++)
         wv[j] = Wc[(j * 64 + r) * OC + o] * wslow[j];
       mbar_wait(&full_x[xs], xph);
-      mma_stage<WM, WN>(acc, Xs + xs * (M_TILE * KT), Bw, wv, ngroups, r, s, nm, nn);
+      if (nn > 0)
+        mma_stage<WM, WN>(acc, Xs + xs * (M_TILE * KT), Bw, wv, ngroups, r, s, nm, nn);
       __syncwarp();
       if (lane == 0)
         mbar_arrive(&empty_x[xs]);

@@ -42,8 +42,7 @@ __global__ void sched_kernel(const SchedParams p) {
   }
   __syncthreads();
   if (replan && (int)threadIdx.x < p.plans.n_modes)
-    mttkrp_make_plan(p.plans.plan[threadIdx.x], p.plans.In[threadIdx.x], p.plans.WM[threadIdx.x], p.st->C,
-                     p.plans.Tp[threadIdx.x], p.plans.G);
+    mttkrp_make_plan(p.plans.plan[threadIdx.x], p.plans.shape[threadIdx.x], p.st->C, p.plans.G);
 }
 
 __device__ void sched_serial(const SchedParams &p) {

@@ -13,12 +13,17 @@ int main() {
     for (int In : {1, 8, 41, 100, 200, 299, 1000})
       for (int WM : {4, 5, 6, 7})
         for (int C : {1, 7, 52, 220, 256, 257, 2100, 2691})
-          for (int Tp : {1, 2, 13, 125, 3125}) {
+          for (int shape_id = 0; shape_id < 7; shape_id++) {
+            // (Ip, Iq, S): single chunk, ragged K tail, ragged outer tail (41 = 5 * 8 + 1), config 2/3/4-like, 5 modes
+            static const int shapes[7][3] = {{1, 1, 1},    {7, 9, 1},    {301, 41, 1}, {200, 200, 1},
+                                             {299, 301, 1}, {80, 80, 80}, {20, 5, 12}};
+            PlanShape sh{In, WM, shapes[shape_id][0], shapes[shape_id][1], shapes[shape_id][2]};
+            const int Tp = (int)plan_tp(sh);
             const int In8 = (In + 7) / 8, NO = (C + 63) / 64;
             const int m_tiles = (In8 + WM - 1) / WM, n_tiles = (NO + OCT_TILE - 1) / OCT_TILE;
             const int pairs = m_tiles * n_tiles;
             std::vector<int> plan(plan_capacity(G, pairs) + 4, -12345);
-            mttkrp_make_plan(plan.data(), In, WM, C, Tp, G);
+            mttkrp_make_plan(plan.data(), sh, C, G);
             if (plan[plan_capacity(G, pairs)] != -12345) {
               printf("FAIL overrun\n");
               return 1;
@@ -97,14 +102,27 @@ int main() {
                   seg_pair[seg] = pair;
                 }
                 int nt = pair / m_tiles, mt = pair - nt * m_tiles;
-                long long w = 2LL * plan_wm(mt, In8, m_tiles) * plan_nn(nt, NO, n_tiles) + PLAN_FIXED_COST;
-                wcta += w;
-                if (w > wchunk_max)
-                  wchunk_max = w;
-                if (Tp > 64 && ch + 64 < hi && (ch + 64) / Tp == pair) { // fast-forward inside a pair
-                  wcta += 63 * w;
-                  ch += 63;
+                const PairCost pc = plan_pair_cost(sh, plan_wm(mt, In8, m_tiles), plan_nn(nt, NO, n_tiles));
+                // the rest of this CTA's range inside this pair in one step (the cost model has a closed-form prefix)
+                const long long k0 = ch - (long long)pair * Tp;
+                long long k1 = (long long)hi - (long long)pair * Tp;
+                if (k1 > Tp)
+                  k1 = Tp;
+                wcta += pc.prefix(k1) - pc.prefix(k0);
+                const long long one = pc.prefix(1); // a full chunk in a full K tile (or the only kind there is)
+                if (one > wchunk_max)
+                  wchunk_max = one;
+                // prefix is consistent with a chunk-by-chunk walk
+                if (k1 - k0 <= 50) {
+                  long long walk = 0;
+                  for (long long k = k0; k < k1; k++)
+                    walk += pc.prefix(k + 1) - pc.prefix(k);
+                  if (walk != pc.prefix(k1) - pc.prefix(k0) || pc.prefix(k0 + 1) <= pc.prefix(k0)) {
+                    printf("FAIL prefix\n");
+                    return 1;
+                  }
                 }
+                ch = (int)((long long)pair * Tp + k1) - 1;
               }
               wsum += wcta;
               if (wcta > wmax)
