@@ -41,7 +41,7 @@ def test_cpp_library_and_binaries_build():
     _build()
     for f in ("libcals.so", "libcals_b200.so"):
         assert os.path.exists(os.path.join(ROOT, "cp-cals_b200", f))
-    for f in ("driver", "test_cals", "test_als"):
+    for f in ("driver", "c_abi_demo", "test_cals", "test_als"):
         assert os.path.exists(os.path.join(BIN, f))
     syms = subprocess.run(["nm", "-DC", os.path.join(ROOT, "cp-cals_b200", "libcals.so")], capture_output=True,
                           text=True).stdout
@@ -114,3 +114,11 @@ def test_driver_example():
     rc, out = _run("driver", "-t", "100-100-100", "-c", "1:10:4", "-i", "20")
     assert rc == 0, out[-2000:]
     assert "800 model-iterations" in out
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_of_the_c_abi():
+    """examples/c_abi_demo.c: the boundary is usable from C (gcc, no C++ runtime on the caller's side)."""
+    rc, out = _run("c_abi_demo")
+    assert rc == 0, out[-2000:]
+    assert out.strip().endswith("OK") and "sm_100a" in out

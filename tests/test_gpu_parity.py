@@ -171,6 +171,25 @@ def test_cp_cals_per_iteration_vs_oracle(pkg, modes, ranks, K, buffer):
                 assert abs(g.fit - r.fit) <= RTOL and abs(g.old_fit - r.old_fit) <= RTOL
 
 
+def test_cp_cals_large_ranks_vs_oracle(pkg):
+    """Ranks as in BASELINE config 5 (up to 50) and beyond: the update kernel keeps two R x R matrices in shared
+    memory and stages the factor rows in chunks."""
+    rng = np.random.default_rng(50)
+    modes = (70, 66, 61)
+    gen = [rng.uniform(-1, 1, size=(i, 8)) for i in modes]
+    X = caseio.ktensor_to_tensor(gen, np.ones(8)) + 0.1 * rng.standard_normal(modes)
+    ranks = [50, 33, 64, 1]
+    ms = caseio.random_models(rng, modes, ranks)
+    K = 3
+    want = oracle.cp_cals(X, ms, max_iter=K, force_max_iter=True)
+    kts = to_ktensors(pkg, ms)
+    rep = pkg.cp_cals(X, kts, pkg.CalsParams(max_iterations=K, buffer_size=sum(ranks), force_max_iter=True))
+    assert rep.iter == K
+    # rank 64 > every extent but one: H is still positive definite here (Hadamard of three Gramians), so everything compares
+    assert all(k.chol_info == 0 for k in kts)
+    assert_models_close(kts, want.models, want.x_norm, rtol=1e-8, what="large ranks")
+
+
 def test_cp_cals_config1_shape_vs_oracle(pkg):
     """BASELINE config 1: 100x100x100, 40 models of ranks 1..10 x4, forced iterations."""
     rng = np.random.default_rng(1)
