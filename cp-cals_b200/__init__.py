@@ -37,6 +37,7 @@ ABI_SYMBOLS = [
     "cals_b200_comm_alloc", "cals_b200_comm_local_block", "cals_b200_comm_connect", "cals_b200_set_tensor_slab",
     "cals_b200_set_tensor_norm", "cals_b200_comm_disconnect", "cals_b200_set_model_active_set",
     "cals_b200_fetch_model_active_set", "cals_b200_set_line_search", "cals_b200_line_search_counts",
+    "cals_b200_enqueue_models",
 ]
 
 
@@ -104,6 +105,7 @@ def lib():
     L.cals_b200_set_tensor_slab.argtypes = [vp, i, C.POINTER(u64), i, C.POINTER(u64), vp]
     L.cals_b200_set_tensor_norm.argtypes = [vp, dbl]
     L.cals_b200_comm_disconnect.argtypes = [vp]
+    L.cals_b200_enqueue_models.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(vp), C.POINTER(i), C.POINTER(C.c_int64)]
     L.cals_b200_set_line_search.argtypes = [vp, i, i, i, dbl]
     L.cals_b200_line_search_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.cals_b200_set_model_active_set.argtypes = [vp, i, C.POINTER(vp)]
@@ -352,6 +354,35 @@ class Engine:
         self._ranks.append(rank)
         return mid.value
 
+    def enqueue_many(self, models: Sequence[Sequence[np.ndarray]], jk: Optional[Sequence[tuple]] = None):
+        """Queue a list of models with one call through the C ABI.  models[m][n] is (I_n, R_m); jk[m] = (mode, fiber)
+        or (-1, 0).  The arrays must be float64; Fortran-ordered ones are passed as they are (no copy)."""
+        N = len(self.modes)
+        keep, ptrs, ranks = [], [], []
+        for fs in models:
+            if len(fs) != N:
+                raise ValueError("a model has %d factors, the tensor has %d modes" % (len(fs), N))
+            R = fs[0].shape[1]
+            ranks.append(R)
+            for F, I in zip(fs, self.modes):
+                if F.shape != (I, R):
+                    raise ValueError("factor shape %s does not match (%d, %d)" % (F.shape, I, R))
+                if F.dtype != np.float64 or not F.flags.f_contiguous:
+                    F = np.asfortranarray(F, dtype=np.float64)
+                    keep.append(F)
+                ptrs.append(F.ctypes.data)
+        M = len(ranks)
+        a_ranks = (C.c_uint64 * M)(*ranks)
+        a_ptrs = (C.c_void_p * (M * N))(*ptrs)
+        a_jm = a_jf = None
+        if jk is not None and any(j[0] >= 0 for j in jk):
+            a_jm = (C.c_int * M)(*[j[0] for j in jk])
+            a_jf = (C.c_int64 * M)(*[j[1] for j in jk])
+        self._ck(self._L.cals_b200_enqueue_models(self._ctx, M, a_ranks, a_ptrs, a_jm, a_jf))
+        if not hasattr(self, "_ranks"):
+            self._ranks = []
+        self._ranks.extend(ranks)
+
     # -- run ---------------------------------------------------------------------------------------------------------------
     def run(self) -> Report:
         rep = Report()
@@ -388,10 +419,22 @@ class Engine:
     def fetch_all(self):
         """All models of the last run with ONE call through the C ABI: [(factors, lam, stats), ...] in queue order."""
         M, N = len(self._ranks), len(self.modes)
-        fs = [[np.empty((I, r), order="F") for I in self.modes] for r in self._ranks]
-        lams = [np.empty(r) for r in self._ranks]
-        fptr = (C.c_void_p * (M * N))(*[F.ctypes.data for row in fs for F in row])
-        lptr = (C.c_void_p * M)(*[l.ctypes.data for l in lams])
+        # one allocation per mode (and one for lambda) holding all models side by side; every model gets column views
+        total = sum(self._ranks)
+        big = [np.empty((I, total), order="F") for I in self.modes]
+        lam_all = np.empty(total)
+        base = [b.ctypes.data for b in big]
+        lbase = lam_all.ctypes.data
+        fptr = (C.c_void_p * (M * N))()
+        lptr = (C.c_void_p * M)()
+        fs, lams, col = [], [], 0
+        for m, r in enumerate(self._ranks):
+            fs.append([b[:, col:col + r] for b in big])
+            lams.append(lam_all[col:col + r])
+            for n, I in enumerate(self.modes):
+                fptr[m * N + n] = base[n] + 8 * I * col
+            lptr[m] = lbase + 8 * col
+            col += r
         stats = (ModelStats * M)()
         self._ck(self._L.cals_b200_fetch_all(self._ctx, fptr, lptr, stats))
         return [(fs[m], lams[m], stats[m]) for m in range(M)]
@@ -460,8 +503,7 @@ def cp_cals(X: np.ndarray, ktensors: Sequence[Ktensor], params: CalsParams, *, e
         eng.set_timing(timing)
         eng.set_mttkrp_variant(mttkrp_variant)
         eng.clear_models()
-        for kt in ktensors:
-            eng.enqueue(kt.factors, kt.jk_mode, kt.jk_fiber)
+        eng.enqueue_many([kt.factors for kt in ktensors], [(kt.jk_mode, kt.jk_fiber) for kt in ktensors])
         if nnls:  # active sets persist in the Ktensor across calls (reference include/ktensor.h:36)
             for i, kt in enumerate(ktensors):
                 if kt.active_set is not None:

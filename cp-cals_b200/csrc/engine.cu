@@ -1383,6 +1383,18 @@ int cals_b200_enqueue_model(cals_b200_ctx *c, uint64_t rank, const double *const
   return 0;
 }
 
+int cals_b200_enqueue_models(cals_b200_ctx *c, uint64_t n_models, const uint64_t *ranks,
+                             const double *const *host_factors, const int *jk_modes, const int64_t *jk_fibers) {
+  if (!c || !ranks || !host_factors)
+    return fail(c, "null argument");
+  const int N = c->geo.n_modes;
+  for (uint64_t m = 0; m < n_models; m++)
+    if (cals_b200_enqueue_model(c, ranks[m], host_factors + m * N, jk_modes ? jk_modes[m] : -1,
+                                jk_fibers ? jk_fibers[m] : 0, nullptr))
+      return 1;
+  return 0;
+}
+
 int cals_b200_run(cals_b200_ctx *c, cals_b200_report *rep) {
   if (!c)
     return 1;

@@ -577,12 +577,7 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
     const int sl = lc % g.S, pt = lc / g.S;
     // number of valid m8 row groups / n8 column groups of this pair (CTA-uniform)
     const int nm = plan_wm(mt, pv.In8, m_tiles);
-    int nn = plan_nn(nt, pv.NO, n_tiles);
-    // Only the last octet of the last n-tile can reach beyond C; a warp whose n8 group there starts at or beyond C has
-    // nothing to compute for it (the factor tile is zero-filled).  Warps w and w+4 share an SM sub-partition, so
-    // dropping the groups of the upper warps shortens the tile for every sub-partition alike.
-    if (64 * (plan_oct_start(nt, pv.NO, n_tiles) + nn - 1) + warp * 8 >= C)
-      nn -= 1;
+    const int nn = plan_nn(nt, pv.NO, n_tiles);
     if (pair != prev_pair) {
       if (prev_pair >= 0)
         flush();
@@ -634,8 +629,7 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
       for (int j = 0; j < WN; j++)
         wv[j] = Wc[(j * 64 + r) * OC + o] * wslow[j];
       mbar_wait(&full_x[xs], xph);
-      if (nn > 0)
-        mma_stage<WM, WN>(acc, Xs + xs * (M_TILE * KT), Bw, wv, ngroups, r, s, nm, nn);
+      mma_stage<WM, WN>(acc, Xs + xs * (M_TILE * KT), Bw, wv, ngroups, r, s, nm, nn);
       __syncwarp();
       if (lane == 0)
         mbar_arrive(&empty_x[xs]);

@@ -121,6 +121,11 @@ int cals_b200_clear_models(cals_b200_ctx *ctx);
 int cals_b200_enqueue_model(cals_b200_ctx *ctx, uint64_t rank, const double *const *host_factors, int jk_mode,
                             int64_t jk_fiber, int *model_id);
 
+/* The same for a whole queue in one call: host_factors[m * n_modes + n]; jk_modes / jk_fibers may be NULL (no
+ * jackknife models).  Model ids are the queue positions. */
+int cals_b200_enqueue_models(cals_b200_ctx *ctx, uint64_t n_models, const uint64_t *ranks,
+                             const double *const *host_factors, const int *jk_modes, const int64_t *jk_fibers);
+
 /* ---- the hot path: the do/while loop of cals::cp_cals (reference src/cals.cpp:174-382) ------------------------- */
 /* Uploads the queued models, runs concurrent ALS until every model has been evicted, leaves results on the device. */
 int cals_b200_run(cals_b200_ctx *ctx, cals_b200_report *report);
