@@ -255,3 +255,43 @@ def test_jk_cp_cals_vs_oracle(pkg):
                 a[got.jk_fiber] = 0.0
             assert rel_err(a, b) <= RTOL
         assert rel_err(got.lam, wk.lam) <= RTOL
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_cp_cals_random_configurations_vs_oracle(pkg, seed):
+    """Randomised sweep: number of modes, ragged extents, ranks, buffer sizes (queueing / eviction / compaction),
+    jackknife flags and the update method are drawn at random; forced iteration counts so that the comparison is exact
+    in the discrete outcomes (iterations, admissions) and within 1e-8 in the values."""
+    rng = np.random.default_rng(1000 + seed)
+    N = int(rng.integers(3, 6))
+    modes = tuple(int(x) for x in rng.integers(2, [40, 30, 20, 8, 6][:N], endpoint=True))
+    n_models = int(rng.integers(1, 12))
+    ranks = [int(r) for r in rng.integers(1, 9, size=n_models)]
+    nnls = bool(rng.integers(0, 3) == 0)
+    K = int(rng.integers(1, 7))
+    buffer = int(rng.integers(max(ranks), sum(ranks) + 1))
+    R0 = int(rng.integers(2, 5))
+    gen = [rng.uniform(0 if nnls else -1, 1, size=(i, R0)) for i in modes]
+    X = caseio.ktensor_to_tensor(gen, np.ones(R0)) + 0.05 * rng.standard_normal(modes)
+    ms = caseio.random_models(rng, modes, ranks)
+    if not nnls:
+        for m in ms:
+            if rng.integers(0, 4) == 0:  # leave-one-out flag on some models (any mode, as Ktensor::to_jk allows)
+                m.jk_mode = int(rng.integers(0, N))
+                m.jk_fiber = int(rng.integers(0, modes[m.jk_mode]))
+                m.factors[m.jk_mode][m.jk_fiber, :] = 0.0
+    # the reference keeps jackknife norms for mode 0 only (src/utils/utils.cpp:103): restrict flags to mode 0 fibres
+    for m in ms:
+        if m.jk_mode > 0:
+            m.factors[m.jk_mode][m.jk_fiber, :] = rng.uniform(-1, 1, size=m.rank)
+            m.jk_mode, m.jk_fiber = 0, int(rng.integers(0, modes[0]))
+            m.factors[0][m.jk_fiber, :] = 0.0
+    want = oracle.cp_cals(X, ms, max_iter=K, force_max_iter=True, buffer_size=buffer, nnls=nnls)
+    kts = to_ktensors(pkg, ms)
+    rep = pkg.cp_cals(X, kts, pkg.CalsParams(max_iterations=K, buffer_size=buffer, force_max_iter=True,
+                                             update_method="nnls" if nnls else "unconstrained"))
+    tag = "seed %d: modes %s ranks %s K %d buffer %d nnls %s" % (seed, modes, ranks, K, buffer, nnls)
+    assert (rep.iter, rep.n_ktensors, rep.ktensor_comp_sum) == (want.iters, want.n_ktensors, want.comp_sum), tag
+    clean = [i for i, w in enumerate(want.models) if not w.chol_fail and not kts[i].chol_info]
+    assert len(clean) >= len(ms) - 2, tag  # singular systems (rank > extents) have nothing to compare
+    assert_models_close([kts[i] for i in clean], [want.models[i] for i in clean], want.x_norm, rtol=1e-7, what=tag)
