@@ -443,7 +443,8 @@ def main():
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
-    roofline = {"bound": "tensor", "kernel": "mttkrp_dmma_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+    roofline = {"bound": "tensor", "kernel": "mttkrp_dmma_kernel (timed together with its mttkrp_reduce_kernel)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "mttkrp_ms_per_launch": mt_ms / mt_launches, "flops_per_launch": flops_per_launch,
                 "mttkrp_share_of_step": mt_ms / (mt_ms + up_ms) if mt_ms + up_ms > 0 else None}

@@ -1,8 +1,10 @@
-// Wall-clock timers with the reference's names (reference include/timer.h:8-54), so CalsReport / AlsReport CSV
-// columns keep their meaning.  On the B200 path the per-phase numbers come from CUDA events (cals_b200_report).
+// Wall-clock timers and the three timer groups whose names end up as CSV columns of CalsReport / AlsReport
+// (counterpart of the reference's include/timer.h; the group and member names are part of the API).  On the B200 path
+// the per-phase numbers come from CUDA events (cals_b200_report) and are loaded into these objects with Timer::set.
 #ifndef CALS_B200_TIMER_H
 #define CALS_B200_TIMER_H
 
+#include <array>
 #include <chrono>
 #include <string>
 
@@ -11,37 +13,49 @@ namespace cals {
 class Timer {
   using clock = std::chrono::steady_clock;
   clock::time_point begin_{};
-  double seconds_{-1.0}; // < 0: never stopped
+  double seconds_{-1.0}; // negative: never stopped, reads as 0
 
 public:
   void start() { begin_ = clock::now(); }
   void stop() { seconds_ = std::chrono::duration<double>(clock::now() - begin_).count(); }
   void reset() { seconds_ = 0.0; }
-  void set(double seconds) { seconds_ = seconds; } // extension: load a device-measured time
+  void set(double seconds) { seconds_ = seconds; } // extension: a time measured on the device
   [[nodiscard]] double get_time() const { return seconds_ < 0.0 ? 0.0 : seconds_; }
 };
 
 namespace detail {
-template <int N> struct TimerSet {
-  Timer timers[N];
-  Timer &operator[](int i) { return timers[i]; }
-  const Timer &operator[](int i) const { return timers[i]; }
+// N timers addressed by an enum, plus the column names that go with them.
+template <int N> struct TimerGroup {
+  std::array<Timer, N> timers{};
+  std::string names[N];
+  Timer &operator[](int which) { return timers[static_cast<size_t>(which)]; }
+  const Timer &operator[](int which) const { return timers[static_cast<size_t>(which)]; }
+
+protected:
+  TimerGroup(std::initializer_list<const char *> labels) {
+    int i = 0;
+    for (const char *l : labels)
+      names[i++] = l;
+  }
 };
 } // namespace detail
 
-struct MttkrpTimers : detail::TimerSet<4> {
+// Inside one MTTKRP (the reference's KRP + GEMM / two-step split; one fused kernel here, so these stay 0).
+struct MttkrpTimers : detail::TimerGroup<4> {
   enum TIMERS { MT_KRP = 0, MT_GEMM, TS_GEMM, TS_GEMV, LENGTH };
-  std::string names[LENGTH] = {"MT_KRP", "MT_GEMM", "TS_GEMM", "TS_GEMV"};
+  MttkrpTimers() : TimerGroup({"MT_KRP", "MT_GEMM", "TS_GEMM", "TS_GEMV"}) {}
 };
 
-struct ModeTimers : detail::TimerSet<2> {
+// Per mode of one ALS iteration.
+struct ModeTimers : detail::TimerGroup<2> {
   enum TIMERS { MTTKRP = 0, UPDATE, LENGTH };
-  std::string names[LENGTH] = {"TOTAL_MTTKRP", "UPDATE"};
+  ModeTimers() : TimerGroup({"TOTAL_MTTKRP", "UPDATE"}) {}
 };
 
-struct AlsTimers : detail::TimerSet<5> {
+// Per ALS / CALS iteration.
+struct AlsTimers : detail::TimerGroup<5> {
   enum TIMERS { ITERATION = 0, DEFRAGMENTATION, ERROR, LINE_SEARCH, G_COPY, LENGTH };
-  std::string names[LENGTH] = {"ITERATION", "DEFRAGMENTATION", "ERROR", "LINESEARCH", "G_COPY"};
+  AlsTimers() : TimerGroup({"ITERATION", "DEFRAGMENTATION", "ERROR", "LINESEARCH", "G_COPY"}) {}
 };
 
 } // namespace cals
