@@ -281,7 +281,7 @@ int build_mode_plans(cals_b200_ctx *c, Buffers &b) {
     long long S = 1;
     for (int k = 1; k < no; k++)
       S *= g.outer_dim[k];
-    if (S > 0x7fffffff / std::max(1, g.QC * g.P_tiles))
+    if (S > 0x7fffffff / std::max(1, g.outer_dim[0] * g.P_tiles))
       return fail(c, "tensor too large for 32-bit chunk indices");
     g.S = (int)S;
     const int wm = pick_wm(g.In);
@@ -370,7 +370,7 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
     b.plans.shape[n].Ip = b.mg[n].Ip;
     b.plans.shape[n].Iq = b.mg[n].outer_dim[0];
     b.plans.shape[n].S = b.mg[n].S;
-    const long long tp = (long long)b.mg[n].P_tiles * b.mg[n].S * b.mg[n].QC;
+    const long long tp = (long long)b.mg[n].P_tiles * b.mg[n].S * b.mg[n].outer_dim[0];
     if (tp * pairs_max > 0x7fffffffLL)
       return fail(c, "tensor too large for 32-bit chunk indices");
     if (tp != plan_tp(b.plans.shape[n]))

@@ -121,16 +121,15 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 //     warp), again an even split.  Inside a tile, octet j / group w (columns 64*j + 8*w ..) belongs to warp w, so every
 //     warp of a CTA has the same number nn of column groups and no per-warp predicates are needed; only the last octet
 //     of the last tile can reach beyond C, where TMA zero-fills the factor tile.
-//   * Every (m,n) pair has Tp K-chunks; a chunk of pair (mt, nt) gets the weight 2*nm(mt)*nn(nt) + PLAN_FIXED_COST
-//     (DMMAs per K8 group per warp plus the per-stage overhead in the same unit).  The flattened chunk sequence is cut
-//     into G_eff = min(G, #chunks) contiguous ranges of (nearly) equal weight, every range non-empty.
-//   * A "segment" is the part of one CTA's range that lies in one pair; segments are numbered globally in chunk order
+//   * Every (m,n) pair has Tp stages (PlanShape below); a stage of pair (mt, nt) is priced by the DMMAs it issues,
+//     groups * 2*nm(mt)*nn(nt), plus a fixed per-stage cost.  The flattened stage sequence is cut into
+//     G_eff = min(G, #stages) contiguous ranges of (nearly) equal cost, every range non-empty.
+//   * A "segment" is the part of one CTA's range that lies in one pair; segments are numbered globally in stage order
 //     and segment s writes workspace tile s.  The segments of a pair are consecutive: the reduce kernel sums tiles
 //     pair_seg0[pair] .. pair_seg0[pair+1]-1 in that order (deterministic, no atomics).
 constexpr int N8_TILE = 32; // n8 groups per full n-tile (8 warps x WN = 4)
 constexpr int OCT_TILE = 4; // octets per full n-tile
 constexpr int PLAN_HDR = 8;
-constexpr int PLAN_FIXED_COST = 8;
 
 struct PlanView {
   int n_tiles, m_tiles, pairs, Tp, G_eff, n_segments, NO, In8; // NO = number of 64-column octets covering C
@@ -177,43 +176,31 @@ __host__ __device__ inline PlanView plan_view(const int *plan, int G) {
   return v;
 }
 
-// Shape of one mode's chunk space: a chunk is (K tile pt, slow outer index sl, chunk qc of OC fastest-outer indices),
-// qc fastest; Tp = P_tiles * S * QC chunks per (m,n) pair.
+// Shape of one mode's work space.  The unit of work is a STAGE: one X tile (K tile pt, slow outer index sl, fastest
+// outer index iq), iq fastest; Tp = P_tiles * S * Iq stages per (m,n) pair.  Stages are grouped in chunks of OC
+// consecutive iq (one weight-tile load per chunk); a CTA's range may begin and end inside a chunk.
 struct PlanShape {
   int In, WM; // rows of G on this device, tallest m-tile in m8 groups
   int Ip;     // extent of the contiguous (K) mode  -> P_tiles = ceil(Ip / KT), the last tile may hold fewer K8 groups
-  int Iq;     // extent of the fastest outer mode   -> QC = ceil(Iq / OC), the last chunk may hold fewer stages
+  int Iq;     // extent of the fastest outer mode
   int S;      // product of the slower outer extents
 };
 __host__ __device__ inline int plan_p_tiles(const PlanShape &sh) { return (sh.Ip + KT - 1) / KT; }
-__host__ __device__ inline int plan_qc(const PlanShape &sh) { return (sh.Iq + OC - 1) / OC; }
 __host__ __device__ inline long long plan_tp(const PlanShape &sh) {
-  return (long long)plan_p_tiles(sh) * sh.S * plan_qc(sh);
+  return (long long)plan_p_tiles(sh) * sh.S * sh.Iq;
 }
 
-// Cost model (unit: one DMMA issue slot of one warp).  A stage (one outer index) costs groups * 2*nm*nn DMMAs plus
-// PLAN_STAGE_COST of barrier / weight bookkeeping; a chunk adds PLAN_FIXED_COST.  Chunks of a pair are NOT equally
-// expensive: the last chunk of every OC-run holds Iq - (QC-1)*OC stages and the last K tile ceil(tail/8) groups, which
-// is what unbalanced ragged shapes (299 x 301 x 41) under the old equal-weight split.
-constexpr int PLAN_STAGE_COST = 4;
+// Cost model (unit: one DMMA issue slot of one warp): a stage costs groups * 2*nm*nn DMMAs plus PLAN_STAGE_COST of
+// barrier / weight bookkeeping (the per-chunk weight-tile wait spread over its stages).  Stages of the last K tile hold
+// ceil(tail / 8) groups instead of KT / 8 and are priced as such -- what an equal-weight split gets wrong on ragged
+// shapes (299 x 301 x 41).
+constexpr int PLAN_STAGE_COST = 5;
 struct PairCost {
   long long stage_full, stage_tail; // cost of one stage in a full / in the last K tile
-  int P_tiles, QC, S, Iq;
-  __host__ __device__ long long row(bool tail_k) const { // all QC chunks of one (pt, sl)
-    return (long long)Iq * (tail_k ? stage_tail : stage_full) + (long long)QC * PLAN_FIXED_COST;
-  }
-  __host__ __device__ long long prefix(long long k) const { // cost of the first k chunks of the pair
-    const long long per_pt = (long long)S * QC;
-    const long long pt = k / per_pt, rem = k - pt * per_pt;
-    const long long sl = rem / QC, qc = rem - sl * QC;
-    const bool tail = (pt >= P_tiles - 1);
-    const long long full_pts = pt < P_tiles - 1 ? pt : P_tiles - 1;
-    long long c = full_pts * S * row(false);
-    if (pt >= P_tiles) // k == Tp
-      return c + (long long)S * row(true);
-    c += sl * row(tail);
-    c += qc * ((long long)OC * (tail ? stage_tail : stage_full) + PLAN_FIXED_COST); // chunks before qc are full ones
-    return c;
+  long long full_stages;            // stages of the pair that lie in full K tiles
+  __host__ __device__ long long prefix(long long k) const { // cost of the first k stages of the pair
+    const long long nf = k < full_stages ? k : full_stages;
+    return nf * stage_full + (k - nf) * stage_tail;
   }
 };
 __host__ __device__ inline PairCost plan_pair_cost(const PlanShape &sh, int nm, int nn) {
@@ -222,10 +209,7 @@ __host__ __device__ inline PairCost plan_pair_cost(const PlanShape &sh, int nm, 
   const int tail_groups = (sh.Ip - (P_tiles - 1) * KT + 7) / 8;
   pc.stage_full = (long long)(KT / 8) * 2 * nm * nn + PLAN_STAGE_COST;
   pc.stage_tail = (long long)tail_groups * 2 * nm * nn + PLAN_STAGE_COST;
-  pc.P_tiles = P_tiles;
-  pc.QC = plan_qc(sh);
-  pc.S = sh.S;
-  pc.Iq = sh.Iq;
+  pc.full_stages = (long long)(P_tiles - 1) * sh.S * sh.Iq;
   return pc;
 }
 
@@ -482,13 +466,17 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
     uint32_t xph = 1, wph = 1; // ring "empty" barriers: the first pass over the ring does not block
     uint32_t bph = 0;          // empty_b: k-th reload waits for the k-th release by the consumers
     int prev_key = -1;
-    for (int ch = lo; ch < hi; ch++) {
-      const int pair = ch / Tp;
-      int lc = ch - pair * Tp;
+    for (int u = lo; u < hi;) {
+      // decode the stage: pair, K tile, slow outer index, fastest outer index
+      const int pair = u / Tp;
+      int lu = u - pair * Tp;
       const int nt = pair / m_tiles, mt = pair - nt * m_tiles;
-      const int qc = lc % g.QC;
-      lc /= g.QC;
-      const int sl = lc % g.S, pt = lc / g.S;
+      const int iq0 = lu % Iq;
+      lu /= Iq;
+      const int sl = lu % g.S, pt = lu / g.S;
+      const int qc = iq0 / OC;
+      // stages of this chunk that belong to this CTA: up to the end of the chunk, of the iq run, of the CTA's range
+      const int n_here = min(min(OC - (iq0 - qc * OC), Iq - iq0), hi - u);
       const int key = pt * n_tiles + nt;
       if (key != prev_key) {
         if (prev_key >= 0) { // wait until all consumer warps have released the previous A_p tile
@@ -519,9 +507,8 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
         }
       }
       const int m0 = 8 * plan_m8_start(mt, pv.In8, m_tiles);
-      const int nvalid = min(OC, Iq - qc * OC);
-      for (int o = 0; o < nvalid; o++) {
-        const int iq = qc * OC + o;
+      for (int o = 0; o < n_here; o++) {
+        const int iq = iq0 + o;
         mbar_wait(&empty_x[xs], xph);
         mbar_expect_tx(&full_x[xs], Cfg::X_STAGE_BYTES);
         tma_load_4d(Xs + xs * (M_TILE * KT), &maps.X, &full_x[xs], pt * KT, lbase + iq * g.outer_lmul[0], m0,
@@ -531,6 +518,7 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
           xph ^= 1;
         }
       }
+      u += n_here;
     }
     return;
   }
@@ -568,13 +556,15 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
       }
   };
 
-  for (int ch = lo; ch < hi; ch++) {
-    const int pair = ch / Tp;
-    int lc = ch - pair * Tp;
+  for (int u = lo; u < hi;) {
+    const int pair = u / Tp;
+    int lu = u - pair * Tp;
     const int nt = pair / m_tiles, mt = pair - nt * m_tiles;
-    const int qc = lc % g.QC;
-    lc /= g.QC;
-    const int sl = lc % g.S, pt = lc / g.S;
+    const int iq0 = lu % Iq;
+    lu /= Iq;
+    const int sl = lu % g.S, pt = lu / g.S;
+    const int qc = iq0 / OC, o0 = iq0 - qc * OC;
+    const int n_here = min(min(OC - o0, Iq - iq0), hi - u); // same split of the range into chunk pieces as the producer
     // number of valid m8 row groups / n8 column groups of this pair (CTA-uniform)
     const int nm = plan_wm(mt, pv.In8, m_tiles);
     const int nn = plan_nn(nt, pv.NO, n_tiles);
@@ -620,10 +610,9 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
 
     mbar_wait(&full_w[wsi], wph);
     const double *Wc = Ws + wsi * (N_TILE * OC) + warp * 8 * OC;
-    const int nvalid = min(OC, Iq - qc * OC);
     const int kvalid = min(KT, g.Ip - pt * KT);
     const int ngroups = (kvalid + 7) >> 3;
-    for (int o = 0; o < nvalid; o++) {
+    for (int o = o0; o < o0 + n_here; o++) {
       double wv[WN];
 #pragma unroll
       for (int j = 0; j < WN; j++)
@@ -645,6 +634,7 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
       wsi = 0;
       wph ^= 1;
     }
+    u += n_here;
   }
   flush();
 }

@@ -14,7 +14,7 @@ int main() {
       for (int WM : {4, 5, 6, 7})
         for (int C : {1, 7, 52, 220, 256, 257, 2100, 2691})
           for (int shape_id = 0; shape_id < 7; shape_id++) {
-            // (Ip, Iq, S): single chunk, ragged K tail, ragged outer tail (41 = 5 * 8 + 1), config 2/3/4-like, 5 modes
+            // (Ip, Iq, S): single stage, ragged K tail, ragged outer run (41 = 5 * 8 + 1), config 2/3/4-like, 5 modes
             static const int shapes[7][3] = {{1, 1, 1},    {7, 9, 1},    {301, 41, 1}, {200, 200, 1},
                                              {299, 301, 1}, {80, 80, 80}, {20, 5, 12}};
             PlanShape sh{In, WM, shapes[shape_id][0], shapes[shape_id][1], shapes[shape_id][2]};
@@ -109,7 +109,7 @@ int main() {
                 if (k1 > Tp)
                   k1 = Tp;
                 wcta += pc.prefix(k1) - pc.prefix(k0);
-                const long long one = pc.prefix(1); // a full chunk in a full K tile (or the only kind there is)
+                const long long one = pc.prefix(1); // one stage in a full K tile (or the only kind there is)
                 if (one > wchunk_max)
                   wchunk_max = one;
                 // prefix is consistent with a chunk-by-chunk walk
