@@ -29,109 +29,143 @@ struct SchedParams {
 };
 constexpr int ITER_LOG_CAP = 65536;
 
-// Thread 0 does the queue bookkeeping (the live list is short, <= buffer_cols entries, and this runs once per CALS
-// iteration); then one thread per mode rebuilds that mode's MTTKRP plan if the column count changed.
-__device__ void sched_serial(const SchedParams &p);
-
-__global__ void sched_kernel(const SchedParams p) {
-  __shared__ int replan;
-  if (threadIdx.x == 0) {
-    const int C_before = p.st->C;
-    sched_serial(p);
-    replan = (p.st->C != C_before && p.st->C > 0) ? 1 : 0;
-  }
-  __syncthreads();
-  if (replan && (int)threadIdx.x < p.plans.n_modes)
-    mttkrp_make_plan(p.plans.plan[threadIdx.x], p.plans.shape[threadIdx.x], p.st->C, p.plans.G);
-}
-
-__device__ void sched_serial(const SchedParams &p) {
+// One warp.  Lane 0 does the eviction / compaction bookkeeping (the live list is short and this part only runs when a
+// model was flagged); admission -- up to hundreds of models and thousands of columns in the first iteration of a run --
+// is done by the whole warp: 32 queued models at a time, a warp scan of their ranks decides how many still fit, every
+// lane fills the gather list of its own model.  Then one thread per mode rebuilds that mode's MTTKRP plan if the column
+// count changed.
+__global__ void __launch_bounds__(32) sched_kernel(const SchedParams p) {
   SchedState *st = p.st;
-  if (st->done) {
-    st->changed = 0;
-    return;
-  }
-  const int B = st->buffer_cols;
-  bool changed = false;
+  const int lane = threadIdx.x;
+  __shared__ int sh_col, sh_nlive, sh_changed, sh_done, sh_C_before;
 
-  // always_evict_first: evict the leftmost live model, whatever its state (reference src/cals.cpp:348-354)
-  if ((st->flags & 2u) && st->global_iter > 0 && st->n_live > 0) {
-    p.models[p.live[0]].state = MODEL_EVICT;
-    st->n_evict = 1;
-  }
-
-  int n_live = st->n_live, col = 0, kept = 0;
-  if (st->n_evict > 0) {
-    for (int j = 0; j < B; j++)
-      p.evict_dst[j] = -1;
-    for (int li = 0; li < n_live; li++) {
-      const int m = p.live[li];
-      ModelDesc &md = p.models[m];
-      if (md.state == MODEL_EVICT) {
-        for (int j = 0; j < md.rank; j++)
-          p.evict_dst[md.col + j] = md.home_col + j;
-        md.state = MODEL_DONE;
-      } else {
-        for (int j = 0; j < md.rank; j++)
-          p.gather_src[col + j] = md.col + j;
-        md.col = col;
-        col += md.rank;
-        p.live_tmp[kept++] = m;
+  if (lane == 0) {
+    sh_done = st->done;
+    sh_C_before = st->C;
+    if (st->done) {
+      st->changed = 0;
+    } else {
+      const int B = st->buffer_cols;
+      bool changed = false;
+      // always_evict_first: evict the leftmost live model, whatever its state (reference src/cals.cpp:348-354)
+      if ((st->flags & 2u) && st->global_iter > 0 && st->n_live > 0) {
+        p.models[p.live[0]].state = MODEL_EVICT;
+        st->n_evict = 1;
       }
+      int n_live = st->n_live, col = 0, kept = 0;
+      if (st->n_evict > 0) {
+        for (int j = 0; j < B; j++)
+          p.evict_dst[j] = -1;
+        for (int li = 0; li < n_live; li++) {
+          const int m = p.live[li];
+          ModelDesc &md = p.models[m];
+          if (md.state == MODEL_EVICT) {
+            for (int j = 0; j < md.rank; j++)
+              p.evict_dst[md.col + j] = md.home_col + j;
+            md.state = MODEL_DONE;
+          } else {
+            for (int j = 0; j < md.rank; j++)
+              p.gather_src[col + j] = md.col + j;
+            md.col = col;
+            col += md.rank;
+            p.live_tmp[kept++] = m;
+          }
+        }
+        for (int li = 0; li < kept; li++)
+          p.live[li] = p.live_tmp[li];
+        n_live = kept;
+        changed = true;
+        st->n_evict = 0;
+      } else {
+        col = st->C;
+      }
+      sh_col = col;
+      sh_nlive = n_live;
+      sh_changed = changed ? 1 : 0;
     }
-    for (int li = 0; li < kept; li++)
-      p.live[li] = p.live_tmp[li];
-    n_live = kept;
-    changed = true;
-    st->n_evict = 0;
-  } else {
-    col = st->C;
   }
+  __syncwarp();
+  if (sh_done)
+    return;
 
-  // admission
-  bool admitted = false;
-  while (st->next < st->n_models) {
-    ModelDesc &md = p.models[st->next];
-    if (col + md.rank > B)
-      break;
-    if (!changed && !admitted) {
-      // first structural change of this iteration without evictions: identity map for the resident columns
-      for (int j = 0; j < B; j++)
-        p.evict_dst[j] = -1;
-      for (int j = 0; j < col; j++)
-        p.gather_src[j] = j;
+  // ---- admission: FIFO, stop at the first model that does not fit (reference src/cals.cpp:182-192; first-fit equals
+  // append because the buffer is compact, src/multi_ktensor.cpp:14-39) ----
+  {
+    const int B = st->buffer_cols, n_models = st->n_models;
+    int next = st->next, col = sh_col, n_live = sh_nlive;
+    bool changed = sh_changed != 0, admitted_any = false;
+    unsigned long long comp = 0;
+    const int next0 = next;
+    for (bool more = true; more && next < n_models;) {
+      const int m = next + lane;
+      const int rank = m < n_models ? p.models[m].rank : 0x3fffffff; // beyond the queue: never fits
+      int incl = rank > B ? B + 1 : rank;                             // clamp: sums stay far from overflow
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+          incl = min(incl + v, B + 1);
+      }
+      const bool fits = col + incl <= B; // monotone in the lane index
+      const unsigned mask = __ballot_sync(0xffffffffu, fits);
+      const int n_fit = __popc(mask);
+      if (n_fit > 0 && !changed && !admitted_any) {
+        // first structural change of this iteration without evictions: identity map for the resident columns
+        for (int j = lane; j < B; j += 32)
+          p.evict_dst[j] = -1;
+        for (int j = lane; j < col; j += 32)
+          p.gather_src[j] = j;
+      }
+      if (fits) {
+        ModelDesc &md = p.models[m];
+        const int my_col = col + incl - rank;
+        for (int j = 0; j < rank; j++)
+          p.gather_src[my_col + j] = -1 - (md.home_col + j);
+        md.col = my_col;
+        md.state = MODEL_LIVE;
+        md.iters = 1; // reference src/multi_ktensor.cpp:96
+        p.live[n_live + lane] = m;
+      }
+      if (n_fit > 0) {
+        admitted_any = true;
+        const int total = __shfl_sync(0xffffffffu, incl, n_fit - 1);
+        comp += (unsigned long long)total;
+        col += total;
+        n_live += n_fit;
+        next += n_fit;
+      }
+      more = (n_fit == 32);
     }
-    admitted = true;
-    for (int j = 0; j < md.rank; j++)
-      p.gather_src[col + j] = -1 - (md.home_col + j);
-    md.col = col;
-    md.state = MODEL_LIVE;
-    md.iters = 1; // reference src/multi_ktensor.cpp:96
-    col += md.rank;
-    p.live[n_live++] = st->next;
-    st->n_admitted += 1;
-    st->comp_sum += md.rank;
-    st->next += 1;
+    __syncwarp();
+    if (lane == 0) {
+      changed = changed || admitted_any;
+      st->next = next;
+      st->n_admitted += (unsigned long long)(next - next0);
+      st->comp_sum += comp;
+      st->n_live = n_live;
+      st->C = col;
+      st->changed = changed ? 1 : 0;
+      if (changed)
+        st->cur ^= 1;
+      if (n_live == 0 && next >= n_models) {
+        st->done = 1;
+      } else {
+        if (st->global_iter < (unsigned long long)ITER_LOG_CAP)
+          p.iter_cols[st->global_iter] = (unsigned)col;
+        st->global_iter += 1; // reference: rep.iter counts executed loop bodies (src/cals.cpp:175-176)
+        st->col_iter_sum += (unsigned long long)col;
+      }
+      p.host_flags[1] = (int)(st->global_iter & 0x7fffffff);
+      p.host_flags[2] = n_live;
+      __threadfence_system();
+      p.host_flags[0] = st->done;
+      sh_col = col;
+    }
   }
-  changed = changed || admitted;
-
-  st->n_live = n_live;
-  st->C = col;
-  st->changed = changed ? 1 : 0;
-  if (changed)
-    st->cur ^= 1;
-  if (n_live == 0 && st->next >= st->n_models) {
-    st->done = 1;
-  } else {
-    if (st->global_iter < (unsigned long long)ITER_LOG_CAP)
-      p.iter_cols[st->global_iter] = (unsigned)col;
-    st->global_iter += 1; // reference: rep.iter counts executed loop bodies (src/cals.cpp:175-176)
-    st->col_iter_sum += (unsigned long long)col;
-  }
-  p.host_flags[1] = (int)(st->global_iter & 0x7fffffff);
-  p.host_flags[2] = n_live;
-  __threadfence_system();
-  p.host_flags[0] = st->done;
+  __syncwarp();
+  const int C_now = sh_col;
+  if (C_now != sh_C_before && C_now > 0 && lane < p.plans.n_modes)
+    mttkrp_make_plan(p.plans.plan[lane], p.plans.shape[lane], C_now, p.plans.G);
 }
 
 // Column mover.  grid = (ceil(buffer_cols / COLS_PER_CTA), n_modes, 2): z == 0 copies evicted columns old buffer ->
