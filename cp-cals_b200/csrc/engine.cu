@@ -141,6 +141,12 @@ struct cals_b200_ctx {
   int cuts[CALS_MAX_PEERS + 1] = {};
   unsigned long long seq_base = 0;
 
+  // one CALS iteration captured as a CUDA graph (the launch parameters do not change between iterations, nor between
+  // runs that reuse the same allocations and options)
+  cudaGraphExec_t iter_graph = nullptr;
+  std::vector<long long> iter_graph_key;
+  long long alloc_generation = 0; // bumped whenever prepare_run (re)allocates
+
   std::vector<cudaEvent_t> ev_pool;
   bool dmma_attr_done[16] = {};
   size_t update_attr_smem = 0;
@@ -384,13 +390,35 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
 
 double *exchange_data(cals_b200_ctx *c) { return (double *)((char *)c->xblock + COMM_FLAG_BYTES); }
 
+template <int WM> int set_dmma_attr(cals_b200_ctx *c) {
+  if (!c->dmma_attr_done[WM]) {
+    CU_TRY(c, cudaFuncSetAttribute(mttkrp_dmma_kernel<WM, WN_FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   smem_bytes<WM>()));
+    c->dmma_attr_done[WM] = true;
+  }
+  return 0;
+}
+
+int ensure_dmma_attr(cals_b200_ctx *c, int wm) {
+  switch (wm) {
+  case 4:
+    return set_dmma_attr<4>(c);
+  case 5:
+    return set_dmma_attr<5>(c);
+  case 6:
+    return set_dmma_attr<6>(c);
+  case 7:
+    return set_dmma_attr<7>(c);
+  default:
+    return set_dmma_attr<8>(c);
+  }
+}
+
 template <int WM>
 int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchange) {
   auto kern = mttkrp_dmma_kernel<WM, WN_FIXED>;
-  if (!c->dmma_attr_done[WM]) {
-    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<WM>()));
-    c->dmma_attr_done[WM] = true;
-  }
+  if (set_dmma_attr<WM>(c))
+    return 1;
   const int G = c->sm_count;
   kern<<<G, MTTKRP_THREADS, smem_bytes<WM>(), c->stream>>>(b.maps[n], b.mg[n], c->d_st, b.fac, b.plans.plan[n], b.ws,
                                                             C_override);
@@ -448,7 +476,15 @@ int ensure_dummy_state(cals_b200_ctx *c) {
   return 0;
 }
 
+void drop_iteration_graph(cals_b200_ctx *c) {
+  if (c->iter_graph)
+    cudaGraphExecDestroy(c->iter_graph);
+  c->iter_graph = nullptr;
+  c->iter_graph_key.clear();
+}
+
 void release_run(cals_b200_ctx *c) {
+  drop_iteration_graph(c);
   free_all(c->bufs.allocs);
   free_all(c->run_allocs);
   c->bufs = Buffers();
@@ -630,8 +666,10 @@ int prepare_run(cals_b200_ctx *c) {
   for (int m = 0; m < M; m++)
     sig.push_back(c->hmodels[m].rank);
   const bool reuse = !c->run_sig.empty() && sig == c->run_sig && c->d_models && c->bufs.cols == c->buffer_cols;
-  if (!reuse)
+  if (!reuse) {
     release_run(c);
+    c->alloc_generation++;
+  }
 
   c->hdesc.assign(M, ModelDesc{});
   int col = 0, max_rank = 0;
@@ -889,13 +927,16 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   auto t0 = std::chrono::steady_clock::now();
   CU_TRY(c, cudaEventRecord(ev_begin, s));
   long long it = 0;
-  for (;; it++) {
+  // everything one CALS iteration launches, in stream order
+  int launches_per_iteration = 0;
+  auto enqueue_iteration = [&](bool count) -> int {
+    int n_launch = 0;
     sched_kernel<<<1, 32, 0, s>>>(sp);
     move_kernel<<<move_grid, 256, 0, s>>>(geo, b.fac, c->d_st, c->d_gather, c->d_evict);
-    launches += 2;
+    n_launch += 2;
     if (c->ls_enabled) {
       ls_snapshot_kernel<<<max_live, 256, 0, s>>>(lp);
-      launches++;
+      n_launch++;
     }
     for (int n = 0; n < N; n++) {
       if (c->timing) {
@@ -903,13 +944,12 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
         cudaEventRecord(get_event(c, ev_next), s);
       }
       if (launch_mttkrp(c, b, n, 0, c->variant, exchange))
-        return 1;
+        return -1;
       if (exchange) {
         exchange_sum_kernel<<<c->sm_count * 2, 256, 0, s>>>(cp, c->d_st, b.G, n, N, geo.dims[n], geo.ldF[n]);
-        launches++;
+        n_launch++;
       }
-      mttkrp_launches++;
-      launches += (c->variant == CALS_B200_MTTKRP_NAIVE) ? 1 : 2;
+      n_launch += (c->variant == CALS_B200_MTTKRP_NAIVE) ? 1 : 2;
       if (c->timing) {
         cudaEventRecord(get_event(c, ev_next + 1), s);
         timed.push_back({ev_next + 1, 1});
@@ -919,7 +959,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
         model_update_kernel<true><<<max_live, UPDATE_THREADS, up_smem[n], s>>>(up[n]);
       else
         model_update_kernel<false><<<max_live, UPDATE_THREADS, up_smem[n], s>>>(up[n]);
-      launches++;
+      n_launch++;
       if (c->timing) {
         cudaEventRecord(get_event(c, ev_next), s);
         ev_next += 1;
@@ -927,13 +967,64 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     }
     if (c->ls_enabled) {
       ls_main_kernel<<<max_live, 256, 0, s>>>(lp);
-      launches++;
+      n_launch++;
       if (c->ls_method != 0) {
         ls_explicit_error_kernel<<<dim3(max_live, LS_CHUNKS), 256, (size_t)(c->max_rank + 32) * 8, s>>>(lp);
         ls_decide_kernel<<<max_live, 256, 0, s>>>(lp);
-        launches += 2;
+        n_launch += 2;
       }
     }
+    if (count)
+      launches_per_iteration = n_launch;
+    return n_launch;
+  };
+
+  // Graph mode (default): capture the iteration once, replay it.  Off with per-kernel timing (events sit between the
+  // kernels), with the sliced-tensor exchange (its sequence base changes from run to run) and with CALS_B200_NO_GRAPH=1.
+  static const bool graphs_off = getenv("CALS_B200_NO_GRAPH") != nullptr;
+  const bool use_graph = !c->timing && !exchange && !graphs_off;
+  if (use_graph) {
+    std::vector<long long> key = {c->alloc_generation, (long long)c->flags, c->ls_enabled, c->ls_method, c->variant,
+                                  (long long)max_live};
+    const bool same_graph = c->iter_graph && c->iter_graph_key.size() == key.size() + 1 &&
+                            std::equal(key.begin(), key.end(), c->iter_graph_key.begin());
+    if (!same_graph) {
+      drop_iteration_graph(c);
+      // function attributes must be set outside of a capture: launch_dmma does it lazily, so trigger it here
+      for (int n = 0; n < N; n++)
+        if (c->variant == CALS_B200_MTTKRP_DMMA && ensure_dmma_attr(c, b.wm[n]))
+          return 1;
+      cudaGraph_t graph = nullptr;
+      CU_TRY(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const int rc = enqueue_iteration(true);
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc < 0 || ce != cudaSuccess) {
+        if (graph)
+          cudaGraphDestroy(graph);
+        return rc < 0 ? 1 : fail(c, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+      }
+      ce = cudaGraphInstantiate(&c->iter_graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess)
+        return fail(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+      c->iter_graph_key = key;
+      c->iter_graph_key.push_back(launches_per_iteration);
+    } else {
+      launches_per_iteration = (int)c->iter_graph_key.back();
+    }
+  }
+
+  for (;; it++) {
+    if (use_graph) {
+      CU_TRY(c, cudaGraphLaunch(c->iter_graph, s));
+      launches += launches_per_iteration;
+    } else {
+      const int rc = enqueue_iteration(false);
+      if (rc < 0)
+        return 1;
+      launches += rc;
+    }
+    mttkrp_launches += N;
     CU_TRY(c, cudaEventRecord(ring[it % RA], s));
     if (it >= RA - 1)
       CU_TRY(c, cudaEventSynchronize(ring[(it + 1) % RA]));
@@ -1098,6 +1189,7 @@ int cals_b200_destroy(cals_b200_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   release_tensor(c);
+  drop_iteration_graph(c);
   if (c->d_st)
     cudaFree(c->d_st);
   if (c->d_iter_cols)
