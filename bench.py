@@ -6,7 +6,8 @@
 Metric (BASELINE.json): concurrent-ALS iterations per second summed over all models ("model-iterations/s").  The
 default workload is BASELINE config 2 (the largest configuration the metric is quoted on that fits one GPU): synthetic
 200x200x200 FP64 tensor, 200 concurrent models (ranks 1..20 x 10), buffer = sum of ranks, forced iteration count.
-One "step" = one complete cals::cp_cals pass: all models x ALS_ITERS ALS iterations.
+One "step" = one complete cals::cp_cals pass: all 200 models x 50 forced ALS iterations (the iteration count of the
+reference's own experiments, src/experiments/experiments.cpp:62-63).
 
   value    : whole-job throughput with the tensor and the initial models already resident in HBM (cals_b200_rerun),
              timed with CUDA events on the engine's stream, max over ranks
@@ -37,12 +38,13 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "concurrent-ALS iters/sec (all models)"
 UNIT = "model-iterations/s"
 
-# BASELINE.json configs.  als_iters: forced ALS iterations per model per step; ref_iters: per reference-arm step.
+# BASELINE.json configs.  als_iters: forced ALS iterations per model per step (config 2: 50, the protocol of the
+# reference's own experiments, src/experiments/experiments.cpp:62-63); ref_iters: per reference-arm step (bounded sample).
 CONFIGS = {
     1: dict(name="config 1: 100x100x100 tensor, 40 models (ranks 1..10 x4), buffer 220", modes=(100, 100, 100),
             ranks=[r for r in range(1, 11) for _ in range(4)], als_iters=50, ref_iters=20, jk=False),
     2: dict(name="config 2: 200x200x200 tensor, 200 models (ranks 1..20 x10), buffer 2100", modes=(200, 200, 200),
-            ranks=[r for r in range(1, 21) for _ in range(10)], als_iters=10, ref_iters=2, jk=False),
+            ranks=[r for r in range(1, 21) for _ in range(10)], als_iters=50, ref_iters=2, jk=False),
     3: dict(name="config 3: jackknife on a 299x301x41 tensor (fluorescence_cancer_UD shape, synthetic), all 299 "
                  "leave-one-out sub-models of base models of ranks 3,5,7,9", modes=(299, 301, 41),
             ranks=[r for r in (3, 5, 7, 9) for _ in range(299)], als_iters=10, ref_iters=1, jk=True),

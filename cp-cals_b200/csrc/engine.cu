@@ -415,13 +415,15 @@ int ensure_dmma_attr(cals_b200_ctx *c, int wm) {
 }
 
 template <int WM>
-int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchange) {
+int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchange, bool skip_reduce) {
   auto kern = mttkrp_dmma_kernel<WM, WN_FIXED>;
   if (set_dmma_attr<WM>(c))
     return 1;
   const int G = c->sm_count;
   kern<<<G, MTTKRP_THREADS, smem_bytes<WM>(), c->stream>>>(b.maps[n], b.mg[n], c->d_st, b.fac, b.plans.plan[n], b.ws,
                                                             C_override);
+  if (skip_reduce) // the update kernel sums the partial tiles itself
+    return 0;
   const int cols = C_override > 0 ? C_override : b.cols;
   dim3 rg((cols + 31) / 32, (b.mg[n].In + 31) / 32);
   mttkrp_reduce_kernel<8 * WM, TILE_N><<<rg, 256, 0, c->stream>>>(
@@ -430,7 +432,8 @@ int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchan
   return 0;
 }
 
-int launch_mttkrp(cals_b200_ctx *c, Buffers &b, int n, int C_override, int variant, bool exchange = false) {
+int launch_mttkrp(cals_b200_ctx *c, Buffers &b, int n, int C_override, int variant, bool exchange = false,
+                  bool skip_reduce = false) {
   if (variant == CALS_B200_MTTKRP_NAIVE) {
     if (exchange)
       return fail(c, "the naive MTTKRP variant does not support a sliced tensor over several GPUs");
@@ -454,15 +457,15 @@ int launch_mttkrp(cals_b200_ctx *c, Buffers &b, int n, int C_override, int varia
   }
   switch (b.wm[n]) {
   case 4:
-    return launch_dmma<4>(c, b, n, C_override, exchange);
+    return launch_dmma<4>(c, b, n, C_override, exchange, skip_reduce);
   case 5:
-    return launch_dmma<5>(c, b, n, C_override, exchange);
+    return launch_dmma<5>(c, b, n, C_override, exchange, skip_reduce);
   case 6:
-    return launch_dmma<6>(c, b, n, C_override, exchange);
+    return launch_dmma<6>(c, b, n, C_override, exchange, skip_reduce);
   case 7:
-    return launch_dmma<7>(c, b, n, C_override, exchange);
+    return launch_dmma<7>(c, b, n, C_override, exchange, skip_reduce);
   default:
-    return launch_dmma<8>(c, b, n, C_override, exchange);
+    return launch_dmma<8>(c, b, n, C_override, exchange, skip_reduce);
   }
 }
 
@@ -806,6 +809,17 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   const int max_live = std::min(M, c->buffer_cols);
   const dim3 move_grid((c->buffer_cols + MOVE_COLS - 1) / MOVE_COLS, N, 2);
 
+  // The update kernel sums the stream-K partial tiles itself unless the partial result has to leave the device first
+  // (sliced tensor), there are no partial tiles (naive variant), or CALS_B200_NO_FUSED_REDUCE=1 asks for the two-kernel
+  // path (kept for A/B measurements).
+  static const bool fusion_off = getenv("CALS_B200_NO_FUSED_REDUCE") != nullptr;
+  // Only worth it when the MTTKRP itself is short (measured: +11 % at 100^3 x 220 columns, -1 % at 200^3 x 2100, where
+  // the separate, much wider reduce kernel is cheaper than lengthening the largest model's update CTA).
+  static const bool fusion_forced = getenv("CALS_B200_FUSED_REDUCE") != nullptr;
+  const bool small_problem = (double)c->nX * (double)c->buffer_cols <= 2.0e9;
+  const bool fused_reduce = c->variant == CALS_B200_MTTKRP_DMMA && !(c->slice_mode >= 0 && c->comm_world > 1) &&
+                            !fusion_off && (small_problem || fusion_forced);
+
   // shared memory of the update kernel
   UpdateParams up[CALS_MAX_MODES];
   size_t up_smem[CALS_MAX_MODES];
@@ -846,6 +860,12 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     u.live = c->d_live;
     u.st = c->d_st;
     u.act_pool = c->d_active;
+    u.plan = fused_reduce ? b.plans.plan[n] : nullptr;
+    u.ws = b.ws;
+    u.plan_ctas = c->sm_count;
+    u.tile_elems = tile_m(b.wm[n]) * TILE_N;
+    u.n_tile = TILE_N;
+    u.G_out = b.G;
     u.rows_before = 0;
     for (int k = 0; k < n; k++)
       u.rows_before += geo.dims[k];
@@ -943,13 +963,13 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
         timed.push_back({ev_next, 0});
         cudaEventRecord(get_event(c, ev_next), s);
       }
-      if (launch_mttkrp(c, b, n, 0, c->variant, exchange))
+      if (launch_mttkrp(c, b, n, 0, c->variant, exchange, fused_reduce))
         return -1;
       if (exchange) {
         exchange_sum_kernel<<<c->sm_count * 2, 256, 0, s>>>(cp, c->d_st, b.G, n, N, geo.dims[n], geo.ldF[n]);
         n_launch++;
       }
-      n_launch += (c->variant == CALS_B200_MTTKRP_NAIVE) ? 1 : 2;
+      n_launch += (c->variant == CALS_B200_MTTKRP_NAIVE || fused_reduce) ? 1 : 2;
       if (c->timing) {
         cudaEventRecord(get_event(c, ev_next + 1), s);
         timed.push_back({ev_next + 1, 1});
@@ -985,7 +1005,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   const bool use_graph = !c->timing && !exchange && !graphs_off;
   if (use_graph) {
     std::vector<long long> key = {c->alloc_generation, (long long)c->flags, c->ls_enabled, c->ls_method, c->variant,
-                                  (long long)max_live};
+                                  (long long)max_live, fused_reduce ? 1 : 0};
     const bool same_graph = c->iter_graph && c->iter_graph_key.size() == key.size() + 1 &&
                             std::equal(key.begin(), key.end(), c->iter_graph_key.begin());
     if (!same_graph) {

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "common.cuh"
+#include "mttkrp.cuh"
 
 namespace calsb200 {
 
@@ -39,6 +40,16 @@ struct UpdateParams {
   ModelDesc *models;
   const int *live;
   SchedState *st;
+  // fused reduction of the stream-K partial tiles (replaces mttkrp_reduce_kernel on the iteration path): when
+  // plan != nullptr the MTTKRP result is not read from G but summed here, per (m,n) pair in segment order, from the
+  // partial-tile workspace the DMMA kernel has just written; for the last mode the sum is also written to G (the
+  // error term needs it after the solve).
+  const int *plan;
+  const double *ws;
+  int plan_ctas;  // gridDim.x of the DMMA kernel (layout of the plan tables)
+  int tile_elems; // M_TILE * N_TILE of this mode's DMMA kernel
+  int n_tile;     // N_TILE
+  double *G_out;  // == G (mutable alias)
   // non-negative update (update_method == NNLS)
   int nnls;                 // 0: Cholesky solve, 1: row-wise active-set NNLS
   int nnls_warps;           // warps of the CTA that work on rows (each owns a scratch block in shared memory)
@@ -307,7 +318,7 @@ __device__ int nnls_row(const double *H, int R, double tol, double *Srow, int pi
 }
 
 template <bool NNLS>
-__global__ void __launch_bounds__(UPDATE_THREADS)
+__global__ void __launch_bounds__(UPDATE_THREADS, 2)
 model_update_kernel(const UpdateParams p) {
   SchedState *st = p.st;
   if ((int)blockIdx.x >= st->n_live)
@@ -402,9 +413,37 @@ model_update_kernel(const UpdateParams p) {
   for (int r0 = 0; r0 < rows; r0 += CR) {
     const int nr = min(CR, rows - r0);
     __syncthreads();
-    for (int e = tid; e < nr * R; e += nthr) {
-      const int rr = e % nr, j = e / nr;
-      S[rr + j * pitch] = Gm[(size_t)j * ld + r0 + rr];
+    if (p.plan != nullptr) {
+      // columns fastest: a warp reads runs of R consecutive doubles of a row-major partial tile
+      const PlanView pv = plan_view(p.plan, p.plan_ctas);
+      for (int e = tid; e < nr * R; e += nthr) {
+        const int j = e % R, rr = e / R;
+        const int m = r0 + rr, cg = col + j;
+        const int mt = plan_tile_of(m >> 3, pv.In8, pv.m_tiles);
+        const int nt = plan_tile_of(cg >> 6, pv.NO, pv.n_tiles);
+        const int pair = nt * pv.m_tiles + mt;
+        const int s0 = pv.pair_seg0[pair], s1 = pv.pair_seg0[pair + 1];
+        const double *q = p.ws + (size_t)s0 * p.tile_elems +
+                          (size_t)(m - 8 * plan_m8_start(mt, pv.In8, pv.m_tiles)) * p.n_tile +
+                          (cg - 64 * plan_oct_start(nt, pv.NO, pv.n_tiles));
+        double sum = 0.0;
+        for (int k = s0; k < s1; k++, q += p.tile_elems)
+          sum += *q;
+        S[rr + j * pitch] = sum;
+      }
+      if (n == N - 1) { // keep G for the error term
+        __syncthreads();
+        double *Gw = p.G_out + (size_t)col * ld;
+        for (int e = tid; e < nr * R; e += nthr) {
+          const int rr = e % nr, j = e / nr;
+          Gw[(size_t)j * ld + r0 + rr] = S[rr + j * pitch];
+        }
+      }
+    } else {
+      for (int e = tid; e < nr * R; e += nthr) {
+        const int rr = e % nr, j = e / nr;
+        S[rr + j * pitch] = Gm[(size_t)j * ld + r0 + rr];
+      }
     }
     __syncthreads();
     if (NNLS) { // warp per row, active sets warm-started from the previous iteration
