@@ -281,7 +281,18 @@ def run_sliced(args, cfg, rank, world, local_rank):
     flops_per_launch = 2.0 * float(np.prod(shape)) * C
     peak, peak_src = fp64_peak()
     ach = flops_per_launch / (mt_ms * 1e-3) / 1e12
+    # NVLink volume of the exchange: every GPU pulls the partials of the other W-1 GPUs (full-size for the modes that
+    # are not sliced, the foreign row blocks for the sliced one)
+    ld = [(m + 1) // 2 * 2 for m in modes]
+    pulled = [8.0 * C * ((modes[n] - (hi - lo)) if n == s_mode else (world - 1) * ld[n]) for n in range(len(modes))]
+    xch_ms = max_over_ranks(rep.exchange_ms) / rep.mttkrp_launches
+    exchange = {"kernel": "exchange_sum_kernel (barrier wait + peer-memory pulls + rank-ordered sum)",
+                "ms_per_launch": xch_ms, "nvlink_bytes_pulled_per_gpu_per_launch": float(np.mean(pulled)),
+                "achieved_gbs_incl_barrier_wait": float(np.mean(pulled)) / (xch_ms * 1e-3) / 1e9 if xch_ms > 0 else None,
+                "peer_copy_peak_gbs": 770.0, "share_of_mttkrp_window": rep.exchange_ms / rep.mttkrp_ms
+                if rep.mttkrp_ms > 0 else None} if world > 1 else None
     roofline = {"bound": "tensor", "kernel": "mttkrp_dmma_kernel (+ reduce + NVLink exchange_sum_kernel)",
+                "exchange": exchange,
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s per GPU", "frac": ach / peak, "traffic": None,
                 "peak_source": peak_src, "mttkrp_ms_per_launch": mt_ms, "flops_per_launch_per_gpu": flops_per_launch,
                 "mttkrp_share_of_step": rep.mttkrp_ms / (rep.mttkrp_ms + rep.update_ms)}

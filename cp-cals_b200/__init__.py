@@ -51,7 +51,7 @@ class Report(C.Structure):
     _fields_ = [("iter", C.c_uint64), ("n_ktensors", C.c_uint64), ("ktensor_comp_sum", C.c_uint64),
                 ("x_norm", C.c_double), ("total_time", C.c_double), ("device_ms", C.c_double),
                 ("mttkrp_ms", C.c_double), ("update_ms", C.c_double), ("mttkrp_launches", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("mttkrp_flops", C.c_double)]
+                ("kernel_launches", C.c_uint64), ("mttkrp_flops", C.c_double), ("exchange_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -966,7 +966,13 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
       if (launch_mttkrp(c, b, n, 0, c->variant, exchange, fused_reduce))
         return -1;
       if (exchange) {
+        if (c->timing) {
+          timed.push_back({ev_next + 3, 2}); // kind 2: exchange window = [ev_next+3, ev_next+4]
+          cudaEventRecord(get_event(c, ev_next + 3), s);
+        }
         exchange_sum_kernel<<<c->sm_count * 2, 256, 0, s>>>(cp, c->d_st, b.G, n, N, geo.dims[n], geo.ldF[n]);
+        if (c->timing)
+          cudaEventRecord(get_event(c, ev_next + 4), s);
         n_launch++;
       }
       n_launch += (c->variant == CALS_B200_MTTKRP_NAIVE || fused_reduce) ? 1 : 2;
@@ -982,7 +988,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
       n_launch++;
       if (c->timing) {
         cudaEventRecord(get_event(c, ev_next), s);
-        ev_next += 1;
+        ev_next += exchange ? 3 : 1; // skip the two events of the exchange window
       }
     }
     if (c->ls_enabled) {
@@ -1089,19 +1095,23 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     rep->kernel_launches = launches;
     rep->mttkrp_flops = 2.0 * (double)c->nX * (double)N * (double)st.col_iter_sum;
     if (c->timing) {
-      double mt = 0, ut = 0;
-      uint64_t seen_m = 0, seen_u = 0;
+      double mt = 0, ut = 0, xt = 0;
+      uint64_t seen_m = 0, seen_u = 0, seen_x = 0;
       for (auto &t : timed) {
         float e = 0;
         cudaEventElapsedTime(&e, get_event(c, t.first), get_event(c, t.first + 1));
         if (t.second == 0) {
           if (seen_m++ < real_mttkrp)
             mt += e;
-        } else if (seen_u++ < real_mttkrp)
-          ut += e;
+        } else if (t.second == 1) {
+          if (seen_u++ < real_mttkrp)
+            ut += e;
+        } else if (seen_x++ < real_mttkrp)
+          xt += e;
       }
       rep->mttkrp_ms = mt;
       rep->update_ms = ut;
+      rep->exchange_ms = xt;
     }
   }
   c->results_fresh = false;

@@ -49,6 +49,8 @@ typedef struct cals_b200_report {
   uint64_t mttkrp_launches;  /* number of MTTKRP kernel launches */
   uint64_t kernel_launches;  /* all kernels launched by this run */
   double mttkrp_flops;       /* algorithmic flop executed by the MTTKRPs: sum over launches of 2*nX*C */
+  double exchange_ms;        /* sliced tensor + timing: CUDA-event time summed over the peer-memory exchange kernels
+                                (barrier wait + NVLink pulls); it is part of mttkrp_ms as well */
 } cals_b200_report;
 
 typedef struct cals_b200_model_stats {
