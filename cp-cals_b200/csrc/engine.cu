@@ -1438,6 +1438,25 @@ int cals_b200_set_mttkrp_variant(cals_b200_ctx *c, int variant) {
   return 0;
 }
 
+// Pinned input staging of mode n for at least `cols` queued columns; what is already queued is kept.
+static int reserve_input_staging(cals_b200_ctx *c, int n, size_t cols, bool geometric) {
+  const size_t ld = (size_t)c->geo.ldF[n];
+  const size_t need = ld * cols;
+  if (need <= c->h_in_cap[n])
+    return 0;
+  const size_t cap = geometric ? std::max(need, std::max<size_t>(2 * c->h_in_cap[n], ld * 256)) : need;
+  double *fresh = nullptr;
+  CU_TRY(c, cudaHostAlloc((void **)&fresh, cap * 8, cudaHostAllocDefault));
+  if (c->h_in[n]) {
+    CU_TRY(c, cudaStreamSynchronize(c->stream)); // an upload from the old block may still be in flight
+    memcpy(fresh, c->h_in[n], ld * c->queued_cols * 8);
+    cudaFreeHost(c->h_in[n]);
+  }
+  c->h_in[n] = fresh;
+  c->h_in_cap[n] = cap;
+  return 0;
+}
+
 int cals_b200_clear_models(cals_b200_ctx *c) {
   if (!c)
     return 1;
@@ -1475,19 +1494,8 @@ int cals_b200_enqueue_model(cals_b200_ctx *c, uint64_t rank, const double *const
       return fail(c, "factor %d is null", n);
   for (int n = 0; n < geo.n_modes; n++) {
     const int rows = geo.dims[n], ld = geo.ldF[n];
-    const size_t need = (size_t)ld * (c->queued_cols + rank);
-    if (need > c->h_in_cap[n]) { // grow geometrically, keeping what is already queued
-      const size_t cap = std::max(need, std::max<size_t>(2 * c->h_in_cap[n], (size_t)ld * 256));
-      double *fresh = nullptr;
-      CU_TRY(c, cudaHostAlloc((void **)&fresh, cap * 8, cudaHostAllocDefault));
-      if (c->h_in[n]) {
-        CU_TRY(c, cudaStreamSynchronize(c->stream)); // an upload from the old block may still be in flight
-        memcpy(fresh, c->h_in[n], (size_t)ld * c->queued_cols * 8);
-        cudaFreeHost(c->h_in[n]);
-      }
-      c->h_in[n] = fresh;
-      c->h_in_cap[n] = cap;
-    }
+    if (reserve_input_staging(c, n, (size_t)c->queued_cols + rank, true))
+      return 1;
     double *dst = c->h_in[n] + (size_t)ld * c->queued_cols;
     if (ld == rows)
       memcpy(dst, host_factors[n], (size_t)rows * rank * 8);
@@ -1509,7 +1517,15 @@ int cals_b200_enqueue_models(cals_b200_ctx *c, uint64_t n_models, const uint64_t
                              const double *const *host_factors, const int *jk_modes, const int64_t *jk_fibers) {
   if (!c || !ranks || !host_factors)
     return fail(c, "null argument");
+  if (!c->have_tensor)
+    return fail(c, "set the tensor before enqueueing models");
   const int N = c->geo.n_modes;
+  size_t cols = (size_t)c->queued_cols;
+  for (uint64_t m = 0; m < n_models; m++)
+    cols += ranks[m];
+  for (int n = 0; n < N; n++) // one pinned allocation per mode for the whole queue
+    if (reserve_input_staging(c, n, cols, false))
+      return 1;
   for (uint64_t m = 0; m < n_models; m++)
     if (cals_b200_enqueue_model(c, ranks[m], host_factors + m * N, jk_modes ? jk_modes[m] : -1,
                                 jk_fibers ? jk_fibers[m] : 0, nullptr))
@@ -1521,11 +1537,21 @@ int cals_b200_run(cals_b200_ctx *c, cals_b200_report *rep) {
   if (!c)
     return 1;
   cudaSetDevice(c->device);
+  static const bool trace = getenv("CALS_B200_TRACE") != nullptr; // host-side phase times on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   if (prepare_run(c))
     return 1;
+  const auto t1 = now();
   if (run_loop(c, rep, false))
     return 1;
-  return download_results(c);
+  const auto t2 = now();
+  const int rc = download_results(c);
+  if (trace)
+    fprintf(stderr, "[cals_b200] run: prepare %.3f ms, loop %.3f ms (device %.3f ms), download %.3f ms\n", ms(t0, t1),
+            ms(t1, t2), rep ? rep->device_ms : 0.0, ms(t2, now()));
+  return rc;
 }
 
 int cals_b200_rerun(cals_b200_ctx *c, cals_b200_report *rep) {

@@ -6,7 +6,10 @@
 // fill the report.  With CalsParams::devices = {d0, d1, ..} the model set is sharded over several GPUs of the box (X
 // replicated, one host thread per device, no data-path collective).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <map>
@@ -65,12 +68,18 @@ void upload_tensor(EngineHandle &e, const Tensor &X, bool may_skip) {
 }
 
 RunResult run_on_device(int device, const Tensor &X, const std::vector<Ktensor *> &models, const RunOptions &opt) {
+  static const bool trace = getenv("CALS_B200_TRACE") != nullptr; // host-side phase times on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t_begin = now();
   EngineHandle &e = engine_for_device(device);
   std::lock_guard<std::mutex> lk(e.mu);
   RunResult out;
   if (models.empty())
     return out;
+  const auto t_engine = now();
   upload_tensor(e, X, opt.skip_upload_if_resident);
+  const auto t_upload = now();
   const unsigned flags = (opt.force_max_iter ? CALS_B200_FORCE_MAX_ITER : 0u) |
                          (opt.always_evict_first ? CALS_B200_ALWAYS_EVICT_FIRST : 0u) |
                          (opt.nnls ? CALS_B200_NNLS : 0u);
@@ -87,20 +96,26 @@ RunResult run_on_device(int device, const Tensor &X, const std::vector<Ktensor *
   check(e, cals_b200_clear_models(e.ctx), "cals_b200_clear_models");
 
   const dim_t N = X.get_n_modes();
-  std::vector<const double *> in(N);
-  for (Ktensor *kt : models) {
-    if (kt->get_n_modes() != N)
-      throw B200Error("cp_cals: a Ktensor has a different number of modes than the tensor");
-    for (dim_t n = 0; n < N; n++) {
-      if (kt->get_factor(n).get_rows() != X.get_modes()[n])
-        throw B200Error("cp_cals: a Ktensor factor does not match the tensor extents");
-      in[n] = kt->get_factor(n).get_data();
+  {
+    std::vector<const double *> in(models.size() * N);
+    std::vector<uint64_t> ranks(models.size());
+    std::vector<int> jk_modes(models.size());
+    std::vector<int64_t> jk_fibers(models.size());
+    for (size_t m = 0; m < models.size(); m++) {
+      const Ktensor *kt = models[m];
+      if (kt->get_n_modes() != N)
+        throw B200Error("cp_cals: a Ktensor has a different number of modes than the tensor");
+      for (dim_t n = 0; n < N; n++) {
+        if (kt->get_factor(n).get_rows() != X.get_modes()[n])
+          throw B200Error("cp_cals: a Ktensor factor does not match the tensor extents");
+        in[m * N + n] = kt->get_factor(n).get_data();
+      }
+      ranks[m] = kt->get_components();
+      jk_modes[m] = kt->is_jk() ? (int)kt->get_jk_mode() : -1;
+      jk_fibers[m] = kt->is_jk() ? (int64_t)kt->get_jk_fiber() : 0;
     }
-    int id = -1;
-    check(e,
-          cals_b200_enqueue_model(e.ctx, kt->get_components(), in.data(), kt->is_jk() ? (int)kt->get_jk_mode() : -1,
-                                  kt->is_jk() ? (int64_t)kt->get_jk_fiber() : 0, &id),
-          "cals_b200_enqueue_model");
+    check(e, cals_b200_enqueue_models(e.ctx, models.size(), ranks.data(), in.data(), jk_modes.data(), jk_fibers.data()),
+          "cals_b200_enqueue_models");
   }
   if (opt.nnls) { // warm-start active sets live in the Ktensor (reference include/ktensor.h:36); fresh ones are all-true
     std::vector<std::vector<uint8_t>> bytes(N);
@@ -125,7 +140,13 @@ RunResult run_on_device(int device, const Tensor &X, const std::vector<Ktensor *
       check(e, cals_b200_set_model_active_set(e.ctx, (int)m, ptrs.data()), "cals_b200_set_model_active_set");
     }
   }
+  const auto t_queued = now();
   check(e, cals_b200_run(e.ctx, &out.rep), "cals_b200_run");
+  const auto t_ran = now();
+  if (trace)
+    fprintf(stderr, "[cals] device %d: engine %.3f ms, set_tensor %.3f ms, queue %zu models %.3f ms, run %.3f ms\n",
+            device, ms(t_begin, t_engine), ms(t_engine, t_upload), models.size(), ms(t_upload, t_queued),
+            ms(t_queued, t_ran));
   check(e, cals_b200_line_search_counts(e.ctx, &out.ls_performed, &out.ls_failed), "cals_b200_line_search_counts");
 
   // results straight into the callers' storage (Ktensor::detach of the reference, src/ktensor.cpp:127-135)
