@@ -157,3 +157,44 @@ def test_edge_cases(pkg):
                 for Fg, Fw in zip(g.factors, w.factors):
                     assert rel_err(Fg, Fw) <= 1e-7
                 assert abs(g.fit - w.fit) <= 1e-7
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("CALS_B200_BIG"), reason="opt-in (CALS_B200_BIG=1): 8 GB tensor, "
+                    "about two minutes of host time for the generation and the CPU oracle")
+def test_config5_mttkrp_full_size(pkg):
+    """BASELINE config 5 at full size on ONE GPU: 1000^3 tensor (8 GB; byte offsets beyond 2^32), C = 1275 columns.
+    The tensor-core MTTKRP of every mode against the CPU oracle on a few columns, and the slab formulation (tensor cut
+    in two along the last mode, partial results added on the host) against the unsliced one on all columns."""
+    import importlib
+    d = importlib.import_module("cp_cals_b200.distributed")
+    rng = np.random.default_rng(5)
+    modes, C = (1000, 1000, 1000), 1275
+    X = np.empty(modes, order="F")
+    flat = X.reshape(-1, order="F")
+    for o in range(0, flat.size, 1 << 24):
+        flat[o:o + (1 << 24)] = rng.uniform(-1, 1, size=min(1 << 24, flat.size - o))
+    fs = [np.asfortranarray(rng.uniform(-1, 1, size=(i, C))) for i in modes]
+    cols = np.sort(rng.choice(C, size=3, replace=False))
+    sub = [np.asfortranarray(F[:, cols]) for F in fs]
+    full = []
+    with pkg.Engine(0) as eng:
+        eng.set_tensor(X)
+        assert abs(eng.tensor_norm() - np.sqrt(np.sum(np.square(flat)))) <= 1e-10 * eng.tensor_norm()
+        for n in range(3):
+            got, ms = eng.mttkrp(fs, n, repeats=2)
+            want = oracle.mttkrp(X, sub, n)
+            ce = np.linalg.norm(got[:, cols] - want, axis=0) / np.linalg.norm(want, axis=0)
+            assert ce.max() <= 1e-11, "mode %d worst checked column %.3e" % (n, ce.max())
+            full.append(got)
+            print("mode %d: %.2f ms, %.1f TFLOP/s" % (n, ms, 2.0 * X.size * C / ms / 1e9))
+    cuts = [0] + [hi for _, hi in d.shard_slabs(modes[2], 2)]
+    acc = [np.zeros_like(g) for g in full]
+    for r in range(2):
+        with pkg.Engine(0) as eng:
+            eng.comm_alloc(r, 2, d.exchange_capacity(modes, C))
+            eng.set_tensor_slab(modes, 2, cuts, X[:, :, cuts[r]:cuts[r + 1]])
+            for n in range(3):
+                part, _ = eng.mttkrp(fs, n)
+                acc[n] += part
+    for n in range(3):
+        assert rel_err(acc[n], full[n]) <= 1e-12
