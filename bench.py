@@ -348,6 +348,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT; rank 0 prints one JSON line there
 
     if args.impl == "reference":
         if cfg.get("sliced") is not None:
