@@ -56,6 +56,25 @@ CONFIGS = {
 }
 
 
+def init_nccl(local_rank):
+    """init_process_group + the first collective (which creates the communicator) with file descriptor 1 pointed at
+    stderr: NCCL prints its version banner on STDOUT at that moment, and stdout is reserved for the one JSON line."""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    return dist
+
+
 def load_pkg():
     from conftest import load_package
     return load_package()
@@ -207,7 +226,7 @@ def run_sliced(args, cfg, rank, world, local_rank):
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl(local_rank)
     pkg = load_pkg()
     dmod = importlib.import_module("cp_cals_b200.distributed")
     modes, s_mode, als_iters = cfg["modes"], cfg["sliced"], cfg["als_iters"]
@@ -348,8 +367,6 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on STDOUT; rank 0 prints one JSON line there
 
     if args.impl == "reference":
         if cfg.get("sliced") is not None:
@@ -373,8 +390,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = init_nccl(local_rank)
 
     pkg = load_pkg()
     import importlib
