@@ -2,6 +2,8 @@
 // identities, jackknife helpers, linear sum assignment, the model sharding plan.  Prints OK and exits 0 on success.
 #include <cmath>
 #include <cstdio>
+#include <fstream>
+#include <sstream>
 #include <numeric>
 #include <random>
 
@@ -231,6 +233,86 @@ int main() {
     mk.remove(3);
     mk.remove(4);
     REQUIRE(mk.get_factor(0).get_cols() == 0 && mk.get_registry().empty());
+  }
+
+  // text tensor files (reference src/tensor.cpp:35-65: extents on the first line, values in column-major order)
+  {
+    const char *path = "/tmp/cals_b200_tensor_check.txt";
+    {
+      std::ofstream f(path);
+      f << "3 2 2\n";
+      for (int i = 0; i < 12; i++)
+        f << (i * 0.5 - 1.25) << (i % 4 == 3 ? "\n" : " ");
+    }
+    Tensor F{std::string(path)};
+    REQUIRE(F.get_n_modes() == 3 && F.get_modes()[0] == 3 && F.get_modes()[2] == 2 && F.get_n_elements() == 12);
+    REQUIRE(F[0] == -1.25 && F[7] == 2.25 && F[11] == 4.25);
+    bool threw = false;
+    try {
+      Tensor missing{std::string("/tmp/cals_b200_no_such_file.txt")};
+    } catch (const std::exception &) {
+      threw = true;
+    }
+    REQUIRE(threw);
+    std::remove(path);
+  }
+
+  // report CSV writers keep the reference's column set (include/cals.h:70-132, include/als.h:70-135)
+  {
+    CalsReport rep;
+    rep.modes = {4, 3, 5};
+    rep.n_modes = 3;
+    rep.iter = 2;
+    rep.max_iter = 7;
+    rep.buffer_size = 9;
+    rep.n_ktensors = 3;
+    rep.ktensor_comp_sum = 6;
+    rep.n_threads = 4;
+    rep.total_time = 0.5;
+    rep.flops_per_iteration = {10, 20};
+    rep.cols = {6, 4};
+    rep.als_times = Matrix(AlsTimers::LENGTH, 2);
+    rep.mode_times = Matrix(ModeTimers::LENGTH * 3, 2);
+    rep.als_times.zero();
+    rep.mode_times.zero();
+    const char *path = "/tmp/cals_b200_report_check.csv";
+    rep.print_header(path);
+    rep.print_to_file(path);
+    std::ifstream f(path);
+    std::string header, l1, l2, extra;
+    std::getline(f, header);
+    std::getline(f, l1);
+    std::getline(f, l2);
+    REQUIRE(header.rfind("TENSOR_RANK;TENSOR_MODES;BUFFER_SIZE;N_KTENSORS;KTENSOR_COMP_SUM;UPDATE_METHOD;LINE_SEARCH;"
+                         "MAX_ITERS;ITER;NUM_THREADS;TOTAL;FLOPS;COLS;ITERATION;DEFRAGMENTATION;ERROR;LINESEARCH;G_COPY;"
+                         "MODE_0_TOTAL_MTTKRP;MODE_0_UPDATE;", 0) == 0);
+    REQUIRE(l1.rfind("0;4-3-5;9;3;6;unconstrained;0;7;1;4;0.5;10;6;", 0) == 0);
+    REQUIRE(l2.rfind("0;4-3-5;9;3;6;unconstrained;0;7;2;4;0.5;20;4;", 0) == 0);
+    REQUIRE(!std::getline(f, extra));
+    auto fields = [](const std::string &line) { return std::count(line.begin(), line.end(), ';'); };
+    REQUIRE(fields(header) == fields(l1) && fields(header) == 13 + 5 + 6);
+    std::remove(path);
+
+    AlsReport ar;
+    ar.modes = {4, 3, 5};
+    ar.n_modes = 3;
+    ar.iter = 3;
+    ar.max_iter = 5;
+    ar.ktensor_id = 17;
+    ar.ktensor_components = 2;
+    ar.als_times = Matrix(AlsTimers::LENGTH, 5);
+    ar.mode_times = Matrix(ModeTimers::LENGTH * 3, 5);
+    ar.als_times.zero();
+    ar.mode_times.zero();
+    ar.print_header(path);
+    ar.print_to_file(path);
+    std::ifstream g(path);
+    std::getline(g, header);
+    std::getline(g, l1);
+    REQUIRE(header.rfind("TENSOR_RANK;TENSOR_MODES;KTENSOR_ID;KTENSOR_COMP;UPDATE_METHOD;LINE_SEARCH;MAX_ITERS;ITER;"
+                         "NUM_THREADS;TOTAL;FLOPS;ITERATION;", 0) == 0);
+    REQUIRE(l1.rfind("0;4-3-5;17;2;unconstrained;0;5;3;", 0) == 0 && fields(header) == fields(l1));
+    std::remove(path);
   }
 
   set_threads(6);
