@@ -35,7 +35,7 @@ class Ktensor {
   double approx_error{0.0};
   bool normalized{false};
   JackKniffing jk{};
-  vector<vector<vector<bool>>> active_set; // NNLS bookkeeping of the reference; kept for interface parity only
+  vector<vector<vector<bool>>> active_set; // NNLS: [mode][row][column] constrained-to-zero flags, warm start of the next call
   vector<dim_t> modes{};
   vector<double> lambda{};
   vector<Matrix> factors{};
