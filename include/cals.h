@@ -28,8 +28,8 @@
 namespace cals {
 
 // Raised for everything the reference answers with `std::cerr << ...; exit(EXIT_FAILURE)` / abort(): unsupported
-// options (the line-search method the reference never dispatches), a missing device, a failed CUDA call.  Uncaught, it terminates the process like the
-// reference does; caught, it lets a host application recover.
+// options (the line-search method the reference never dispatches), a missing device, a failed CUDA call.  Uncaught,
+// it terminates the process like the reference does; caught, it lets a host application recover.
 struct B200Error : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
