@@ -166,6 +166,16 @@ def fp64_peak():
         return 37.0, "fallback (no profiles/fp64_peak_r01.json)"
 
 
+def measured_hbm_peak():
+    """HBM copy bandwidth of this pool's B200 in GB/s: MEASURED_PEAKS.json (driver-written), else the profiling
+    recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6534.8
+
+
 def run_reference_sample(X, models, jk, iters, threads):
     import caseio  # oracle/ (test infrastructure): allowed here as the CPU baseline / reference arm only
     ms = [caseio.Model(factors=fs, jk_mode=j[0], jk_fiber=j[1]) for fs, j in zip(models, jk)]
@@ -360,6 +370,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard-of", type=int, default=0, help="tuning aid on ONE GPU: run only the first shard of an "
                     "N-way --strong split (what each GPU of an N-GPU job gets)")
+    ap.add_argument("--no-pair-node", action="store_true", help="measurement aid: one full MTTKRP per mode (3-mode "
+                    "tensors otherwise share one contraction between modes 1 and 2, csrc/pairnode.cuh)")
     ap.add_argument("--nnls", action="store_true", help="measurement aid: update_method = NNLS instead of the Cholesky solve")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -405,6 +417,7 @@ def main():
         models, jk = [models[i] for i in mine], [jk[i] for i in mine]
         total_models = len(models)
     nX = X.size
+    modes = X.shape
     C = sum(fs[0].shape[1] for fs in models)
     n_models = len(models)
 
@@ -423,6 +436,7 @@ def main():
     eng = pkg.Engine(local_rank)
     eng.set_tensor(X)
     eng.configure(C, als_iters, 1e-7, force_max_iter=True, nnls=args.nnls)
+    eng.set_pair_node(not args.no_pair_node)
     eng.clear_models()
     for fs, j in zip(models, jk):
         eng.enqueue(fs, j[0], j[1])
@@ -457,15 +471,23 @@ def main():
 
     # ---------------- roofline of the dominant kernel (extra passes with per-kernel CUDA events) ----------------
     eng.set_timing(1)
-    mt_ms, mt_launches, up_ms = 0.0, 0, 0.0
+    mt_ms, mt_launches, up_ms, gemm_ms, leaf_ms, tensor_flops, tree = 0.0, 0, 0.0, 0.0, 0.0, 0.0, False
     for _ in range(2):
         rep = eng.rerun()
         mt_ms += rep.mttkrp_ms
         up_ms += rep.update_ms
         mt_launches += rep.mttkrp_launches
+        gemm_ms += rep.pair_gemm_ms
+        leaf_ms += rep.pair_leaf_ms
+        tensor_flops += rep.tensor_flops
+        tree = tree or bool(rep.tree)
     eng.set_timing(0)
+    # The tensor-core kernels: one full MTTKRP per mode, or -- 3-mode tensors, pair node (csrc/pairnode.cuh) -- the MTTKRP
+    # of mode 0 and the shared contraction T = X_(0)^T A_0; each launch is one tensor-sized contraction of 2*nX*C flop.
     flops_per_launch = 2.0 * nX * C
-    ach = flops_per_launch / (mt_ms / mt_launches * 1e-3) / 1e12
+    tensor_ms = mt_ms - leaf_ms
+    tensor_launches = tensor_flops / flops_per_launch
+    ach = tensor_flops / (tensor_ms * 1e-3) / 1e12
     peak, peak_src = fp64_peak()
     traffic = None
     if args.config == 2 and world == 1:
@@ -474,11 +496,31 @@ def main():
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
-    roofline = {"bound": "tensor", "kernel": "mttkrp_dmma_kernel (timed together with its mttkrp_reduce_kernel)",
+    roofline = {"bound": "tensor",
+                "kernel": "mttkrp_dmma_kernel (timed together with its mttkrp_reduce_kernel)" +
+                          (" and pair_gemm_kernel" if tree else ""),
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                "mttkrp_ms_per_launch": mt_ms / mt_launches, "flops_per_launch": flops_per_launch,
+                "ms_per_launch": tensor_ms / tensor_launches, "flops_per_launch": flops_per_launch,
+                "launches_per_als_iteration": tensor_launches / (mt_launches / len(modes)),
+                "mttkrp_ms_per_mode": mt_ms / mt_launches,
                 "mttkrp_share_of_step": mt_ms / (mt_ms + up_ms) if mt_ms + up_ms > 0 else None}
+    if tree:
+        iters = mt_launches / len(modes)
+        t_bytes = 8.0 * modes[1] * modes[2] * C  # one pass over T
+        hbm_peak = measured_hbm_peak()
+        roofline["pair_node"] = {
+            "what": "modes 1 and 2 take their MTTKRP from T = X_(0)^T A_0: two tensor-sized contractions per ALS "
+                    "iteration instead of three; the leaves stream T from HBM",
+            "mttkrp_dmma_ms_per_launch": (tensor_ms - gemm_ms) / iters,
+            "pair_gemm_ms_per_launch": gemm_ms / iters,
+            "pair_gemm_tflops": flops_per_launch / (gemm_ms / iters * 1e-3) / 1e12,
+            "leaf_ms_per_launch": leaf_ms / (2 * iters),
+            "leaf_bytes_per_launch": t_bytes,
+            "leaf_achieved_gbs": t_bytes / (leaf_ms / (2 * iters) * 1e-3) / 1e9,
+            "leaf_peak_gbs": hbm_peak,
+            "algorithmic_mttkrp_tflops": len(modes) * flops_per_launch * iters / (mt_ms * 1e-3) / 1e12,
+        }
 
     # ---------------- e2e: public API, host buffers in pinned memory ----------------
     def pinned_copy(a):
@@ -499,7 +541,8 @@ def main():
             row.append(v)
         pinned_models.append(row)
     params = pkg.CalsParams(max_iterations=als_iters, buffer_size=C, force_max_iter=True,
-                            update_method="nnls" if args.nnls else "unconstrained")
+                            update_method="nnls" if args.nnls else "unconstrained",
+                            mttkrp_method="mttkrp" if args.no_pair_node else "auto")
     h2d = X.nbytes + sum(F.nbytes for fs in models for F in fs)
     d2h = sum(F.nbytes for fs in models for F in fs) + 8 * C + n_models * 40
 

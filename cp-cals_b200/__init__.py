@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "cals_b200_comm_alloc", "cals_b200_comm_local_block", "cals_b200_comm_connect", "cals_b200_set_tensor_slab",
     "cals_b200_set_tensor_norm", "cals_b200_comm_disconnect", "cals_b200_set_model_active_set",
     "cals_b200_fetch_model_active_set", "cals_b200_set_line_search", "cals_b200_line_search_counts",
-    "cals_b200_enqueue_models",
+    "cals_b200_enqueue_models", "cals_b200_set_pair_node",
 ]
 
 
@@ -51,7 +51,9 @@ class Report(C.Structure):
     _fields_ = [("iter", C.c_uint64), ("n_ktensors", C.c_uint64), ("ktensor_comp_sum", C.c_uint64),
                 ("x_norm", C.c_double), ("total_time", C.c_double), ("device_ms", C.c_double),
                 ("mttkrp_ms", C.c_double), ("update_ms", C.c_double), ("mttkrp_launches", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("mttkrp_flops", C.c_double), ("exchange_ms", C.c_double)]
+                ("kernel_launches", C.c_uint64), ("mttkrp_flops", C.c_double), ("exchange_ms", C.c_double),
+                ("pair_gemm_ms", C.c_double), ("pair_leaf_ms", C.c_double), ("tensor_flops", C.c_double),
+                ("tree", C.c_int32), ("reserved_", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -83,6 +85,7 @@ def lib():
     L.cals_b200_configure.argtypes = [vp, u64, u64, dbl, C.c_uint]
     L.cals_b200_set_timing.argtypes = [vp, i]
     L.cals_b200_set_mttkrp_variant.argtypes = [vp, i]
+    L.cals_b200_set_pair_node.argtypes = [vp, i]
     L.cals_b200_clear_models.argtypes = [vp]
     L.cals_b200_enqueue_model.argtypes = [vp, u64, C.POINTER(vp), i, C.c_int64, C.POINTER(i)]
     L.cals_b200_run.argtypes = [vp, C.POINTER(Report)]
@@ -179,7 +182,7 @@ class CalsParams:
     """reference include/cals.h:138-159 (same names, same defaults)."""
 
     update_method: str = "unconstrained"
-    mttkrp_method: str = "auto"  # accepted and ignored: the variant choice belongs to the B200 kernels
+    mttkrp_method: str = "auto"  # "mttkrp": one contraction per mode; anything else: shared where possible (pair node)
     max_iterations: int = 200
     tol: float = 1e-7
     cuda: bool = True
@@ -213,6 +216,7 @@ class CalsReport:
     kernel_launches: int = 0
     ls_performed: int = 0
     ls_failed: int = 0
+    pair_node: bool = False  # modes 1 and 2 took their MTTKRP from the shared contraction (csrc/pairnode.cuh)
 
 
 class Engine:
@@ -334,6 +338,9 @@ class Engine:
 
     def set_mttkrp_variant(self, variant: int):
         self._ck(self._L.cals_b200_set_mttkrp_variant(self._ctx, variant))
+
+    def set_pair_node(self, enabled: bool):
+        self._ck(self._L.cals_b200_set_pair_node(self._ctx, int(bool(enabled))))
 
     # -- queue -----------------------------------------------------------------------------------------------------------
     def clear_models(self):
@@ -502,6 +509,7 @@ def cp_cals(X: np.ndarray, ktensors: Sequence[Ktensor], params: CalsParams, *, e
                             params.line_search_interval, params.line_search_step)
         eng.set_timing(timing)
         eng.set_mttkrp_variant(mttkrp_variant)
+        eng.set_pair_node(str(params.mttkrp_method).lower() != "mttkrp")
         eng.clear_models()
         eng.enqueue_many([kt.factors for kt in ktensors], [(kt.jk_mode, kt.jk_fiber) for kt in ktensors])
         if nnls:  # active sets persist in the Ktensor across calls (reference include/ktensor.h:36)
@@ -520,7 +528,7 @@ def cp_cals(X: np.ndarray, ktensors: Sequence[Ktensor], params: CalsParams, *, e
                           ktensor_comp_sum=rep.ktensor_comp_sum, tol=params.tol, total_time=rep.total_time,
                           device_ms=rep.device_ms, mttkrp_ms=rep.mttkrp_ms, update_ms=rep.update_ms,
                           mttkrp_launches=rep.mttkrp_launches, kernel_launches=rep.kernel_launches,
-                          ls_performed=lsp, ls_failed=lsf)
+                          ls_performed=lsp, ls_failed=lsf, pair_node=bool(rep.tree))
     finally:
         if own:
             eng.close()

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "ls.cuh"
 #include "mttkrp.cuh"
+#include "pairnode.cuh"
 #include "prep.cuh"
 #include "sched.cuh"
 #include "update.cuh"
@@ -47,6 +48,12 @@ struct Buffers {
   MttkrpGeom mg[CALS_MAX_MODES];
   int wm[CALS_MAX_MODES];
   PlanArgs plans{}; // per-mode work partition tables (device memory) + the inputs of mttkrp_make_plan
+  // pair node (pairnode.cuh): modes 1 and 2 of a 3-mode tensor share T = X_(0)^T A_0
+  bool tree = false;
+  double *T = nullptr; // (I1*I2) x cols
+  PairMaps pmaps;
+  PairGeom pg{};
+  int pair_wm = 0;
   std::vector<void *> allocs;
 };
 
@@ -85,6 +92,7 @@ struct cals_b200_ctx {
   unsigned flags = 0;
   int timing = 0;
   int variant = CALS_B200_MTTKRP_DMMA;
+  int pair_node = 1; // cals_b200_set_pair_node
 
   // models
   std::vector<HostModel> hmodels;
@@ -149,6 +157,7 @@ struct cals_b200_ctx {
 
   std::vector<cudaEvent_t> ev_pool;
   bool dmma_attr_done[16] = {};
+  bool pair_attr_done[16] = {};
   size_t update_attr_smem = 0;
 };
 
@@ -339,6 +348,13 @@ int build_mode_plans(cals_b200_ctx *c, Buffers &b) {
   return 0;
 }
 
+// The pair node needs the whole 3-mode tensor on this device and factor columns that fit the leaf kernels' shared memory
+// (the run loop uses it with the tensor-core MTTKRP variant only); CALS_B200_NO_PAIR_NODE=1 keeps the three per-mode MTTKRPs (A/B measurements).
+bool pair_node_wanted(cals_b200_ctx *c) {
+  static const bool off = getenv("CALS_B200_NO_PAIR_NODE") != nullptr;
+  return !off && c->pair_node && c->geo.n_modes == 3 && c->slice_mode < 0 && std::max(c->xd[1], c->xd[2]) <= 5000;
+}
+
 int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, int home_cols) {
   const Geom &geo = c->geo;
   b.cols = cols;
@@ -385,6 +401,83 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
   b.ws_tiles = tiles;
   if (dev_alloc(c, &b.ws, tiles * tile_elems, b.allocs))
     return 1;
+  b.tree = false;
+  if (with_home_cols && pair_node_wanted(c)) { // run buffers only (the single-MTTKRP test hook stays per mode)
+    const long long R = (long long)c->xd[1] * c->xd[2];
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(c, cudaMemGetInfo(&free_b, &total_b));
+    const size_t need = (size_t)R * (size_t)cols * 8;
+    if (R <= 0x7fffffffLL && need + ((size_t)2 << 30) < free_b) {
+      if (dev_alloc(c, &b.T, (size_t)R * cols, b.allocs))
+        return 1;
+      PairGeom pg{};
+      pg.R = (int)R;
+      pg.Ip = c->xd[0];
+      pg.E1 = c->xd[1];
+      pg.E2 = c->xd[2];
+      pg.mode_fast = 1;
+      pg.mode_slow = 2;
+      pg.ldT = R;
+      for (int k = 0; k < geo.n_modes; k++)
+        pg.ldF[k] = geo.ldF[k];
+      b.pg = pg;
+      b.pair_wm = pick_wm(pg.R);
+      cuuint64_t dx[2] = {(cuuint64_t)c->xd[0], (cuuint64_t)R};
+      cuuint64_t sx[1] = {(cuuint64_t)c->ldX0 * 8};
+      cuuint32_t bx[2] = {(cuuint32_t)KT, (cuuint32_t)tile_m(b.pair_wm)};
+      if (encode_map(c, &b.pmaps.X, c->Xp, 2, dx, sx, bx))
+        return 1;
+      for (int cu = 0; cu < 2; cu++) {
+        cuuint64_t d2[2] = {(cuuint64_t)c->xd[0], (cuuint64_t)cols};
+        cuuint64_t s2[1] = {(cuuint64_t)geo.ldF[0] * 8};
+        cuuint32_t b2[2] = {(cuuint32_t)KT, (cuuint32_t)TILE_N};
+        if (encode_map(c, &b.pmaps.B[cu], b.fac.buf[cu][0], 2, d2, s2, b2))
+          return 1;
+      }
+      b.tree = true;
+    }
+  }
+  return 0;
+}
+
+template <int WM> int launch_pair_gemm_wm(cals_b200_ctx *c, Buffers &b, bool attr_only) {
+  auto kern = pair_gemm_kernel<WM, WN_FIXED>;
+  constexpr int smem = PairCfg<WM, WN_FIXED>::SMEM_BYTES;
+  if (!c->pair_attr_done[WM]) {
+    CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    c->pair_attr_done[WM] = true;
+  }
+  if (!attr_only)
+    kern<<<c->sm_count, MTTKRP_THREADS, smem, c->stream>>>(b.pmaps, b.pg, c->d_st, b.T);
+  return 0;
+}
+
+// T = X_(0)^T A_0 (attr_only: just make sure the kernel's shared-memory attribute is set, outside of a graph capture)
+int launch_pair_gemm(cals_b200_ctx *c, Buffers &b, bool attr_only = false) {
+  switch (b.pair_wm) {
+  case 4:
+    return launch_pair_gemm_wm<4>(c, b, attr_only);
+  case 5:
+    return launch_pair_gemm_wm<5>(c, b, attr_only);
+  case 6:
+    return launch_pair_gemm_wm<6>(c, b, attr_only);
+  case 7:
+    return launch_pair_gemm_wm<7>(c, b, attr_only);
+  default:
+    return launch_pair_gemm_wm<8>(c, b, attr_only);
+  }
+}
+
+// MTTKRP of mode 1 or 2 from T
+int launch_pair_leaf(cals_b200_ctx *c, Buffers &b, int n) {
+  const PairGeom &pg = b.pg;
+  if (n == pg.mode_fast) {
+    dim3 grid((unsigned)b.cols, (unsigned)((pg.E1 + 255) / 256));
+    pair_leaf_slow_kernel<<<grid, 256, (size_t)pg.E2 * 8, c->stream>>>(pg, c->d_st, b.fac, b.T, b.G);
+  } else {
+    dim3 grid((unsigned)b.cols, 1);
+    pair_leaf_fast_kernel<<<grid, 256, (size_t)pg.E1 * 8, c->stream>>>(pg, c->d_st, b.fac, b.T, b.G);
+  }
   return 0;
 }
 
@@ -666,6 +759,7 @@ int prepare_run(cals_b200_ctx *c) {
   }
   sig.push_back(c->buffer_cols);
   sig.push_back(c->ls_enabled ? 1 + c->ls_method : 0);
+  sig.push_back(c->pair_node);
   for (int m = 0; m < M; m++)
     sig.push_back(c->hmodels[m].rank);
   const bool reuse = !c->run_sig.empty() && sig == c->run_sig && c->d_models && c->bufs.cols == c->buffer_cols;
@@ -820,6 +914,9 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   const bool fused_reduce = c->variant == CALS_B200_MTTKRP_DMMA && !(c->slice_mode >= 0 && c->comm_world > 1) &&
                             !fusion_off && (small_problem || fusion_forced);
 
+  // modes 1 and 2 of a 3-mode tensor: shared contraction with the factor of mode 0 (pairnode.cuh)
+  const bool tree = b.tree && c->variant == CALS_B200_MTTKRP_DMMA && !(c->slice_mode >= 0);
+
   // shared memory of the update kernel
   UpdateParams up[CALS_MAX_MODES];
   size_t up_smem[CALS_MAX_MODES];
@@ -860,7 +957,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     u.live = c->d_live;
     u.st = c->d_st;
     u.act_pool = c->d_active;
-    u.plan = fused_reduce ? b.plans.plan[n] : nullptr;
+    u.plan = (fused_reduce && !(tree && n >= 1)) ? b.plans.plan[n] : nullptr;
     u.ws = b.ws;
     u.plan_ctas = c->sm_count;
     u.tile_elems = tile_m(b.wm[n]) * TILE_N;
@@ -941,12 +1038,29 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     ring[i] = get_event(c, i);
   cudaEvent_t ev_begin = get_event(c, RA), ev_end = get_event(c, RA + 1);
   size_t ev_next = RA + 2;
-  std::vector<std::pair<size_t, int>> timed; // (first event index, kind 0 = mttkrp, 1 = update)
+  // per-kernel timing (cals_b200_set_timing): windows between events recorded on the stream
+  enum { T_MTTKRP = 0, T_UPDATE = 1, T_EXCHANGE = 2, T_PAIR_GEMM = 3, T_PAIR_LEAF = 4 };
+  struct Window {
+    size_t e0, e1;
+    int kind;
+    long long iteration;
+  };
+  std::vector<Window> timed;
 
   uint64_t launches = 1, mttkrp_launches = 0;
   auto t0 = std::chrono::steady_clock::now();
   CU_TRY(c, cudaEventRecord(ev_begin, s));
   long long it = 0;
+  auto mark = [&]() -> size_t { // no-op unless timing is on
+    if (!c->timing)
+      return 0;
+    cudaEventRecord(get_event(c, ev_next), s);
+    return ev_next++;
+  };
+  auto window = [&](size_t e0, size_t e1, int kind) {
+    if (c->timing)
+      timed.push_back({e0, e1, kind, it});
+  };
   // everything one CALS iteration launches, in stream order
   int launches_per_iteration = 0;
   auto enqueue_iteration = [&](bool count) -> int {
@@ -959,37 +1073,41 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
       n_launch++;
     }
     for (int n = 0; n < N; n++) {
-      if (c->timing) {
-        timed.push_back({ev_next, 0});
-        cudaEventRecord(get_event(c, ev_next), s);
-      }
-      if (launch_mttkrp(c, b, n, 0, c->variant, exchange, fused_reduce))
-        return -1;
-      if (exchange) {
-        if (c->timing) {
-          timed.push_back({ev_next + 3, 2}); // kind 2: exchange window = [ev_next+3, ev_next+4]
-          cudaEventRecord(get_event(c, ev_next + 3), s);
+      const size_t e0 = mark();
+      size_t e1;
+      if (tree && n >= 1) {
+        size_t el = e0;
+        if (n == 1) {
+          if (launch_pair_gemm(c, b))
+            return -1;
+          n_launch++;
+          el = mark();
+          window(e0, el, T_PAIR_GEMM);
         }
-        exchange_sum_kernel<<<c->sm_count * 2, 256, 0, s>>>(cp, c->d_st, b.G, n, N, geo.dims[n], geo.ldF[n]);
-        if (c->timing)
-          cudaEventRecord(get_event(c, ev_next + 4), s);
+        if (launch_pair_leaf(c, b, n))
+          return -1;
         n_launch++;
-      }
-      n_launch += (c->variant == CALS_B200_MTTKRP_NAIVE || fused_reduce) ? 1 : 2;
-      if (c->timing) {
-        cudaEventRecord(get_event(c, ev_next + 1), s);
-        timed.push_back({ev_next + 1, 1});
-        ev_next += 2;
+        e1 = mark();
+        window(el, e1, T_PAIR_LEAF);
+      } else {
+        if (launch_mttkrp(c, b, n, 0, c->variant, exchange, fused_reduce))
+          return -1;
+        n_launch += (c->variant == CALS_B200_MTTKRP_NAIVE || fused_reduce) ? 1 : 2;
+        if (exchange) {
+          const size_t x0 = mark();
+          exchange_sum_kernel<<<c->sm_count * 2, 256, 0, s>>>(cp, c->d_st, b.G, n, N, geo.dims[n], geo.ldF[n]);
+          window(x0, mark(), T_EXCHANGE);
+          n_launch++;
+        }
+        e1 = mark();
+        window(e0, e1, T_MTTKRP); // includes the exchange
       }
       if (up[n].nnls)
         model_update_kernel<true><<<max_live, UPDATE_THREADS, up_smem[n], s>>>(up[n]);
       else
         model_update_kernel<false><<<max_live, UPDATE_THREADS, up_smem[n], s>>>(up[n]);
       n_launch++;
-      if (c->timing) {
-        cudaEventRecord(get_event(c, ev_next), s);
-        ev_next += exchange ? 3 : 1; // skip the two events of the exchange window
-      }
+      window(e1, mark(), T_UPDATE);
     }
     if (c->ls_enabled) {
       ls_main_kernel<<<max_live, 256, 0, s>>>(lp);
@@ -1011,7 +1129,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   const bool use_graph = !c->timing && !exchange && !graphs_off;
   if (use_graph) {
     std::vector<long long> key = {c->alloc_generation, (long long)c->flags, c->ls_enabled, c->ls_method, c->variant,
-                                  (long long)max_live, fused_reduce ? 1 : 0};
+                                  (long long)max_live, fused_reduce ? 1 : 0, tree ? 1 : 0};
     const bool same_graph = c->iter_graph && c->iter_graph_key.size() == key.size() + 1 &&
                             std::equal(key.begin(), key.end(), c->iter_graph_key.begin());
     if (!same_graph) {
@@ -1020,6 +1138,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
       for (int n = 0; n < N; n++)
         if (c->variant == CALS_B200_MTTKRP_DMMA && ensure_dmma_attr(c, b.wm[n]))
           return 1;
+      if (tree && launch_pair_gemm(c, b, true))
+        return 1;
       cudaGraph_t graph = nullptr;
       CU_TRY(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       const int rc = enqueue_iteration(true);
@@ -1056,8 +1176,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
       CU_TRY(c, cudaEventSynchronize(ring[(it + 1) % RA]));
     if (*(volatile int *)&c->h_flags[0])
       break;
-    if (c->timing && ev_next > 60000) {
-      return fail(c, "timing level 1 supports at most ~6000 iterations per run");
+    if (c->timing && ev_next > 100000) {
+      return fail(c, "per-kernel timing supports at most ~100000 events per run");
     }
   }
   CU_TRY(c, cudaEventRecord(ev_end, s));
@@ -1094,24 +1214,24 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     rep->mttkrp_launches = real_mttkrp;
     rep->kernel_launches = launches;
     rep->mttkrp_flops = 2.0 * (double)c->nX * (double)N * (double)st.col_iter_sum;
+    // flop that actually ran on the tensor cores: with the pair node two contractions per iteration instead of N
+    rep->tree = tree ? 1 : 0;
+    rep->tensor_flops = 2.0 * (double)c->nX * (double)(tree ? 2 : N) * (double)st.col_iter_sum;
     if (c->timing) {
-      double mt = 0, ut = 0, xt = 0;
-      uint64_t seen_m = 0, seen_u = 0, seen_x = 0;
+      // passes launched after the queue drained (host run-ahead) are not counted
+      double sum[5] = {0, 0, 0, 0, 0};
       for (auto &t : timed) {
+        if (t.iteration >= (long long)st.global_iter)
+          continue;
         float e = 0;
-        cudaEventElapsedTime(&e, get_event(c, t.first), get_event(c, t.first + 1));
-        if (t.second == 0) {
-          if (seen_m++ < real_mttkrp)
-            mt += e;
-        } else if (t.second == 1) {
-          if (seen_u++ < real_mttkrp)
-            ut += e;
-        } else if (seen_x++ < real_mttkrp)
-          xt += e;
+        cudaEventElapsedTime(&e, get_event(c, t.e0), get_event(c, t.e1));
+        sum[t.kind] += e;
       }
-      rep->mttkrp_ms = mt;
-      rep->update_ms = ut;
-      rep->exchange_ms = xt;
+      rep->mttkrp_ms = sum[T_MTTKRP] + sum[T_PAIR_GEMM] + sum[T_PAIR_LEAF];
+      rep->update_ms = sum[T_UPDATE];
+      rep->exchange_ms = sum[T_EXCHANGE];
+      rep->pair_gemm_ms = sum[T_PAIR_GEMM];
+      rep->pair_leaf_ms = sum[T_PAIR_LEAF];
     }
   }
   c->results_fresh = false;
@@ -1435,6 +1555,13 @@ int cals_b200_set_mttkrp_variant(cals_b200_ctx *c, int variant) {
   if (variant != CALS_B200_MTTKRP_DMMA && variant != CALS_B200_MTTKRP_NAIVE)
     return fail(c, "unknown MTTKRP variant %d", variant);
   c->variant = variant;
+  return 0;
+}
+
+int cals_b200_set_pair_node(cals_b200_ctx *c, int enabled) {
+  if (!c)
+    return 1;
+  c->pair_node = enabled ? 1 : 0;
   return 0;
 }
 

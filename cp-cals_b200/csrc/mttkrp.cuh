@@ -314,15 +314,18 @@ __global__ void mttkrp_plan_kernel(const PlanArgs a, int C) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // One K8 group of one stage for one warp: NM valid m8 row groups x NN n8 column groups (both CTA-uniform, compile time).
-template <int WM, int WN, int NM, int NN>
+// SCALE = false: plain contraction (no outer weight), used by the pair-node kernel (pairnode.cuh).
+template <int WM, int WN, int NM, int NN, bool SCALE = true>
 __device__ __forceinline__ void mma_group(double (&acc)[WM][WN][2], const double *__restrict__ Xt,
                                           const double *__restrict__ Bw, const double (&wv)[WN], int gk, int r, int s) {
   double2 b[NN];
 #pragma unroll
   for (int j = 0; j < NN; j++) {
     b[j] = *reinterpret_cast<const double2 *>(Bw + (j * 64 + r) * KT + gk * 8 + 2 * s);
-    b[j].x *= wv[j];
-    b[j].y *= wv[j];
+    if (SCALE) {
+      b[j].x *= wv[j];
+      b[j].y *= wv[j];
+    }
   }
   // Row group by row group: k = 8*gk + 2s first, then k = 8*gk + 2s + 1; only one A fragment is live at a time.
 #pragma unroll
@@ -338,48 +341,48 @@ __device__ __forceinline__ void mma_group(double (&acc)[WM][WN][2], const double
 }
 
 // All K8 groups of one stage for a compile-time (NM, NN).
-template <int WM, int WN, int NM, int NN>
+template <int WM, int WN, int NM, int NN, bool SCALE = true>
 __device__ __forceinline__ void mma_stage_nm(double (&acc)[WM][WN][2], const double *Xt, const double *Bw,
                                              const double (&wv)[WN], int ngroups, int r, int s) {
   if (NM == WM && NN == WN && ngroups == KT / 8) { // the common case: fully unrolled
 #pragma unroll
     for (int gk = 0; gk < KT / 8; gk++)
-      mma_group<WM, WN, NM, NN>(acc, Xt, Bw, wv, gk, r, s);
+      mma_group<WM, WN, NM, NN, SCALE>(acc, Xt, Bw, wv, gk, r, s);
   } else {
 #pragma unroll 1
     for (int gk = 0; gk < ngroups; gk++) // K tail: rows of the K tile beyond Ip are zero-filled by TMA, skip them
-      mma_group<WM, WN, NM, NN>(acc, Xt, Bw, wv, gk, r, s);
+      mma_group<WM, WN, NM, NN, SCALE>(acc, Xt, Bw, wv, gk, r, s);
   }
 }
 
-template <int WM, int WN, int NM>
+template <int WM, int WN, int NM, bool SCALE = true>
 __device__ __forceinline__ void mma_stage_n(double (&acc)[WM][WN][2], const double *Xt, const double *Bw,
                                             const double (&wv)[WN], int ngroups, int r, int s, int nn) {
   static_assert(WN == 4, "dispatch below assumes 4 column groups per warp");
   switch (nn) {
   case 1:
-    mma_stage_nm<WM, WN, NM, 1>(acc, Xt, Bw, wv, ngroups, r, s);
+    mma_stage_nm<WM, WN, NM, 1, SCALE>(acc, Xt, Bw, wv, ngroups, r, s);
     break;
   case 2:
-    mma_stage_nm<WM, WN, NM, 2>(acc, Xt, Bw, wv, ngroups, r, s);
+    mma_stage_nm<WM, WN, NM, 2, SCALE>(acc, Xt, Bw, wv, ngroups, r, s);
     break;
   case 3:
-    mma_stage_nm<WM, WN, NM, 3>(acc, Xt, Bw, wv, ngroups, r, s);
+    mma_stage_nm<WM, WN, NM, 3, SCALE>(acc, Xt, Bw, wv, ngroups, r, s);
     break;
   default:
-    mma_stage_nm<WM, WN, NM, 4>(acc, Xt, Bw, wv, ngroups, r, s);
+    mma_stage_nm<WM, WN, NM, 4, SCALE>(acc, Xt, Bw, wv, ngroups, r, s);
     break;
   }
 }
 
-template <int WM, int WN>
+template <int WM, int WN, bool SCALE = true>
 __device__ __forceinline__ void mma_stage(double (&acc)[WM][WN][2], const double *Xt, const double *Bw,
                                           const double (&wv)[WN], int ngroups, int r, int s, int nm, int nn) {
   static_assert(WM >= 1 && WM <= 8, "extend the dispatch below");
 #define CALS_MMA_CASE(NMV)                                                                                             \
   case NMV:                                                                                                            \
     if (WM >= NMV)                                                                                                     \
-      mma_stage_n<WM, WN, (WM >= NMV ? NMV : 1)>(acc, Xt, Bw, wv, ngroups, r, s, nn);                                  \
+      mma_stage_n<WM, WN, (WM >= NMV ? NMV : 1), SCALE>(acc, Xt, Bw, wv, ngroups, r, s, nn);                           \
     break;
   switch (nm) {
     CALS_MMA_CASE(1)

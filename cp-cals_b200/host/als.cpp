@@ -51,6 +51,7 @@ static AlsReport run_single(const Tensor &X, Ktensor &ktensor, AlsParams &p, boo
   opt.ls_method = static_cast<int>(p.line_search_method);
   opt.ls_interval = p.line_search_interval;
   opt.ls_step = p.line_search_step;
+  opt.pair_node = p.mttkrp_method != mttkrp::MTTKRP_METHOD::MTTKRP;
   opt.skip_upload_if_resident = may_skip_upload;
   std::vector<Ktensor *> one{&ktensor};
   const detail::RunResult r = detail::run_on_device(p.device, X, one, opt);

@@ -93,6 +93,7 @@ RunResult run_on_device(int device, const Tensor &X, const std::vector<Ktensor *
   check(e, cals_b200_set_line_search(e.ctx, opt.line_search, opt.ls_method, opt.ls_interval, opt.ls_step),
         "cals_b200_set_line_search");
   check(e, cals_b200_set_timing(e.ctx, opt.timing), "cals_b200_set_timing");
+  check(e, cals_b200_set_pair_node(e.ctx, opt.pair_node), "cals_b200_set_pair_node");
   check(e, cals_b200_clear_models(e.ctx), "cals_b200_clear_models");
 
   const dim_t N = X.get_n_modes();
@@ -402,6 +403,7 @@ CalsReport cp_cals(const Tensor &X, KtensorQueue &kt_queue, CalsParams &cals_par
   opt.ls_interval = cals_params.line_search_interval;
   opt.ls_step = cals_params.line_search_step;
   opt.timing = cals_params.timing;
+  opt.pair_node = cals_params.mttkrp_method != mttkrp::MTTKRP_METHOD::MTTKRP;
 
   std::vector<int> devices = cals_params.devices.empty() ? std::vector<int>{0} : cals_params.devices;
   rep.n_devices = static_cast<int>(devices.size());
@@ -528,7 +530,7 @@ void CalsParams::print() const {
   cout << "Tol:             " << tol << endl;
   cout << "Max Iterations:  " << max_iterations << endl;
   cout << "Buffer Size:     " << buffer_size << endl;
-  cout << "Mttkrp Method:   " << mttkrp::mttkrp_method_names[mttkrp_method] << " (ignored: B200 kernels)" << endl;
+  cout << "Mttkrp Method:   " << mttkrp::mttkrp_method_names[mttkrp_method] << " (MTTKRP: one contraction per mode; otherwise shared where possible)" << endl;
   cout << "Update Method:   " << update::update_method_names[update_method] << endl;
   cout << "Line Search:     " << (line_search ? "true" : "false") << endl;
   if (line_search) {

@@ -43,6 +43,7 @@ struct RunOptions {
   int ls_interval{5};
   double ls_step{0.0};
   int timing{0};
+  bool pair_node{true}; // mttkrp_method != MTTKRP: modes 1 and 2 of a 3-mode tensor share one contraction
   bool skip_upload_if_resident{false};
 };
 

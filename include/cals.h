@@ -86,7 +86,7 @@ struct CalsReport {
 
 struct CalsParams {
   update::UPDATE_METHOD update_method{update::UPDATE_METHOD::UNCONSTRAINED};
-  mttkrp::MTTKRP_METHOD mttkrp_method{mttkrp::MTTKRP_METHOD::AUTO}; // accepted, ignored
+  mttkrp::MTTKRP_METHOD mttkrp_method{mttkrp::MTTKRP_METHOD::AUTO}; // MTTKRP: one contraction per mode; else shared (pair node)
   cals::mttkrp::MttkrpLut mttkrp_lut{};                             // accepted, ignored
 
   dim_t max_iterations{200};

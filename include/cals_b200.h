@@ -51,6 +51,13 @@ typedef struct cals_b200_report {
   double mttkrp_flops;       /* algorithmic flop executed by the MTTKRPs: sum over launches of 2*nX*C */
   double exchange_ms;        /* sliced tensor + timing: CUDA-event time summed over the peer-memory exchange kernels
                                 (barrier wait + NVLink pulls); it is part of mttkrp_ms as well */
+  /* 3-mode tensors held whole by one device: modes 1 and 2 take their MTTKRP from the shared contraction
+     T = X_(0)^T A_0 (csrc/pairnode.cuh), so an iteration runs two tensor-sized contractions instead of three. */
+  double pair_gemm_ms;       /* timing: CUDA-event time summed over the T contractions (part of mttkrp_ms) */
+  double pair_leaf_ms;       /* timing: CUDA-event time summed over the leaf kernels that read T (part of mttkrp_ms) */
+  double tensor_flops;       /* flop that actually ran on the FP64 tensor cores (== mttkrp_flops without the pair node) */
+  int32_t tree;              /* 1 when the pair node was used by this run */
+  int32_t reserved_;
 } cals_b200_report;
 
 typedef struct cals_b200_model_stats {
@@ -115,6 +122,10 @@ int cals_b200_line_search_counts(cals_b200_ctx *ctx, uint64_t *performed, uint64
 /* 0: no per-kernel timing (default).  1: bracket MTTKRP / update kernels with CUDA events (adds syncs at the end). */
 int cals_b200_set_timing(cals_b200_ctx *ctx, int level);
 int cals_b200_set_mttkrp_variant(cals_b200_ctx *ctx, int variant);
+/* CalsParams::mttkrp_method (reference include/cals.h:148, mttkrp::MTTKRP_METHOD in include/utils/mttkrp.h): 1 (default,
+ * AUTO / TWOSTEP0 / TWOSTEP1) lets a 3-mode tensor held whole by one device take the MTTKRPs of modes 1 and 2 from
+ * the shared contraction T = X_(0)^T A_0 (csrc/pairnode.cuh); 0 (method MTTKRP) runs one full MTTKRP per mode. */
+int cals_b200_set_pair_node(cals_b200_ctx *ctx, int enabled);
 
 /* ---- model queue (KtensorQueue, reference include/cals.h:22; MultiKtensor::add, src/multi_ktensor.cpp:41) ----- */
 int cals_b200_clear_models(cals_b200_ctx *ctx);

@@ -171,6 +171,62 @@ def test_cp_cals_per_iteration_vs_oracle(pkg, modes, ranks, K, buffer):
                 assert abs(g.fit - r.fit) <= RTOL and abs(g.old_fit - r.old_fit) <= RTOL
 
 
+@pytest.mark.parametrize("modes,ranks,K,buffer", [
+    ((23, 17, 29), [1, 2, 3, 4, 5, 6, 7], 6, None),             # ragged everything, one n-tile
+    ((40, 41, 9), [3, 8, 2, 5], 5, 10),                          # queueing: live columns change between iterations
+    ((64, 100, 48), list(range(1, 13)) * 4, 4, None),            # 312 columns: two n-tiles, several m-tiles of T
+    ((299, 31, 41), [5, 9, 2], 3, None),                         # K tail of the contracted mode (299 = 7 * 40 + 19)
+])
+def test_pair_node_equals_per_mode_mttkrp(pkg, modes, ranks, K, buffer):
+    """3-mode tensors: modes 1 and 2 take their MTTKRP from the shared contraction T = X_(0)^T A_0 (csrc/pairnode.cuh).
+    Same sums as one full MTTKRP per mode (reference src/cals.cpp:214-222), only associated differently: both paths
+    against each other and against the oracle."""
+    rng = np.random.default_rng(hash((modes, K, 7)) % 2 ** 32)
+    X = rng.uniform(-1, 1, size=modes)
+    ms = caseio.random_models(rng, modes, ranks)
+    bs = buffer or sum(ranks)
+    want = oracle.cp_cals(X, ms, max_iter=K, force_max_iter=True, buffer_size=bs)
+    out = {}
+    for method in ("auto", "mttkrp"):
+        kts = to_ktensors(pkg, ms)
+        rep = pkg.cp_cals(X, kts, pkg.CalsParams(max_iterations=K, buffer_size=bs, force_max_iter=True,
+                                                 mttkrp_method=method))
+        assert rep.pair_node == (method == "auto")
+        assert rep.iter == want.iters
+        assert_models_close(kts, want.models, want.x_norm, what=method)
+        out[method] = kts
+    for a, b in zip(out["auto"], out["mttkrp"]):
+        for Fa, Fb in zip(a.factors, b.factors):
+            assert rel_err(Fa, Fb) <= 1e-11
+        assert abs(a.fit - b.fit) <= 1e-12
+
+
+def test_pair_node_with_jackknife_nnls_and_line_search(pkg):
+    """The pair node only replaces where G comes from: flagged (jackknife) models, the NNLS update and line search
+    give the same results with and without it."""
+    rng = np.random.default_rng(77)
+    modes = (21, 19, 16)
+    gen = [rng.uniform(0, 1, size=(i, 3)) for i in modes]
+    X = caseio.ktensor_to_tensor(gen, np.ones(3)) + 0.05 * rng.standard_normal(modes)
+    ms = caseio.random_models(rng, modes, [2, 3, 4, 3])
+    ms[1].jk_mode, ms[1].jk_fiber = 0, 5
+    ms[3].jk_mode, ms[3].jk_fiber = 0, 20
+    cases = [dict(), dict(update_method="nnls"), dict(line_search=True, line_search_interval=3)]
+    for extra in cases:
+        res = {}
+        for method in ("auto", "mttkrp"):
+            kts = to_ktensors(pkg, ms)
+            rep = pkg.cp_cals(X, kts, pkg.CalsParams(max_iterations=8, buffer_size=12, force_max_iter=True,
+                                                     mttkrp_method=method, **extra))
+            assert rep.pair_node == (method == "auto")
+            res[method] = kts
+        for a, b in zip(res["auto"], res["mttkrp"]):
+            assert a.iters == b.iters
+            for Fa, Fb in zip(a.factors, b.factors):
+                assert rel_err(Fa, Fb) <= 1e-9, extra
+            assert abs(a.fit - b.fit) <= 1e-10, extra
+
+
 def test_cp_cals_large_ranks_vs_oracle(pkg):
     """Ranks as in BASELINE config 5 (up to 50) and beyond: the update kernel keeps two R x R matrices in shared
     memory and stages the factor rows in chunks."""
