@@ -498,7 +498,7 @@ def main():
             pass
     roofline = {"bound": "tensor",
                 "kernel": "mttkrp_dmma_kernel (timed together with its mttkrp_reduce_kernel)" +
-                          (" and pair_gemm_kernel" if tree else ""),
+                          (" and the pair-node contraction (pair_gemm_kernel)" if tree and len(modes) == 3 else ""),
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "ms_per_launch": tensor_ms / tensor_launches, "flops_per_launch": flops_per_launch,
@@ -507,18 +507,22 @@ def main():
                 "mttkrp_share_of_step": mt_ms / (mt_ms + up_ms) if mt_ms + up_ms > 0 else None}
     if tree:
         iters = mt_launches / len(modes)
-        t_bytes = 8.0 * modes[1] * modes[2] * C  # one pass over T
-        hbm_peak = measured_hbm_peak()
+        # 3 modes: one pair node (modes 1, 2) next to the full MTTKRP of mode 0; 4 modes: two pair nodes (0, 1), (2, 3)
+        node_rows = [modes[1] * modes[2]] if len(modes) == 3 else [modes[0] * modes[1], modes[2] * modes[3]]
+        full_modes = len(modes) - 2 * len(node_rows)
+        leaf_launches = 2 * len(node_rows) * iters
+        leaf_bytes = sum(2 * 8.0 * r * C for r in node_rows) * iters  # every leaf streams its node's T once
         roofline["pair_node"] = {
-            "what": "modes 1 and 2 take their MTTKRP from T = X_(0)^T A_0: two tensor-sized contractions per ALS "
-                    "iteration instead of three; the leaves stream T from HBM",
-            "mttkrp_dmma_ms_per_launch": (tensor_ms - gemm_ms) / iters,
-            "pair_gemm_ms_per_launch": gemm_ms / iters,
-            "pair_gemm_tflops": flops_per_launch / (gemm_ms / iters * 1e-3) / 1e12,
-            "leaf_ms_per_launch": leaf_ms / (2 * iters),
-            "leaf_bytes_per_launch": t_bytes,
-            "leaf_achieved_gbs": t_bytes / (leaf_ms / (2 * iters) * 1e-3) / 1e9,
-            "leaf_peak_gbs": hbm_peak,
+            "what": "two modes take their MTTKRP from one shared contraction T (csrc/pairnode.cuh): %d tensor-sized "
+                    "contractions per ALS iteration instead of %d; the leaf kernels stream T from HBM"
+                    % (full_modes + len(node_rows), len(modes)),
+            "mttkrp_dmma_ms_per_launch": (tensor_ms - gemm_ms) / (iters * full_modes) if full_modes else None,
+            "pair_contraction_ms_per_launch": gemm_ms / (iters * len(node_rows)),
+            "pair_contraction_tflops": flops_per_launch / (gemm_ms / (iters * len(node_rows)) * 1e-3) / 1e12,
+            "leaf_ms_per_launch": leaf_ms / leaf_launches,
+            "leaf_bytes_per_launch": leaf_bytes / leaf_launches,
+            "leaf_achieved_gbs": leaf_bytes / (leaf_ms * 1e-3) / 1e9,
+            "leaf_peak_gbs": measured_hbm_peak(),
             "algorithmic_mttkrp_tflops": len(modes) * flops_per_launch * iters / (mt_ms * 1e-3) / 1e12,
         }
 

@@ -48,11 +48,19 @@ struct Buffers {
   MttkrpGeom mg[CALS_MAX_MODES];
   int wm[CALS_MAX_MODES];
   PlanArgs plans{}; // per-mode work partition tables (device memory) + the inputs of mttkrp_make_plan
-  // pair node (pairnode.cuh): modes 1 and 2 of a 3-mode tensor share T = X_(0)^T A_0
+  // pair nodes (pairnode.cuh): two modes that take their MTTKRP from one shared contraction T.  3 modes: one node
+  // (modes 1, 2; T from pair_gemm_kernel).  4 modes: two nodes (modes 0, 1 and modes 2, 3); their T comes from
+  // mttkrp_dmma_kernel run on a 3-way view of the tensor, set up in the slots n_modes + k of maps / mg / wm / plans.
+  struct PairNode {
+    PairGeom pg{};
+    double *T = nullptr; // (E1 * E2) x cols
+    int slot = -1;       // -1: pair_gemm_kernel
+  };
   bool tree = false;
-  double *T = nullptr; // (I1*I2) x cols
+  int n_nodes = 0;
+  PairNode node[2];
+  int node_of[CALS_MAX_MODES] = {}; // node that serves mode n, -1: the mode runs its own full MTTKRP
   PairMaps pmaps;
-  PairGeom pg{};
   int pair_wm = 0;
   std::vector<void *> allocs;
 };
@@ -76,7 +84,8 @@ struct cals_b200_ctx {
   long long nX = 0;
   double *Xp = nullptr; // original order, pitch ldX0
   double *Xt = nullptr; // modes 0 and 1 swapped, pitch ldX1
-  int ldX0 = 0, ldX1 = 0;
+  double *Xq = nullptr; // 4 modes, whole tensor on this device: mode pairs (0,1) and (2,3) exchanged, pitch ldXq
+  int ldX0 = 0, ldX1 = 0, ldXq = 0;
   double *jk_norms = nullptr; // dims[0]
   double *d_norm = nullptr;
   double x_norm = 0.0;        // host copy of ||X||; valid only when x_norm_valid
@@ -348,11 +357,73 @@ int build_mode_plans(cals_b200_ctx *c, Buffers &b) {
   return 0;
 }
 
-// The pair node needs the whole 3-mode tensor on this device and factor columns that fit the leaf kernels' shared memory
-// (the run loop uses it with the tensor-core MTTKRP variant only); CALS_B200_NO_PAIR_NODE=1 keeps the three per-mode MTTKRPs (A/B measurements).
+// 4 modes: geometry and TMA descriptors of the two pair-node contractions, as slots n_modes + k of the per-mode tables.
+//   slot N   (node 0, modes 0 and 1):  T0[(i0,i1), c] = sum_{i2,i3} X A_2[i2,c] A_3[i3,c]   from Xq (mode 2 contiguous)
+//   slot N+1 (node 1, modes 2 and 3):  T1[(i2,i3), c] = sum_{i0,i1} X A_0[i0,c] A_1[i1,c]   from Xp (mode 0 contiguous)
+// Both are the MTTKRP of the last mode of a 3-way view (P, Q, R = the node's two modes flattened) of the tensor, which is
+// what mttkrp_dmma_kernel computes.
+int build_node_slots(cals_b200_ctx *c, Buffers &b) {
+  const Geom &geo = c->geo;
+  const int N = geo.n_modes;
+  for (int k = 0; k < 2; k++) {
+    const int slot = N + k;
+    const int p = k == 0 ? 2 : 0, q = p + 1; // contracted modes: p contiguous, q the outer one
+    const int R = b.node[k].pg.R;
+    const double *base = k == 0 ? c->Xq : c->Xp;
+    const long long ldp = k == 0 ? c->ldXq : c->ldX0;
+    MttkrpGeom g{};
+    g.mode = slot;
+    g.In = R;
+    g.p_mode = p;
+    g.Ip = c->xd[p];
+    g.ldG = R;
+    g.g_row_off = 0;
+    for (int m = 0; m < N; m++)
+      g.ldF[m] = geo.ldF[m];
+    g.n_outer = 1;
+    g.outer_mode[0] = q;
+    g.outer_dim[0] = c->xd[q];
+    g.outer_off[0] = 0;
+    g.outer_lmul[0] = 1;
+    g.outer_umul[0] = 0;
+    g.P_tiles = (g.Ip + KT - 1) / KT;
+    g.QC = (g.outer_dim[0] + OC - 1) / OC;
+    g.S = 1;
+    const int wm = pick_wm(R);
+    b.wm[slot] = wm;
+    g.m_tiles = (R + tile_m(wm) - 1) / tile_m(wm);
+    b.mg[slot] = g;
+    cuuint64_t dims[4] = {(cuuint64_t)c->xd[p], (cuuint64_t)c->xd[q], (cuuint64_t)R, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)ldp * 8, (cuuint64_t)ldp * c->xd[q] * 8, (cuuint64_t)ldp * c->xd[q] * R * 8};
+    cuuint32_t box[4] = {(cuuint32_t)KT, 1, (cuuint32_t)tile_m(wm), 1};
+    if (encode_map(c, &b.maps[slot].X, const_cast<double *>(base), 4, dims, strides, box))
+      return 1;
+    for (int cu = 0; cu < 2; cu++) {
+      cuuint64_t d2[2] = {(cuuint64_t)c->xd[p], (cuuint64_t)b.cols};
+      cuuint64_t s2[1] = {(cuuint64_t)geo.ldF[p] * 8};
+      cuuint32_t bx[2] = {(cuuint32_t)KT, (cuuint32_t)TILE_N};
+      if (encode_map(c, &b.maps[slot].B[cu], b.fac.buf[cu][p], 2, d2, s2, bx))
+        return 1;
+      cuuint64_t d3[2] = {(cuuint64_t)c->xd[q], (cuuint64_t)b.cols};
+      cuuint64_t s3[1] = {(cuuint64_t)geo.ldF[q] * 8};
+      cuuint32_t bw[2] = {(cuuint32_t)OC, (cuuint32_t)TILE_N};
+      if (encode_map(c, &b.maps[slot].W[cu], b.fac.buf[cu][q], 2, d3, s3, bw))
+        return 1;
+    }
+  }
+  return 0;
+}
+
+// Pair nodes need the whole 3- or 4-mode tensor on this device and factor columns that fit the leaf kernels' shared
+// memory (the run loop uses them with the tensor-core MTTKRP variant only); CALS_B200_NO_PAIR_NODE=1 keeps the three per-mode MTTKRPs (A/B measurements).
 bool pair_node_wanted(cals_b200_ctx *c) {
   static const bool off = getenv("CALS_B200_NO_PAIR_NODE") != nullptr;
-  return !off && c->pair_node && c->geo.n_modes == 3 && c->slice_mode < 0 && std::max(c->xd[1], c->xd[2]) <= 5000;
+  if (off || !c->pair_node || c->slice_mode >= 0 || (c->geo.n_modes != 3 && c->geo.n_modes != 4))
+    return false;
+  for (int n = 0; n < c->geo.n_modes; n++)
+    if (c->xd[n] > 5000)
+      return false;
+  return c->geo.n_modes == 3 || c->Xq != nullptr;
 }
 
 int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, int home_cols) {
@@ -376,18 +447,77 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
     return 1;
   if (build_mode_plans(c, b))
     return 1;
+
+  // pair nodes (run buffers only; the single-MTTKRP test hook stays per mode)
+  const int N = geo.n_modes;
+  b.tree = false;
+  b.n_nodes = 0;
+  for (int n = 0; n < CALS_MAX_MODES; n++)
+    b.node_of[n] = -1;
+  if (with_home_cols && pair_node_wanted(c)) {
+    // 3 modes: node 0 = modes (1,2).  4 modes: node 0 = modes (0,1), node 1 = modes (2,3).
+    const int n_nodes = N == 3 ? 1 : 2;
+    size_t need = 0;
+    for (int k = 0; k < n_nodes; k++) {
+      const int mf = N == 3 ? 1 : 2 * k;
+      need += (size_t)c->xd[mf] * c->xd[mf + 1] * (size_t)cols * 8;
+    }
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(c, cudaMemGetInfo(&free_b, &total_b));
+    if (2 * need + ((size_t)2 << 30) < free_b) { // T plus, for 4 modes, a partial-tile workspace of similar size
+      for (int k = 0; k < n_nodes; k++) {
+        Buffers::PairNode &nd = b.node[k];
+        const int mf = N == 3 ? 1 : 2 * k;
+        nd.pg = PairGeom{};
+        nd.pg.E1 = c->xd[mf];
+        nd.pg.E2 = c->xd[mf + 1];
+        nd.pg.R = c->xd[mf] * c->xd[mf + 1];
+        nd.pg.ldT = nd.pg.R;
+        nd.pg.mode_fast = mf;
+        nd.pg.mode_slow = mf + 1;
+        for (int m = 0; m < N; m++)
+          nd.pg.ldF[m] = geo.ldF[m];
+        nd.slot = N == 3 ? -1 : N + k;
+        if (dev_alloc(c, &nd.T, (size_t)nd.pg.R * cols, b.allocs))
+          return 1;
+        b.node_of[mf] = b.node_of[mf + 1] = k;
+      }
+      b.n_nodes = n_nodes;
+      b.tree = true;
+      if (N == 3) {
+        PairGeom &pg = b.node[0].pg;
+        pg.Ip = c->xd[0];
+        b.pair_wm = pick_wm(pg.R);
+        cuuint64_t dx[2] = {(cuuint64_t)c->xd[0], (cuuint64_t)pg.R};
+        cuuint64_t sx[1] = {(cuuint64_t)c->ldX0 * 8};
+        cuuint32_t bx[2] = {(cuuint32_t)KT, (cuuint32_t)tile_m(b.pair_wm)};
+        if (encode_map(c, &b.pmaps.X, c->Xp, 2, dx, sx, bx))
+          return 1;
+        for (int cu = 0; cu < 2; cu++) {
+          cuuint64_t d2[2] = {(cuuint64_t)c->xd[0], (cuuint64_t)cols};
+          cuuint64_t s2[1] = {(cuuint64_t)geo.ldF[0] * 8};
+          cuuint32_t b2[2] = {(cuuint32_t)KT, (cuuint32_t)TILE_N};
+          if (encode_map(c, &b.pmaps.B[cu], b.fac.buf[cu][0], 2, d2, s2, b2))
+            return 1;
+        }
+      } else if (build_node_slots(c, b))
+        return 1;
+    }
+  }
+
   size_t tiles = 0, tile_elems = 0;
   const int n_tiles_max = ((cols + 63) / 64 + OCT_TILE - 1) / OCT_TILE;
+  const int n_plans = N + ((b.tree && N == 4) ? 2 : 0);
   b.plans = PlanArgs{};
-  b.plans.n_modes = geo.n_modes;
+  b.plans.n_modes = n_plans;
   b.plans.G = c->sm_count;
-  for (int n = 0; n < geo.n_modes; n++) {
+  for (int n = 0; n < n_plans; n++) {
     const int pairs_max = b.mg[n].m_tiles * n_tiles_max;
     tiles = std::max(tiles, (size_t)(c->sm_count + pairs_max + 2));
     tile_elems = std::max(tile_elems, (size_t)tile_m(b.wm[n]) * TILE_N);
     if (dev_alloc(c, &b.plans.plan[n], (size_t)plan_capacity(c->sm_count, pairs_max), b.allocs))
       return 1;
-    b.plans.shape[n].In = c->xd[n];
+    b.plans.shape[n].In = b.mg[n].In;
     b.plans.shape[n].WM = b.wm[n];
     b.plans.shape[n].Ip = b.mg[n].Ip;
     b.plans.shape[n].Iq = b.mg[n].outer_dim[0];
@@ -401,42 +531,6 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
   b.ws_tiles = tiles;
   if (dev_alloc(c, &b.ws, tiles * tile_elems, b.allocs))
     return 1;
-  b.tree = false;
-  if (with_home_cols && pair_node_wanted(c)) { // run buffers only (the single-MTTKRP test hook stays per mode)
-    const long long R = (long long)c->xd[1] * c->xd[2];
-    size_t free_b = 0, total_b = 0;
-    CU_TRY(c, cudaMemGetInfo(&free_b, &total_b));
-    const size_t need = (size_t)R * (size_t)cols * 8;
-    if (R <= 0x7fffffffLL && need + ((size_t)2 << 30) < free_b) {
-      if (dev_alloc(c, &b.T, (size_t)R * cols, b.allocs))
-        return 1;
-      PairGeom pg{};
-      pg.R = (int)R;
-      pg.Ip = c->xd[0];
-      pg.E1 = c->xd[1];
-      pg.E2 = c->xd[2];
-      pg.mode_fast = 1;
-      pg.mode_slow = 2;
-      pg.ldT = R;
-      for (int k = 0; k < geo.n_modes; k++)
-        pg.ldF[k] = geo.ldF[k];
-      b.pg = pg;
-      b.pair_wm = pick_wm(pg.R);
-      cuuint64_t dx[2] = {(cuuint64_t)c->xd[0], (cuuint64_t)R};
-      cuuint64_t sx[1] = {(cuuint64_t)c->ldX0 * 8};
-      cuuint32_t bx[2] = {(cuuint32_t)KT, (cuuint32_t)tile_m(b.pair_wm)};
-      if (encode_map(c, &b.pmaps.X, c->Xp, 2, dx, sx, bx))
-        return 1;
-      for (int cu = 0; cu < 2; cu++) {
-        cuuint64_t d2[2] = {(cuuint64_t)c->xd[0], (cuuint64_t)cols};
-        cuuint64_t s2[1] = {(cuuint64_t)geo.ldF[0] * 8};
-        cuuint32_t b2[2] = {(cuuint32_t)KT, (cuuint32_t)TILE_N};
-        if (encode_map(c, &b.pmaps.B[cu], b.fac.buf[cu][0], 2, d2, s2, b2))
-          return 1;
-      }
-      b.tree = true;
-    }
-  }
   return 0;
 }
 
@@ -448,7 +542,7 @@ template <int WM> int launch_pair_gemm_wm(cals_b200_ctx *c, Buffers &b, bool att
     c->pair_attr_done[WM] = true;
   }
   if (!attr_only)
-    kern<<<c->sm_count, MTTKRP_THREADS, smem, c->stream>>>(b.pmaps, b.pg, c->d_st, b.T);
+    kern<<<c->sm_count, MTTKRP_THREADS, smem, c->stream>>>(b.pmaps, b.node[0].pg, c->d_st, b.node[0].T);
   return 0;
 }
 
@@ -468,15 +562,16 @@ int launch_pair_gemm(cals_b200_ctx *c, Buffers &b, bool attr_only = false) {
   }
 }
 
-// MTTKRP of mode 1 or 2 from T
+// MTTKRP of mode n from the T of its pair node
 int launch_pair_leaf(cals_b200_ctx *c, Buffers &b, int n) {
-  const PairGeom &pg = b.pg;
+  const Buffers::PairNode &nd = b.node[b.node_of[n]];
+  const PairGeom &pg = nd.pg;
   if (n == pg.mode_fast) {
     dim3 grid((unsigned)b.cols, (unsigned)((pg.E1 + 255) / 256));
-    pair_leaf_slow_kernel<<<grid, 256, (size_t)pg.E2 * 8, c->stream>>>(pg, c->d_st, b.fac, b.T, b.G);
+    pair_leaf_slow_kernel<<<grid, 256, (size_t)pg.E2 * 8, c->stream>>>(pg, c->d_st, b.fac, nd.T, b.G);
   } else {
     dim3 grid((unsigned)b.cols, 1);
-    pair_leaf_fast_kernel<<<grid, 256, (size_t)pg.E1 * 8, c->stream>>>(pg, c->d_st, b.fac, b.T, b.G);
+    pair_leaf_fast_kernel<<<grid, 256, (size_t)pg.E1 * 8, c->stream>>>(pg, c->d_st, b.fac, nd.T, b.G);
   }
   return 0;
 }
@@ -508,7 +603,7 @@ int ensure_dmma_attr(cals_b200_ctx *c, int wm) {
 }
 
 template <int WM>
-int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchange, bool skip_reduce) {
+int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchange, bool skip_reduce, double *out) {
   auto kern = mttkrp_dmma_kernel<WM, WN_FIXED>;
   if (set_dmma_attr<WM>(c))
     return 1;
@@ -520,13 +615,16 @@ int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchan
   const int cols = C_override > 0 ? C_override : b.cols;
   dim3 rg((cols + 31) / 32, (b.mg[n].In + 31) / 32);
   mttkrp_reduce_kernel<8 * WM, TILE_N><<<rg, 256, 0, c->stream>>>(
-      b.mg[n], c->d_st, b.plans.plan[n], b.ws, b.G, G, C_override, exchange ? exchange_data(c) : nullptr,
+      b.mg[n], c->d_st, b.plans.plan[n], b.ws, out, G, C_override, exchange ? exchange_data(c) : nullptr,
       (unsigned long long)c->xcap, c->seq_base, c->geo.n_modes);
   return 0;
 }
 
+// n < n_modes: MTTKRP of mode n into G.  n >= n_modes: contraction of a pair node's slot into `out` (its T).
 int launch_mttkrp(cals_b200_ctx *c, Buffers &b, int n, int C_override, int variant, bool exchange = false,
-                  bool skip_reduce = false) {
+                  bool skip_reduce = false, double *out = nullptr) {
+  if (!out)
+    out = b.G;
   if (variant == CALS_B200_MTTKRP_NAIVE) {
     if (exchange)
       return fail(c, "the naive MTTKRP variant does not support a sliced tensor over several GPUs");
@@ -550,15 +648,15 @@ int launch_mttkrp(cals_b200_ctx *c, Buffers &b, int n, int C_override, int varia
   }
   switch (b.wm[n]) {
   case 4:
-    return launch_dmma<4>(c, b, n, C_override, exchange, skip_reduce);
+    return launch_dmma<4>(c, b, n, C_override, exchange, skip_reduce, out);
   case 5:
-    return launch_dmma<5>(c, b, n, C_override, exchange, skip_reduce);
+    return launch_dmma<5>(c, b, n, C_override, exchange, skip_reduce, out);
   case 6:
-    return launch_dmma<6>(c, b, n, C_override, exchange, skip_reduce);
+    return launch_dmma<6>(c, b, n, C_override, exchange, skip_reduce, out);
   case 7:
-    return launch_dmma<7>(c, b, n, C_override, exchange, skip_reduce);
+    return launch_dmma<7>(c, b, n, C_override, exchange, skip_reduce, out);
   default:
-    return launch_dmma<8>(c, b, n, C_override, exchange, skip_reduce);
+    return launch_dmma<8>(c, b, n, C_override, exchange, skip_reduce, out);
   }
 }
 
@@ -626,7 +724,9 @@ void release_tensor(cals_b200_ctx *c) {
     cudaFree(c->Xp);
   if (c->jk_norms)
     cudaFree(c->jk_norms);
-  c->Xp = c->Xt = c->jk_norms = nullptr;
+  if (c->Xq)
+    cudaFree(c->Xq);
+  c->Xp = c->Xt = c->Xq = c->jk_norms = nullptr;
   c->have_tensor = false;
 }
 
@@ -697,6 +797,14 @@ int install_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const d
   {
     dim3 grid((I0 + 31) / 32, (I1 + 31) / 32, (unsigned)std::min<long long>(rest2, 65535));
     swap01_copy_kernel<<<grid, 256, 0, c->stream>>>(dense, c->Xt, I0, I1, c->ldX1, rest2);
+  }
+  if (n_modes == 4 && slice_mode < 0) { // third layout, for the pair node of modes (0,1) (pairnode.cuh)
+    const int I2 = c->xd[2], I3 = c->xd[3];
+    c->ldXq = round_up_int(I2, 2);
+    if (!c->Xq)
+      CU_TRY(c, cudaMalloc((void **)&c->Xq, (size_t)c->ldXq * I3 * I0 * I1 * 8));
+    dim3 grid((I0 + 31) / 32, (I2 + 31) / 32, (unsigned)std::min<long long>((long long)I1 * I3, 65535));
+    halves_swap_kernel<<<grid, 256, 0, c->stream>>>(c->Xp, c->Xq, I0, I1, I2, I3, c->ldX0, c->ldXq);
   }
   // norms: one pass over Xp
   if (!c->jk_norms)
@@ -914,8 +1022,9 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   const bool fused_reduce = c->variant == CALS_B200_MTTKRP_DMMA && !(c->slice_mode >= 0 && c->comm_world > 1) &&
                             !fusion_off && (small_problem || fusion_forced);
 
-  // modes 1 and 2 of a 3-mode tensor: shared contraction with the factor of mode 0 (pairnode.cuh)
+  // pair nodes: two modes share one contraction of the tensor (pairnode.cuh)
   const bool tree = b.tree && c->variant == CALS_B200_MTTKRP_DMMA && !(c->slice_mode >= 0);
+  auto node_of = [&](int n) { return tree ? b.node_of[n] : -1; };
 
   // shared memory of the update kernel
   UpdateParams up[CALS_MAX_MODES];
@@ -957,7 +1066,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     u.live = c->d_live;
     u.st = c->d_st;
     u.act_pool = c->d_active;
-    u.plan = (fused_reduce && !(tree && n >= 1)) ? b.plans.plan[n] : nullptr;
+    u.plan = (fused_reduce && node_of(n) < 0) ? b.plans.plan[n] : nullptr;
     u.ws = b.ws;
     u.plan_ctas = c->sm_count;
     u.tile_elems = tile_m(b.wm[n]) * TILE_N;
@@ -1075,12 +1184,19 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     for (int n = 0; n < N; n++) {
       const size_t e0 = mark();
       size_t e1;
-      if (tree && n >= 1) {
+      if (node_of(n) >= 0) {
+        const Buffers::PairNode &nd = b.node[node_of(n)];
         size_t el = e0;
-        if (n == 1) {
-          if (launch_pair_gemm(c, b))
-            return -1;
-          n_launch++;
+        if (n == nd.pg.mode_fast) { // first mode of the pair: refresh T
+          if (nd.slot < 0) {
+            if (launch_pair_gemm(c, b))
+              return -1;
+            n_launch++;
+          } else {
+            if (launch_mttkrp(c, b, nd.slot, 0, c->variant, false, false, nd.T))
+              return -1;
+            n_launch += 2;
+          }
           el = mark();
           window(e0, el, T_PAIR_GEMM);
         }
@@ -1138,8 +1254,11 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
       for (int n = 0; n < N; n++)
         if (c->variant == CALS_B200_MTTKRP_DMMA && ensure_dmma_attr(c, b.wm[n]))
           return 1;
-      if (tree && launch_pair_gemm(c, b, true))
+      if (tree && b.node[0].slot < 0 && launch_pair_gemm(c, b, true))
         return 1;
+      for (int k = 0; tree && k < b.n_nodes; k++)
+        if (b.node[k].slot >= 0 && ensure_dmma_attr(c, b.wm[b.node[k].slot]))
+          return 1;
       cudaGraph_t graph = nullptr;
       CU_TRY(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       const int rc = enqueue_iteration(true);
@@ -1216,7 +1335,11 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     rep->mttkrp_flops = 2.0 * (double)c->nX * (double)N * (double)st.col_iter_sum;
     // flop that actually ran on the tensor cores: with the pair node two contractions per iteration instead of N
     rep->tree = tree ? 1 : 0;
-    rep->tensor_flops = 2.0 * (double)c->nX * (double)(tree ? 2 : N) * (double)st.col_iter_sum;
+    int contractions = 0;
+    for (int n = 0; n < N; n++)
+      contractions += node_of(n) < 0 ? 1 : 0;
+    contractions += tree ? b.n_nodes : 0;
+    rep->tensor_flops = 2.0 * (double)c->nX * (double)contractions * (double)st.col_iter_sum;
     if (c->timing) {
       // passes launched after the queue drained (host run-ahead) are not counted
       double sum[5] = {0, 0, 0, 0, 0};

@@ -2,6 +2,7 @@
 //
 //   pad_copy_kernel        X (dense, mode 0 fastest)  ->  Xp with the fastest dimension padded to an even pitch
 //   swap01_copy_kernel     X -> Xt with modes 0 and 1 swapped (mode 1 fastest), pitch padded to even
+//   halves_swap_kernel     4-mode X -> Xq with the mode pairs (0,1) and (2,3) exchanged (mode 2 fastest), pitch padded
 //   rowsumsq_*             per mode-0 index sums of squares in ONE pass over X, from which both
 //                            ||X||          Tensor::norm                       reference include/tensor.h:196
 //                            ||X||_jk[i]    utils::calculate_jackknifing_norms reference src/utils/utils.cpp:103-152
@@ -41,6 +42,31 @@ __global__ void swap01_copy_kernel(const double *__restrict__ X, double *__restr
       const int i0 = a0 + aa, i1 = b0 + tx;
       if (i0 < I0 && i1 < ld1)
         Xd[(long long)i0 * ld1 + i1] = (i1 < I1) ? t[tx][aa] : 0.0;
+    }
+  }
+}
+
+// 4 modes: Xq[i2 + ldq * (i3 + I3 * (i0 + I0 * i1))] = Xp[i0 + ld0 * (i1 + I1 * (i2 + I2 * i3))], i.e. the transpose of X
+// viewed as the (I0*I1) x (I2*I3) matrix; the pair node of modes (0,1) contracts modes 2 and 3 along Xq's contiguous
+// dimension (pairnode.cuh).  grid = (ceil(I0/32), ceil(I2/32), chunks of I1*I3)
+__global__ void halves_swap_kernel(const double *__restrict__ Xp, double *__restrict__ Xq, int I0, int I1, int I2,
+                                   int I3, int ld0, int ldq) {
+  __shared__ double t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 256 threads
+  const int a0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const long long rest = (long long)I1 * I3;
+  for (long long r = blockIdx.z; r < rest; r += gridDim.z) {
+    const int i1 = (int)(r % I1), i3 = (int)(r / I1);
+    __syncthreads();
+    for (int bb = ty; bb < 32; bb += 8) {
+      const int i0 = a0 + tx, i2 = b0 + bb;
+      t[bb][tx] = (i0 < I0 && i2 < I2) ? Xp[i0 + (long long)ld0 * (i1 + (long long)I1 * (i2 + (long long)I2 * i3))] : 0.0;
+    }
+    __syncthreads();
+    for (int aa = ty; aa < 32; aa += 8) {
+      const int i0 = a0 + aa, i2 = b0 + tx;
+      if (i0 < I0 && i2 < ldq)
+        Xq[i2 + (long long)ldq * (i3 + (long long)I3 * (i0 + (long long)I0 * i1))] = (i2 < I2) ? t[tx][aa] : 0.0;
     }
   }
 }

@@ -176,11 +176,14 @@ def test_cp_cals_per_iteration_vs_oracle(pkg, modes, ranks, K, buffer):
     ((40, 41, 9), [3, 8, 2, 5], 5, 10),                          # queueing: live columns change between iterations
     ((64, 100, 48), list(range(1, 13)) * 4, 4, None),            # 312 columns: two n-tiles, several m-tiles of T
     ((299, 31, 41), [5, 9, 2], 3, None),                         # K tail of the contracted mode (299 = 7 * 40 + 19)
+    ((9, 8, 7, 6), [1, 2, 3, 4, 5], 5, None),                    # 4 modes: two pair nodes, (0,1) and (2,3)
+    ((12, 9, 8, 7), [3, 1, 4, 1, 5, 9, 2, 6], 5, 12),            # 4 modes + queueing
+    ((20, 44, 9, 31), list(range(1, 10)) * 8, 3, None),          # 4 modes, 360 columns, odd pitches in both layouts
 ])
 def test_pair_node_equals_per_mode_mttkrp(pkg, modes, ranks, K, buffer):
-    """3-mode tensors: modes 1 and 2 take their MTTKRP from the shared contraction T = X_(0)^T A_0 (csrc/pairnode.cuh).
-    Same sums as one full MTTKRP per mode (reference src/cals.cpp:214-222), only associated differently: both paths
-    against each other and against the oracle."""
+    """Pair nodes (csrc/pairnode.cuh): 3-mode tensors take the MTTKRPs of modes 1 and 2 from T = X_(0)^T A_0, 4-mode
+    tensors those of modes (0,1) and (2,3) from one contraction each.  Same sums as one full MTTKRP per mode (reference
+    src/cals.cpp:214-222), only associated differently: both paths against each other and against the oracle."""
     rng = np.random.default_rng(hash((modes, K, 7)) % 2 ** 32)
     X = rng.uniform(-1, 1, size=modes)
     ms = caseio.random_models(rng, modes, ranks)
