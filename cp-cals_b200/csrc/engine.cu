@@ -236,13 +236,36 @@ int wm_max() {
   return v;
 }
 
-int pick_wm(int In) {
-  // m8 row groups are split evenly over ceil(In8 / wm_max) m-tiles; the tile is then only as tall as that split needs,
+int pick_wm(int In, int tallest = 0) {
+  // m8 row groups are split evenly over ceil(In8 / tallest) m-tiles; the tile is then only as tall as that split needs,
   // so that most tiles are full and run the fully unrolled path.
+  if (tallest <= 0)
+    tallest = wm_max();
   const int In8 = (In + 7) / 8;
-  const int m_tiles = (In8 + wm_max() - 1) / wm_max();
+  const int m_tiles = (In8 + tallest - 1) / tallest;
   const int wm = (In8 + m_tiles - 1) / m_tiles;
   return wm < 4 ? 4 : wm;
+}
+
+// Tile height of pair_gemm_kernel.  Both operands stream through the ring, so a taller tile has the better flop-per-byte
+// ratio (measured at 200^3 x 2100 columns: 31.6 / 33.6 / 34.6 TFLOP/s for 40 / 48 / 64 rows); small problems want enough
+// tiles to fill the last wave of the persistent grid.  Score = speed of the tile shape x fill of the waves.
+int pick_pair_wm(int R, int cols, int sms) {
+  static const double shape_speed[9] = {0, 0, 0, 0, 0.88, 0.915, 0.97, 0.985, 1.0};
+  const long long R8 = (R + 7) / 8, n_tiles = (cols + TileCfg<4, WN_FIXED>::N_TILE - 1) / TileCfg<4, WN_FIXED>::N_TILE;
+  int best = 8;
+  double best_score = -1.0;
+  for (int wm = 8; wm >= 4; wm--) {
+    const long long tiles = ((R8 + wm - 1) / wm) * n_tiles;
+    const long long waves = (tiles + sms - 1) / sms;
+    const double rows_used = (double)R8 / (double)(((R8 + wm - 1) / wm) * wm);
+    const double score = shape_speed[wm] * rows_used * (double)tiles / (double)(waves * sms);
+    if (score > best_score) {
+      best_score = score;
+      best = wm;
+    }
+  }
+  return best;
 }
 
 template <int WM> int smem_bytes() { return TileCfg<WM, WN_FIXED>::SMEM_BYTES; }
@@ -487,7 +510,7 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
       if (N == 3) {
         PairGeom &pg = b.node[0].pg;
         pg.Ip = c->xd[0];
-        b.pair_wm = pick_wm(pg.R);
+        b.pair_wm = pick_pair_wm(pg.R, cols, c->sm_count);
         cuuint64_t dx[2] = {(cuuint64_t)c->xd[0], (cuuint64_t)pg.R};
         cuuint64_t sx[1] = {(cuuint64_t)c->ldX0 * 8};
         cuuint32_t bx[2] = {(cuuint32_t)KT, (cuuint32_t)tile_m(b.pair_wm)};

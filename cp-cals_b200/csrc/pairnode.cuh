@@ -179,7 +179,9 @@ pair_leaf_slow_kernel(const PairGeom g, const SchedState *__restrict__ st, const
   G[(size_t)c * g.ldF[g.mode_fast] + i1] = sum;
 }
 
-// G_slow[i2, c] = sum_{i1} T[i1 + E1*i2, c] * A_fast[i1, c].  One CTA per column; a warp per i2, lanes over i1.
+// G_slow[i2, c] = sum_{i1} T[i1 + E1*i2, c] * A_fast[i1, c].  One CTA per column; a warp takes LEAF_ROWS values of i2 at a
+// time (independent loads in flight), lanes run over i1.
+constexpr int LEAF_ROWS = 4;
 __global__ void __launch_bounds__(256)
 pair_leaf_fast_kernel(const PairGeom g, const SchedState *__restrict__ st, const FactorPtrs fac,
                       const double *__restrict__ T, double *__restrict__ G) {
@@ -194,16 +196,33 @@ pair_leaf_fast_kernel(const PairGeom g, const SchedState *__restrict__ st, const
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const double *tc = T + (size_t)c * g.ldT;
-  for (int i2 = blockIdx.y * nw + warp; i2 < g.E2; i2 += gridDim.y * nw) {
-    const double *t = tc + (size_t)i2 * g.E1;
-    double sum = 0.0;
-    for (int i1 = lane; i1 < g.E1; i1 += 32)
-      sum += __ldcs(t + i1) * wcol[i1];
+  double *out = G + (size_t)c * g.ldF[g.mode_slow];
+  for (int b2 = (blockIdx.y * nw + warp) * LEAF_ROWS; b2 < g.E2; b2 += gridDim.y * nw * LEAF_ROWS) {
+    const double *t[LEAF_ROWS];
+    double sum[LEAF_ROWS];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0)
-      G[(size_t)c * g.ldF[g.mode_slow] + i2] = sum;
+    for (int u = 0; u < LEAF_ROWS; u++) {
+      t[u] = tc + (size_t)min(b2 + u, g.E2 - 1) * g.E1; // rows beyond E2 re-read the last row; their sums are dropped
+      sum[u] = 0.0;
+    }
+    for (int i1 = lane; i1 < g.E1; i1 += 32) {
+      const double w = wcol[i1];
+      double v[LEAF_ROWS];
+#pragma unroll
+      for (int u = 0; u < LEAF_ROWS; u++)
+        v[u] = __ldcs(t[u] + i1);
+#pragma unroll
+      for (int u = 0; u < LEAF_ROWS; u++)
+        sum[u] += v[u] * w;
+    }
+#pragma unroll
+    for (int u = 0; u < LEAF_ROWS; u++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+      if (lane == 0 && b2 + u < g.E2)
+        out[b2 + u] = sum[u];
+    }
   }
 }
 

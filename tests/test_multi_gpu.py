@@ -211,7 +211,8 @@ def test_single_slab_run_equals_plain_run(pkg):
     modes = (20, 16, 30)
     X = rng.uniform(-1, 1, size=modes)
     ms = caseio.random_models(rng, modes, [4, 2, 7, 1])
-    p = pkg.CalsParams(max_iterations=6, buffer_size=14, force_max_iter=True)
+    # one full MTTKRP per mode on both sides: a sliced tensor never uses the pair node (csrc/pairnode.cuh)
+    p = pkg.CalsParams(max_iterations=6, buffer_size=14, force_max_iter=True, mttkrp_method="mttkrp")
     plain = to_ktensors(pkg, ms)
     pkg.cp_cals(X, plain, p)
     sliced = to_ktensors(pkg, ms)
@@ -220,6 +221,12 @@ def test_single_slab_run_equals_plain_run(pkg):
     for a, b in zip(plain, sliced):
         assert all(np.array_equal(x, y) for x, y in zip(a.factors, b.factors))
         assert np.array_equal(a.lam, b.lam) and a.error == b.error
+    # and the default plain run (pair node) agrees with it to rounding
+    shared = to_ktensors(pkg, ms)
+    rep = pkg.cp_cals(X, shared, pkg.CalsParams(max_iterations=6, buffer_size=14, force_max_iter=True))
+    assert rep.pair_node
+    for a, b in zip(shared, sliced):
+        assert all(np.allclose(x, y, rtol=0, atol=1e-11) for x, y in zip(a.factors, b.factors))
 
 
 def _sliced_worker(rank, world, port, out_dir):
