@@ -306,8 +306,10 @@ def run_sliced(args, cfg, rank, world, local_rank):
     eng.set_timing(1)
     rep = eng.rerun()
     eng.set_timing(0)
-    mt_ms = max_over_ranks(rep.mttkrp_ms) / rep.mttkrp_launches
+    # tensor-sized contractions of the slab: one per mode, or -- slab cut along mode 1 or 2, pair node -- two per iteration
     flops_per_launch = 2.0 * float(np.prod(shape)) * C
+    tensor_launches = rep.tensor_flops / flops_per_launch
+    mt_ms = max_over_ranks(rep.mttkrp_ms - rep.pair_leaf_ms) / tensor_launches
     peak, peak_src = fp64_peak()
     ach = flops_per_launch / (mt_ms * 1e-3) / 1e12
     # NVLink volume of the exchange: every GPU pulls the partials of the other W-1 GPUs (full-size for the modes that
@@ -320,10 +322,14 @@ def run_sliced(args, cfg, rank, world, local_rank):
                 "achieved_gbs_incl_barrier_wait": float(np.mean(pulled)) / (xch_ms * 1e-3) / 1e9 if xch_ms > 0 else None,
                 "peer_copy_peak_gbs": 770.0, "share_of_mttkrp_window": rep.exchange_ms / rep.mttkrp_ms
                 if rep.mttkrp_ms > 0 else None} if world > 1 else None
-    roofline = {"bound": "tensor", "kernel": "mttkrp_dmma_kernel (+ reduce + NVLink exchange_sum_kernel)",
+    roofline = {"bound": "tensor", "kernel": "mttkrp_dmma_kernel (+ reduce + NVLink exchange_sum_kernel)" +
+                          (" and pair_gemm_kernel" if rep.tree else ""),
+                "pair_node": {"contractions_per_als_iteration": tensor_launches / rep.iter,
+                              "leaf_ms_per_launch_incl_exchange": max_over_ranks(rep.pair_leaf_ms) / (2 * rep.iter),
+                              "pair_gemm_ms_per_launch": max_over_ranks(rep.pair_gemm_ms) / rep.iter} if rep.tree else None,
                 "exchange": exchange,
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s per GPU", "frac": ach / peak, "traffic": None,
-                "peak_source": peak_src, "mttkrp_ms_per_launch": mt_ms, "flops_per_launch_per_gpu": flops_per_launch,
+                "peak_source": peak_src, "ms_per_launch": mt_ms, "flops_per_launch_per_gpu": flops_per_launch,
                 "mttkrp_share_of_step": rep.mttkrp_ms / (rep.mttkrp_ms + rep.update_ms)}
 
     e2e_steps = 2

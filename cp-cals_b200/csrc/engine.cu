@@ -437,11 +437,14 @@ int build_node_slots(cals_b200_ctx *c, Buffers &b) {
   return 0;
 }
 
-// Pair nodes need the whole 3- or 4-mode tensor on this device and factor columns that fit the leaf kernels' shared
-// memory (the run loop uses them with the tensor-core MTTKRP variant only); CALS_B200_NO_PAIR_NODE=1 keeps the three per-mode MTTKRPs (A/B measurements).
+// Pair nodes need a 3- or 4-mode tensor that is whole on this device (or, 3 modes, sliced along mode 1 or 2) and factor
+// columns that fit the leaf kernels' shared memory (the run loop uses them with the tensor-core MTTKRP variant only); CALS_B200_NO_PAIR_NODE=1 keeps the three per-mode MTTKRPs (A/B measurements).
 bool pair_node_wanted(cals_b200_ctx *c) {
   static const bool off = getenv("CALS_B200_NO_PAIR_NODE") != nullptr;
-  if (off || !c->pair_node || c->slice_mode >= 0 || (c->geo.n_modes != 3 && c->geo.n_modes != 4))
+  if (off || !c->pair_node || (c->geo.n_modes != 3 && c->geo.n_modes != 4))
+    return false;
+  // a sliced tensor: T of a slab is local to its GPU when the slab cuts one of the pair's own modes (3 modes: 1 or 2)
+  if (c->slice_mode >= 0 && !(c->geo.n_modes == 3 && c->slice_mode >= 1))
     return false;
   for (int n = 0; n < c->geo.n_modes; n++)
     if (c->xd[n] > 5000)
@@ -498,6 +501,8 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
         nd.pg.ldT = nd.pg.R;
         nd.pg.mode_fast = mf;
         nd.pg.mode_slow = mf + 1;
+        nd.pg.off_fast = c->roff[mf];
+        nd.pg.off_slow = c->roff[mf + 1];
         for (int m = 0; m < N; m++)
           nd.pg.ldF[m] = geo.ldF[m];
         nd.slot = N == 3 ? -1 : N + k;
@@ -585,16 +590,23 @@ int launch_pair_gemm(cals_b200_ctx *c, Buffers &b, bool attr_only = false) {
   }
 }
 
+double *exchange_data(cals_b200_ctx *c);
+
 // MTTKRP of mode n from the T of its pair node
-int launch_pair_leaf(cals_b200_ctx *c, Buffers &b, int n) {
+int launch_pair_leaf(cals_b200_ctx *c, Buffers &b, int n, bool exchange) {
   const Buffers::PairNode &nd = b.node[b.node_of[n]];
   const PairGeom &pg = nd.pg;
+  LeafExchange x{};
+  x.xbuf = exchange ? exchange_data(c) : nullptr;
+  x.xcap = (unsigned long long)c->xcap;
+  x.seq_base = c->seq_base;
+  x.n_modes = c->geo.n_modes;
   if (n == pg.mode_fast) {
     dim3 grid((unsigned)b.cols, (unsigned)((pg.E1 + 255) / 256));
-    pair_leaf_slow_kernel<<<grid, 256, (size_t)pg.E2 * 8, c->stream>>>(pg, c->d_st, b.fac, nd.T, b.G);
+    pair_leaf_slow_kernel<<<grid, 256, (size_t)pg.E2 * 8, c->stream>>>(pg, c->d_st, b.fac, nd.T, b.G, x);
   } else {
     dim3 grid((unsigned)b.cols, 1);
-    pair_leaf_fast_kernel<<<grid, 256, (size_t)pg.E1 * 8, c->stream>>>(pg, c->d_st, b.fac, nd.T, b.G);
+    pair_leaf_fast_kernel<<<grid, 256, (size_t)pg.E1 * 8, c->stream>>>(pg, c->d_st, b.fac, nd.T, b.G, x);
   }
   return 0;
 }
@@ -1046,7 +1058,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
                             !fusion_off && (small_problem || fusion_forced);
 
   // pair nodes: two modes share one contraction of the tensor (pairnode.cuh)
-  const bool tree = b.tree && c->variant == CALS_B200_MTTKRP_DMMA && !(c->slice_mode >= 0);
+  const bool tree = b.tree && c->variant == CALS_B200_MTTKRP_DMMA;
   auto node_of = [&](int n) { return tree ? b.node_of[n] : -1; };
 
   // shared memory of the update kernel
@@ -1223,11 +1235,17 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
           el = mark();
           window(e0, el, T_PAIR_GEMM);
         }
-        if (launch_pair_leaf(c, b, n))
+        if (launch_pair_leaf(c, b, n, exchange))
           return -1;
         n_launch++;
+        if (exchange) {
+          const size_t x0 = mark();
+          exchange_sum_kernel<<<c->sm_count * 2, 256, 0, s>>>(cp, c->d_st, b.G, n, N, geo.dims[n], geo.ldF[n]);
+          window(x0, mark(), T_EXCHANGE);
+          n_launch++;
+        }
         e1 = mark();
-        window(el, e1, T_PAIR_LEAF);
+        window(el, e1, T_PAIR_LEAF); // includes the exchange
       } else {
         if (launch_mttkrp(c, b, n, 0, c->variant, exchange, fused_reduce))
           return -1;

@@ -35,6 +35,9 @@ struct PairGeom {
   int E1;  // extent of the fast index of a T row (I1)
   int E2;  // extent of the slow index (I2)
   int mode_fast, mode_slow; // the two modes of the pair (1 and 2)
+  // Slab mode (3-mode tensor sliced along mode 1 or 2 over several GPUs): this device's T covers rows
+  // [off, off + E) of the sliced mode's factor and of its G; 0 otherwise.
+  int off_fast, off_slow;
   long long ldT;
   int ldF[CALS_MAX_MODES]; // leading dimensions of the factor buffers == those of G for the same mode
 };
@@ -146,16 +149,31 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
   }
 }
 
+// Slab mode over several GPUs: a leaf's result is this device's PARTIAL sum (or its own row block) and goes to the exchange
+// buffer that comm.cuh's exchange kernel collects, exactly as mttkrp_reduce_kernel does for a full MTTKRP.
+struct LeafExchange {
+  double *xbuf; // nullptr: write G
+  unsigned long long xcap, seq_base;
+  int n_modes;
+};
+__device__ __forceinline__ double *leaf_output(double *G, const LeafExchange &x, const SchedState *st, int mode) {
+  if (x.xbuf == nullptr)
+    return G;
+  const unsigned long long seq = x.seq_base + st->global_iter * (unsigned long long)x.n_modes + mode + 1;
+  return x.xbuf + (seq & 1ull) * x.xcap;
+}
+
 // G_fast[i1, c] = sum_{i2} T[i1 + E1*i2, c] * A_slow[i2, c].  One CTA per column and 256-row chunk of i1; thread = row.
 __global__ void __launch_bounds__(256)
 pair_leaf_slow_kernel(const PairGeom g, const SchedState *__restrict__ st, const FactorPtrs fac,
-                      const double *__restrict__ T, double *__restrict__ G) {
+                      const double *__restrict__ T, double *__restrict__ G, const LeafExchange x) {
   const int C = st->C, cur = st->cur;
   const int c = blockIdx.x;
   if (c >= C)
     return;
+  G = leaf_output(G, x, st, g.mode_fast);
   extern __shared__ double wcol[]; // E2
-  const double *W = fac.buf[cur][g.mode_slow] + (size_t)c * g.ldF[g.mode_slow];
+  const double *W = fac.buf[cur][g.mode_slow] + (size_t)c * g.ldF[g.mode_slow] + g.off_slow;
   for (int k = threadIdx.x; k < g.E2; k += blockDim.x)
     wcol[k] = W[k];
   __syncthreads();
@@ -176,7 +194,7 @@ pair_leaf_slow_kernel(const PairGeom g, const SchedState *__restrict__ st, const
   }
   for (; k < g.E2; k++)
     sum += __ldcs(t + (size_t)k * g.E1) * wcol[k];
-  G[(size_t)c * g.ldF[g.mode_fast] + i1] = sum;
+  G[(size_t)c * g.ldF[g.mode_fast] + i1 + g.off_fast] = sum;
 }
 
 // G_slow[i2, c] = sum_{i1} T[i1 + E1*i2, c] * A_fast[i1, c].  One CTA per column; a warp takes LEAF_ROWS values of i2 at a
@@ -184,19 +202,20 @@ pair_leaf_slow_kernel(const PairGeom g, const SchedState *__restrict__ st, const
 constexpr int LEAF_ROWS = 4;
 __global__ void __launch_bounds__(256)
 pair_leaf_fast_kernel(const PairGeom g, const SchedState *__restrict__ st, const FactorPtrs fac,
-                      const double *__restrict__ T, double *__restrict__ G) {
+                      const double *__restrict__ T, double *__restrict__ G, const LeafExchange x) {
   const int C = st->C, cur = st->cur;
   const int c = blockIdx.x;
   if (c >= C)
     return;
+  G = leaf_output(G, x, st, g.mode_slow);
   extern __shared__ double wcol[]; // E1
-  const double *W = fac.buf[cur][g.mode_fast] + (size_t)c * g.ldF[g.mode_fast];
+  const double *W = fac.buf[cur][g.mode_fast] + (size_t)c * g.ldF[g.mode_fast] + g.off_fast;
   for (int k = threadIdx.x; k < g.E1; k += blockDim.x)
     wcol[k] = W[k];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const double *tc = T + (size_t)c * g.ldT;
-  double *out = G + (size_t)c * g.ldF[g.mode_slow];
+  double *out = G + (size_t)c * g.ldF[g.mode_slow] + g.off_slow;
   for (int b2 = (blockIdx.y * nw + warp) * LEAF_ROWS; b2 < g.E2; b2 += gridDim.y * nw * LEAF_ROWS) {
     const double *t[LEAF_ROWS];
     double sum[LEAF_ROWS];

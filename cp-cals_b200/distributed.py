@@ -185,6 +185,7 @@ def cp_cals_sliced(slab: np.ndarray, modes: Sequence[int], slice_mode: int, kten
         eng.configure(buffer_cols, params.max_iterations, params.tol, params.force_max_iter, params.always_evict_first)
         eng.set_line_search(False)
         eng.set_timing(timing)
+        eng.set_pair_node(str(params.mttkrp_method).lower() != "mttkrp")
         eng.clear_models()
         for kt in ktensors:
             eng.enqueue(kt.factors, kt.jk_mode, kt.jk_fiber)

@@ -284,6 +284,7 @@ static RunResult run_sliced(const std::vector<int> &devices, int slice_mode, con
     check(*eng[r], cals_b200_set_line_search(eng[r]->ctx, opt.line_search, opt.ls_method, opt.ls_interval, opt.ls_step),
           "cals_b200_set_line_search");
     check(*eng[r], cals_b200_set_timing(eng[r]->ctx, opt.timing), "cals_b200_set_timing");
+    check(*eng[r], cals_b200_set_pair_node(eng[r]->ctx, opt.pair_node), "cals_b200_set_pair_node");
     check(*eng[r], cals_b200_clear_models(eng[r]->ctx), "cals_b200_clear_models");
     for (Ktensor *kt : models) {
       for (dim_t n = 0; n < N; n++)

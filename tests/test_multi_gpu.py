@@ -211,22 +211,20 @@ def test_single_slab_run_equals_plain_run(pkg):
     modes = (20, 16, 30)
     X = rng.uniform(-1, 1, size=modes)
     ms = caseio.random_models(rng, modes, [4, 2, 7, 1])
-    # one full MTTKRP per mode on both sides: a sliced tensor never uses the pair node (csrc/pairnode.cuh)
-    p = pkg.CalsParams(max_iterations=6, buffer_size=14, force_max_iter=True, mttkrp_method="mttkrp")
-    plain = to_ktensors(pkg, ms)
-    pkg.cp_cals(X, plain, p)
-    sliced = to_ktensors(pkg, ms)
-    rep = d.cp_cals_sliced(X, modes, 2, sliced, p)
-    assert rep.iter == 6
-    for a, b in zip(plain, sliced):
-        assert all(np.array_equal(x, y) for x, y in zip(a.factors, b.factors))
-        assert np.array_equal(a.lam, b.lam) and a.error == b.error
-    # and the default plain run (pair node) agrees with it to rounding
-    shared = to_ktensors(pkg, ms)
-    rep = pkg.cp_cals(X, shared, pkg.CalsParams(max_iterations=6, buffer_size=14, force_max_iter=True))
-    assert rep.pair_node
-    for a, b in zip(shared, sliced):
-        assert all(np.allclose(x, y, rtol=0, atol=1e-11) for x, y in zip(a.factors, b.factors))
+    # a single slab that covers the whole tensor runs the very same kernels on the very same data, with and without the
+    # pair node (cut along mode 2: T is local to the slab, csrc/pairnode.cuh); cut along mode 0 there is no pair node
+    for method, s_mode, shared in (("mttkrp", 2, False), ("auto", 2, True), ("auto", 0, False)):
+        p = pkg.CalsParams(max_iterations=6, buffer_size=14, force_max_iter=True, mttkrp_method=method)
+        plain = to_ktensors(pkg, ms)
+        rep0 = pkg.cp_cals(X, plain, pkg.CalsParams(max_iterations=6, buffer_size=14, force_max_iter=True,
+                                                    mttkrp_method="auto" if shared else "mttkrp"))
+        assert rep0.pair_node == shared
+        sliced = to_ktensors(pkg, ms)
+        rep = d.cp_cals_sliced(X, modes, s_mode, sliced, p)
+        assert rep.iter == 6
+        for a, b in zip(plain, sliced):
+            assert all(np.array_equal(x, y) for x, y in zip(a.factors, b.factors)), (method, s_mode)
+            assert np.array_equal(a.lam, b.lam) and a.error == b.error
 
 
 def _sliced_worker(rank, world, port, out_dir):
@@ -244,7 +242,7 @@ def _sliced_worker(rank, world, port, out_dir):
         import importlib
         d = importlib.import_module("cp_cals_b200.distributed")
         X, modes, ranks, ms = _sliced_case()
-        for s in (2, 0):
+        for s in (2, 1, 0):  # 2, 1: pair node on every slab; 0: one MTTKRP per mode
             lo, hi = d.shard_slabs(modes[s], world)[rank]
             sl = [slice(None)] * len(modes)
             sl[s] = slice(lo, hi)
@@ -271,7 +269,7 @@ def _sliced_case():
 
 @pytest.mark.gpu
 def test_sliced_tensor_over_gpus_matches_oracle(tmp_path):
-    """Real exchange over NVLink peer memory: W processes, one GPU each, X sliced along the last and the first mode."""
+    """Real exchange over NVLink peer memory: W processes, one GPU each, X sliced along each of its modes in turn."""
     import torch
     import torch.multiprocessing as mp
     import oracle
@@ -281,7 +279,7 @@ def test_sliced_tensor_over_gpus_matches_oracle(tmp_path):
     mp.spawn(_sliced_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     X, modes, ranks, ms = _sliced_case()
     want = oracle.cp_cals(X, ms, max_iter=5, force_max_iter=True)
-    for s in (2, 0):
+    for s in (2, 1, 0):  # 2, 1: pair node on every slab; 0: one MTTKRP per mode
         outs = [np.load(os.path.join(str(tmp_path), "sliced_s%d_rank%d.npz" % (s, r))) for r in range(world)]
         for k in outs[0].files:  # replicated state: bit-identical on every GPU
             for o in outs[1:]:
