@@ -1,13 +1,18 @@
-// Pair node of a one-level dimension tree over the modes (3-mode tensors): the MTTKRPs of modes 1 and 2 share the
-// contraction of the tensor with the factor of mode 0,
-//     T[(i1,i2), c] = sum_{i0} X[i0, i1, i2] * A_0[i0, c]                       (pair_gemm_kernel, FP64 tensor cores)
-//     G_1[i1, c]    = sum_{i2} T[(i1,i2), c] * A_2[i2, c]                       (pair_leaf_slow_kernel, HBM-bound)
-//     G_2[i2, c]    = sum_{i1} T[(i1,i2), c] * A_1[i1, c]                       (pair_leaf_fast_kernel, HBM-bound)
-// T depends on A_0 only, which ALS updates before modes 1 and 2, so both leaves see exactly the factors the
-// reference's per-mode MTTKRPs see (src/cals.cpp:214-222 calls mttkrp::mttkrp once per mode; the sums are the same,
-// only their association differs).  One ALS iteration then costs two tensor-sized contractions instead of three.  This is
-// the reference's own two-step idea (mttkrp_twostep0/1, src/utils/mttkrp.cpp:460-553: "mode1/TS0 uses the same T as
-// mode0/TS0") carried across modes; T (I1*I2 x C doubles) lives in HBM.
+// Pair nodes: a one-level dimension tree over the modes.  Two modes take their MTTKRPs from ONE tensor-sized
+// contraction T that does not involve either of their factors:
+//
+//   3 modes (pair = modes 1, 2):   T[(i1,i2), c] = sum_{i0} X[i0,i1,i2] * A_0[i0,c]           pair_gemm_kernel (FP64 tensor cores)
+//   4 modes (pairs (0,1), (2,3)):  T0[(i0,i1), c] = sum_{i2,i3} X * A_2[i2,c] * A_3[i3,c]      mttkrp_dmma_kernel on a 3-way view
+//                                  T1[(i2,i3), c] = sum_{i0,i1} X * A_0[i0,c] * A_1[i1,c]      (set up in engine.cu)
+//   leaves, for a pair (f, s) with T rows (i_f, i_s), i_f fastest:
+//                                  G_f[i_f, c] = sum_{i_s} T[(i_f,i_s), c] * A_s[i_s, c]        pair_leaf_slow_kernel (HBM-bound)
+//                                  G_s[i_s, c] = sum_{i_f} T[(i_f,i_s), c] * A_f[i_f, c]        pair_leaf_fast_kernel (HBM-bound)
+//
+// ALS updates mode f, then mode s, and T holds neither factor, so both leaves see exactly the factors the reference's
+// per-mode MTTKRPs see (src/cals.cpp:214-222 calls mttkrp::mttkrp once per mode): the sums are the same, only their
+// association differs.  An ALS iteration then costs two tensor-sized contractions instead of three (four).  This is the
+// reference's own two-step idea (mttkrp_twostep0/1, src/utils/mttkrp.cpp:460-553: "mode1/TS0 uses the same T as mode0/TS0")
+// carried across modes; T lives in HBM.  CalsParams::mttkrp_method == MTTKRP selects one full MTTKRP per mode instead.
 #pragma once
 #include "mttkrp.cuh"
 
