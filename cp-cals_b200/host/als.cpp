@@ -178,7 +178,7 @@ void AlsParams::print() const {
   cout << rule << "\nALS parameters\n" << rule << endl;
   cout << "Tol:             " << tol << endl;
   cout << "Max Iterations:  " << max_iterations << endl;
-  cout << "Mttkrp Method:   " << mttkrp::mttkrp_method_names[mttkrp_method] << " (ignored: B200 kernels)" << endl;
+  cout << "Mttkrp Method:   " << mttkrp::mttkrp_method_names[mttkrp_method] << " (MTTKRP: one contraction per mode; otherwise shared where possible)" << endl;
   cout << "Update Method:   " << update::update_method_names[update_method] << endl;
   cout << "Line Search:     " << (line_search ? "true" : "false") << endl;
   if (line_search) {
