@@ -88,6 +88,16 @@ def test_full_config_cp_cals_properties(pkg, modes, ranks, K):
             prev_err = err
         xn = rep.X_norm
         assert abs(xn - np.linalg.norm(X)) <= 1e-12 * xn
+        # pair nodes (default, csrc/pairnode.cuh) == one full MTTKRP per mode, at full size
+        assert rep.pair_node
+        per_mode = to_ktensors(pkg, ms)
+        rep1 = pkg.cp_cals(X, per_mode, pkg.CalsParams(max_iterations=K, buffer_size=C, force_max_iter=True,
+                                                        mttkrp_method="mttkrp"), engine=eng)
+        assert not rep1.pair_node
+        assert max(abs(a.fit - b.fit) for a, b in zip(kts, per_mode)) <= 1e-10
+        for i in probe:
+            for Fa, Fb in zip(kts[i].factors, per_mode[i].factors):
+                assert rel_err(Fa, Fb) <= RTOL
         for i in probe:
             kt = kts[i]
             # fast error == explicit error, fit consistent
