@@ -531,6 +531,18 @@ def main():
             "leaf_peak_gbs": measured_hbm_peak(),
             "algorithmic_mttkrp_tflops": len(modes) * flops_per_launch * iters / (mt_ms * 1e-3) / 1e12,
         }
+        if args.config == 2 and world == 1:  # DRAM traffic of the pair contraction from its ncu --set full capture
+            try:
+                with open(os.path.join(ROOT, "profiles", "pair_node_full_r01.json")) as f:
+                    for l in json.load(f)["launches"]:
+                        if l["kernel"].startswith("pair_gemm_kernel"):
+                            unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+                            roofline["pair_node"]["pair_contraction_traffic"] = sum(
+                                l[k]["value"] * unit.get(l[k]["unit"], 1.0)
+                                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                            break
+            except Exception:
+                pass
 
     # ---------------- e2e: public API, host buffers in pinned memory ----------------
     def pinned_copy(a):
