@@ -16,7 +16,10 @@
 
 namespace calsb200 {
 
-constexpr int I8_SL = 8;        // slices per operand == levels
+#ifndef CALS_I8_SLICES
+#define CALS_I8_SLICES 8
+#endif
+constexpr int I8_SL = CALS_I8_SLICES; // slices per operand == levels (8: below FP64 rounding; 7: 1.6e-14, 28 products)
 constexpr int I8_TM = 128;      // rows per tile (TMEM lanes)
 constexpr int I8_TN = 64;       // columns per tile: I8_SL * I8_TN = 512 TMEM columns
 constexpr int I8_KP = 256;      // bytes of K per operand row: two 128-byte swizzle atoms
@@ -319,7 +322,7 @@ pair_gemm_i8_kernel(const __grid_constant__ I8Maps maps, const I8Geom g, const i
 #pragma unroll
           for (int u = 0; u < HN; u++)
             if (col0 + u < C)
-              __stcs(&T[(size_t)(col0 + u) * g.ldT + row], acc[u] * ((dbg & 16) ? sa : sa * g.sb[col0 + u]));
+              __stcs(&T[(size_t)(col0 + u) * g.ldT + row], acc[u] * ((dbg & 16) ? sa : sa * __ldg(g.sb + col0 + u)));
         }
       }
     }
