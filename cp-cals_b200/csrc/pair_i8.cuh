@@ -75,6 +75,20 @@ __device__ __forceinline__ void i8_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// Waiting warps that are not on the critical path poll with a back-off, so that their try_wait traffic does not compete
+// with the tensor pipe's shared-memory operand reads.
+__device__ __forceinline__ void i8_wait_backoff(uint64_t *bar, uint32_t parity, unsigned ns) {
+  uint32_t done;
+  const uint32_t addr = smem_u32(bar);
+  for (;;) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done)
+      break;
+    __nanosleep(ns);
+  }
+}
+
 // One lane of a converged warp.  The MMA / TMA issue loops are executed by the WHOLE warp (all values warp-uniform) and
 // only the instruction itself is predicated on the elected lane: inside a divergent `if (lane == 0)` the compiler has to
 // wrap every descriptor move to the uniform registers in a waterfall loop (~100 clocks per MMA, measured).
@@ -185,7 +199,10 @@ pair_gemm_i8_kernel(const __grid_constant__ I8Maps maps, const I8Geom g, const i
         for (int i = 0; i < I8_SL; i++) {
           if ((dbg & 2) && (t != t_lo || i >= I8_A_STAGES))
             continue; // measurement aid: X slice tiles are loaded once and reused
-          mbar_wait(&a_empty[st], aph);
+          if (dbg & 32)
+            i8_wait_backoff(&a_empty[st], aph, 100);
+          else
+            mbar_wait(&a_empty[st], aph);
           if (i8_elect_one()) {
             mbar_expect_tx(&a_full[st], I8_A_BYTES);
             const int row = (int)(i * g.R_pad + (long long)mt * I8_TM);
@@ -282,7 +299,10 @@ pair_gemm_i8_kernel(const __grid_constant__ I8Maps maps, const I8Geom g, const i
         acc[u] = 0.0;
 #pragma unroll
       for (int s = 0; s < I8_SL; s++) {
-        mbar_wait(&l_full[s], lfph);
+        if (dbg & 32)
+          i8_wait_backoff(&l_full[s], lfph, 100);
+        else
+          mbar_wait(&l_full[s], lfph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const double w = __longlong_as_double((long long)(1023 - 7 * (s + 2)) << 52); // 2^(-7(s+2))
         int32_t v0[16], v1[16];
