@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "cals_b200_comm_alloc", "cals_b200_comm_local_block", "cals_b200_comm_connect", "cals_b200_set_tensor_slab",
     "cals_b200_set_tensor_norm", "cals_b200_comm_disconnect", "cals_b200_set_model_active_set",
     "cals_b200_fetch_model_active_set", "cals_b200_set_line_search", "cals_b200_line_search_counts",
-    "cals_b200_enqueue_models", "cals_b200_set_pair_node",
+    "cals_b200_enqueue_models", "cals_b200_set_pair_node", "cals_b200_khatri_rao",
 ]
 
 
@@ -110,6 +110,7 @@ def lib():
     L.cals_b200_comm_disconnect.argtypes = [vp]
     L.cals_b200_enqueue_models.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(vp), C.POINTER(i), C.POINTER(C.c_int64)]
     L.cals_b200_set_line_search.argtypes = [vp, i, i, i, dbl]
+    L.cals_b200_khatri_rao.argtypes = [vp, vp, u64, vp, u64, u64, vp]
     L.cals_b200_line_search_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.cals_b200_set_model_active_set.argtypes = [vp, i, C.POINTER(vp)]
     L.cals_b200_fetch_model_active_set.argtypes = [vp, i, C.POINTER(vp)]
@@ -456,6 +457,16 @@ class Engine:
         ms = C.c_double()
         self._ck(self._L.cals_b200_mttkrp(self._ctx, mode, cols, ptrs, G.ctypes.data, variant, repeats, C.byref(ms)))
         return G, ms.value
+
+    def khatri_rao(self, A: np.ndarray, B: np.ndarray) -> np.ndarray:
+        """mttkrp::khatri_rao (reference src/utils/mttkrp.cpp:78-103): K[ib + IB*ia, c] = A[ia, c] * B[ib, c]."""
+        Af, Bf = np.asfortranarray(A, dtype=np.float64), np.asfortranarray(B, dtype=np.float64)
+        if Af.ndim != 2 or Bf.ndim != 2 or Af.shape[1] != Bf.shape[1]:
+            raise ValueError("khatri_rao needs two matrices with the same number of columns")
+        K = np.empty((Af.shape[0] * Bf.shape[0], Af.shape[1]), order="F")
+        self._ck(self._L.cals_b200_khatri_rao(self._ctx, Af.ctypes.data, Af.shape[0], Bf.ctypes.data, Bf.shape[0],
+                                              Af.shape[1], K.ctypes.data))
+        return K
 
     def iteration_cols(self) -> np.ndarray:
         """CalsReport::cols of the last run: active multi-factor columns per global iteration."""

@@ -1771,6 +1771,12 @@ int cals_b200_enqueue_model(cals_b200_ctx *c, uint64_t rank, const double *const
   const Geom &geo = c->geo;
   if (jk_mode >= geo.n_modes)
     return fail(c, "jk_mode %d out of range", jk_mode);
+  // Leave-one-out norms exist for mode 0 only, as in the reference (utils::calculate_jackknifing_norms,
+  // src/utils/utils.cpp:103-152; generate_jk_ktensors flags mode 0, :40-51): another mode would index that table with
+  // a fibre of the wrong mode and silently give a wrong error / fit / eviction decision.
+  if (jk_mode > 0)
+    return fail(c, "jackknife models must leave out a sample of mode 0 (jk_mode %d): the leave-one-out norms "
+                   "||X||_jk are kept for mode 0 only, as in the reference", jk_mode);
   if (jk_mode >= 0 && (jk_fiber < 0 || jk_fiber >= geo.dims[jk_mode]))
     return fail(c, "jk_fiber %lld out of range", (long long)jk_fiber);
   if (jk_mode >= 0 && c->slice_mode >= 0)
@@ -2015,6 +2021,45 @@ int cals_b200_mttkrp(cals_b200_ctx *c, int mode, uint64_t cols, const double *co
     }
   }
   free_all(b.allocs);
+  return rc;
+}
+
+int cals_b200_khatri_rao(cals_b200_ctx *c, const double *host_A, uint64_t rows_A, const double *host_B, uint64_t rows_B,
+                         uint64_t cols, double *host_K) {
+  if (!c || !host_A || !host_B || !host_K)
+    return fail(c, "null argument");
+  if (rows_A < 1 || rows_B < 1 || cols < 1 || rows_A > (1u << 30) || rows_B > (1u << 30) || cols > 65535 ||
+      rows_A * rows_B > (1ull << 40))
+    return fail(c, "khatri_rao: extents out of range (%llu x %llu rows, %llu columns)", (unsigned long long)rows_A,
+                (unsigned long long)rows_B, (unsigned long long)cols);
+  cudaSetDevice(c->device);
+  const size_t nA = (size_t)rows_A * cols, nB = (size_t)rows_B * cols, nK = (size_t)rows_A * rows_B * cols;
+  double *dA = nullptr, *dB = nullptr, *dK = nullptr;
+  int rc = 0;
+  cudaError_t e = cudaMalloc((void **)&dA, nA * 8);
+  if (e == cudaSuccess)
+    e = cudaMalloc((void **)&dB, nB * 8);
+  if (e == cudaSuccess)
+    e = cudaMalloc((void **)&dK, nK * 8);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(dA, host_A, nA * 8, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(dB, host_B, nB * 8, cudaMemcpyHostToDevice, c->stream);
+  if (e == cudaSuccess) {
+    const unsigned long long rows = rows_A * rows_B;
+    dim3 grid((unsigned)((rows + 1023) / 1024), (unsigned)cols);
+    khatri_rao_kernel<<<grid, 256, 0, c->stream>>>(dA, dB, (int)rows_A, (int)rows_B, dK);
+    e = cudaMemcpyAsync(host_K, dK, nK * 8, cudaMemcpyDeviceToHost, c->stream);
+  }
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(c->stream);
+  if (e == cudaSuccess)
+    e = cudaGetLastError();
+  if (e != cudaSuccess)
+    rc = fail(c, "khatri_rao failed: %s", cudaGetErrorString(e));
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dK);
   return rc;
 }
 

@@ -7,10 +7,34 @@
 //                            ||X||          Tensor::norm                       reference include/tensor.h:196
 //                            ||X||_jk[i]    utils::calculate_jackknifing_norms reference src/utils/utils.cpp:103-152
 //                          follow.
+//   khatri_rao_kernel      K = A (.) B, the explicit two-matrix Khatri-Rao product of the reference's API
+//                            (mttkrp::khatri_rao, reference src/utils/mttkrp.cpp:78-103; its CUDA twin
+//                            src/utils/khatri_rao.cu:10-55).  The iteration path never materialises K (mttkrp.cuh); this
+//                            kernel only serves callers of that API function.
 #pragma once
 #include <cuda_runtime.h>
 
 namespace calsb200 {
+
+// K[ib + IB * ia, c] = A[ia, c] * B[ib, c]   (B's row index fastest, reference src/utils/mttkrp.cpp:88-96).
+// grid = (ceil(IA*IB / 1024), cols): one column per blockIdx.y, 4 consecutive rows of K per thread -> coalesced stores;
+// the column of A is read through L1/L2 (IA values per column), B's column likewise.
+__global__ void __launch_bounds__(256)
+khatri_rao_kernel(const double *__restrict__ A, const double *__restrict__ B, int IA, int IB, double *__restrict__ K) {
+  const long long c = blockIdx.y;
+  const long long rows = (long long)IA * IB;
+  const double *a = A + c * IA, *b = B + c * IB;
+  double *k = K + c * rows;
+  const long long r0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const long long r = r0 + u;
+    if (r < rows) {
+      const int ia = (int)(r / IB), ib = (int)(r - (long long)ia * IB);
+      k[r] = a[ia] * b[ib];
+    }
+  }
+}
 
 __global__ void pad_copy_kernel(const double *__restrict__ X, double *__restrict__ Xp, int I0, int ld0,
                                 long long rest) {

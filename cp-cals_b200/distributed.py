@@ -150,7 +150,7 @@ def cp_cals_sliced(slab: np.ndarray, modes: Sequence[int], slice_mode: int, kten
     torch.distributed is used only to pass the CUDA IPC handles and the slab norms around."""
     import torch
     import torch.distributed as dist
-    from . import CalsReport, Engine, _check_params
+    from . import LS_METHODS, CalsReport, Engine, _check_params
     _check_params(params)
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -182,19 +182,30 @@ def cp_cals_sliced(slab: np.ndarray, modes: Sequence[int], slice_mode: int, kten
         else:
             total = float(sq.item())
         eng.set_tensor_norm(total ** 0.5)
-        eng.configure(buffer_cols, params.max_iterations, params.tol, params.force_max_iter, params.always_evict_first)
-        eng.set_line_search(False)
+        # same option forwarding as cp_cals and as the C++ run_sliced (host/cals.cpp); combinations the sliced engine
+        # does not implement (error-checking line search, line search with NNLS) are refused by the engine itself
+        nnls = params.update_method == "nnls"
+        eng.configure(buffer_cols, params.max_iterations, params.tol, params.force_max_iter, params.always_evict_first,
+                      nnls)
+        eng.set_line_search(params.line_search, LS_METHODS.get(params.line_search_method, 0),
+                            params.line_search_interval, params.line_search_step)
         eng.set_timing(timing)
         eng.set_pair_node(str(params.mttkrp_method).lower() != "mttkrp")
         eng.clear_models()
         for kt in ktensors:
             eng.enqueue(kt.factors, kt.jk_mode, kt.jk_fiber)
+        if nnls:  # warm-start active sets travel with the Ktensor (reference include/ktensor.h:36)
+            for i, kt in enumerate(ktensors):
+                if kt.active_set is not None:
+                    eng.set_active_set(i, kt.active_set)
         if world > 1:
             dist.barrier(group=group)  # every peer's exchange block is mapped before anyone starts to signal
         rep = eng.run()
-        for kt, (fs, lam, st) in zip(ktensors, eng.fetch_all()):
+        for i, (kt, (fs, lam, st)) in enumerate(zip(ktensors, eng.fetch_all())):
             kt.factors, kt.lam = fs, lam
             kt.iters, kt.error, kt.fit, kt.old_fit, kt.chol_info = st.iters, st.error, st.fit, st.old_fit, st.chol_info
+            if nnls:
+                kt.active_set = eng.fetch_active_set(i)
         if world > 1:
             dist.barrier(group=group)  # nobody frees its exchange block while a peer may still read it
         return CalsReport(n_modes=len(modes), modes=tuple(modes), X_norm=rep.x_norm, iter=rep.iter,

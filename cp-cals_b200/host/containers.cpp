@@ -62,6 +62,11 @@ void host_free(double *p) {
     operator delete[](raw, std::align_val_t(64));
 }
 
+uint64_t next_tensor_uid() {
+  static std::atomic<uint64_t> counter{0};
+  return ++counter;
+}
+
 } // namespace detail
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -140,6 +145,7 @@ Tensor &Tensor::operator=(const Tensor &rhs) {
   rank = rhs.rank;
   n_elements = max_n_elements = rhs.n_elements;
   modes = rhs.modes;
+  uid = detail::next_tensor_uid();
   if (rhs.is_view()) {
     data_up.reset();
     data = rhs.data;
@@ -175,11 +181,13 @@ double Tensor::norm() const {
 Tensor &Tensor::fill(const function<double()> &&f) {
   for (dim_t i = 0; i < n_elements; i++)
     data[i] = f();
+  uid = detail::next_tensor_uid(); // new contents: a resident device copy of the old ones is stale
   return *this;
 }
 
 Tensor &Tensor::zero() {
   std::fill(data, data + n_elements, 0.0);
+  uid = detail::next_tensor_uid();
   return *this;
 }
 
@@ -189,6 +197,7 @@ Tensor &Tensor::randomize() {
   std::uniform_real_distribution<double> dist(-1.0, 1.0);
   for (dim_t i = 0; i < n_elements; i++)
     data[i] = dist(gen);
+  uid = detail::next_tensor_uid();
   return *this;
 }
 

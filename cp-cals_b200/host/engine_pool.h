@@ -17,9 +17,11 @@ struct EngineHandle {
   cals_b200_ctx *ctx{nullptr};
   int device{0};
   std::mutex mu; // one caller at a time per device (the reference API is not re-entrant either)
-  // what is resident: address + extents of the caller's tensor at the time of the last upload
+  // what is resident: identity (Tensor::get_uid), address, extents and a sampled content fingerprint of the caller's
+  // tensor at the time of the last upload
   const double *resident_data{nullptr};
   std::vector<dim_t> resident_modes;
+  uint64_t resident_uid{0}, resident_fp{0};
 };
 
 // Throws cals::B200Error when the device or the library is unusable (no CPU fallback).

@@ -167,6 +167,13 @@ int cals_b200_jk_norms(cals_b200_ctx *ctx, double *out);
 int cals_b200_mttkrp(cals_b200_ctx *ctx, int mode, uint64_t cols, const double *const *host_factors, double *host_G,
                      int variant, int repeats, double *ms_out);
 
+/* mttkrp::khatri_rao(A, B, workspace, params) (reference include/utils/mttkrp.h:88-89, src/utils/mttkrp.cpp:78-103; CUDA
+ * twin khatri_rao_cuda, src/utils/khatri_rao.cu:40): K[ib + rows_B * ia, c] = A[ia, c] * B[ib, c] for `cols` columns,
+ * all matrices column-major and dense (ld = rows).  The iteration path never materialises this product; the hook
+ * exists for callers of that API function. */
+int cals_b200_khatri_rao(cals_b200_ctx *ctx, const double *host_A, uint64_t rows_A, const double *host_B,
+                         uint64_t rows_B, uint64_t cols, double *host_K);
+
 /* CalsReport::cols (reference include/cals.h:62, filled at src/cals.cpp:214): the number of active multi-factor
  * columns in every global iteration of the last run.  Writes min(*n_out, capacity) entries; *n_out = iterations
  * logged (the device keeps the first 65536). */

@@ -32,6 +32,7 @@ void host_free(double *p);
 struct HostFree {
   void operator()(double *p) const { host_free(p); }
 };
+uint64_t next_tensor_uid();
 } // namespace detail
 
 // Geometry of the mode-n unfolding as a sequence of equally sized matrix blocks (reference include/tensor.h:38-44).
@@ -50,6 +51,10 @@ class Tensor {
   vector<dim_t> modes;
   unique_ptr<double, detail::HostFree> data_up{};
   double *data{nullptr};
+  // Identity of this object for the engine's "tensor already resident" test (AlsParams::cuda_no_tensor_alloc): a fresh
+  // value for every constructed or copy-assigned Tensor, kept by moves, so that a new Tensor that the allocator happens
+  // to place at the address of a freed one is never mistaken for it.
+  uint64_t uid{detail::next_tensor_uid()};
 
   void allocate(dim_t n);
 
@@ -75,10 +80,15 @@ public:
   [[nodiscard]] double *get_data() const noexcept { return data; }
   [[nodiscard]] int get_rank() const noexcept { return rank; }
   [[nodiscard]] bool is_view() const noexcept { return data_up == nullptr; }
+  [[nodiscard]] uint64_t get_uid() const noexcept { return uid; }
 
-  void set_data(double *new_data) noexcept { data = new_data; }
+  void set_data(double *new_data) noexcept {
+    data = new_data;
+    uid = detail::next_tensor_uid();
+  }
   Tensor &reset_data() noexcept {
     data = data_up.get();
+    uid = detail::next_tensor_uid();
     return *this;
   }
 
@@ -99,7 +109,10 @@ public:
   Tensor &zero();
   Tensor &randomize(); // uniform(-1, 1), std::mt19937 seeded from std::random_device (reference src/tensor.cpp:121-129)
 
-  void copy(const Tensor &ten) noexcept { std::copy(ten.data, ten.data + ten.n_elements, data); }
+  void copy(const Tensor &ten) noexcept {
+    std::copy(ten.data, ten.data + ten.n_elements, data);
+    uid = detail::next_tensor_uid();
+  }
 
   dim_t max_id(vector<bool> &mask) noexcept {
     dim_t best = 0;

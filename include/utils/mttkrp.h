@@ -44,6 +44,13 @@ struct MttkrpParams {
 cals::Matrix &mttkrp(const cals::Tensor &X, cals::Ktensor &u, std::vector<cals::Matrix> &workspace, dim_t mode,
                      cals::mttkrp::MttkrpParams &params);
 
+// K = A (.) B, the explicit Khatri-Rao product of two matrices with the same number of columns:
+// K(ib + B.rows * ia, c) = A(ia, c) * B(ib, c); `workspace` is resized to [A.rows * B.rows x A.cols], filled on the
+// device (C ABI cals_b200_khatri_rao) and returned (reference include/utils/mttkrp.h:88-89, src/utils/mttkrp.cpp:78-103).
+// cp_cals / mttkrp() never call it -- they form the Khatri-Rao rows on the fly (cp-cals_b200/csrc/mttkrp.cuh).
+cals::Matrix &khatri_rao(const cals::Matrix &A, const cals::Matrix &B, cals::Matrix &workspace,
+                         cals::mttkrp::KrpParams &params);
+
 // No lookup tables on this path; returns an empty table so that callers that pre-load one keep working.
 MttkrpLut read_lookup_table(std::vector<dim_t> const &modes, int threads, bool gpu = false,
                             bool suppress_warning = false);

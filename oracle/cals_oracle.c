@@ -8,9 +8,9 @@
  * /root/reference).  The reference's BLAS/LAPACK calls (dgemm, dtrsm, dpotrf, dnrm2, idamax, dscal; external
  * OpenBLAS, un-vendored) are restated by their textbook definitions.
  *
- * Parity pin: tests/test_oracle_vs_reference.py checks this file against the UNMODIFIED reference library
- * (oracle/_ref, built from /root/reference by oracle/build_ref.sh) and against tests/golden/ *.npz, which were
- * produced by that same reference build (oracle/make_golden.py).  The reference itself ships no golden vectors
+ * Parity pin: tests/test_oracle.py checks this file against the UNMODIFIED reference library (oracle/_ref, built
+ * from /root/reference by oracle/build_ref.sh; live comparison where that build exists) and against
+ * tests/golden/ *.npz, which were produced by that same reference build (oracle/make_golden.py).  The reference itself ships no golden vectors
  * (its tests are relational: CALS == ALS, fast error == explicit error).
  */
 #include <math.h>

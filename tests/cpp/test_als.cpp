@@ -2,6 +2,7 @@
 // tensor, every MTTKRP method knob leads to the same result (here: to the same kernels), and the fast error formula
 // equals the explicit ||X - model||.  Needs a B200: run by pytest -m gpu (tests/test_cpp_api.py).
 #include <cmath>
+#include <cstdio>
 #include <random>
 
 #include "gtest/gtest.h"
@@ -138,6 +139,74 @@ TEST(Als, MttkrpHookMatchesDirectEvaluation) {
     EXPECT_LT(worst, 1e-12);
     EXPECT_EQ(mp.flops, 2ull * X.get_n_elements() * 4);
   }
+}
+
+// mttkrp::khatri_rao(A, B, workspace, params): the explicit product of the reference's API (include/utils/mttkrp.h:88).
+TEST(Als, KhatriRaoOfTwoMatrices) {
+  std::mt19937 gen(2);
+  std::uniform_real_distribution<double> dist(-1.0, 1.0);
+  const dim_t IA = 9, IB = 13, C = 5;
+  cals::Matrix A(IA, C), B(IB, C), K(IA * IB, C);
+  A.fill([&] { return dist(gen); });
+  B.fill([&] { return dist(gen); });
+  cals::mttkrp::KrpParams kp;
+  cals::Matrix &out = cals::mttkrp::khatri_rao(A, B, K, kp);
+  EXPECT_EQ(&out, &K);
+  EXPECT_EQ(K.get_rows(), IA * IB);
+  double worst = 0.0;
+  for (dim_t c = 0; c < C; c++)
+    for (dim_t a = 0; a < IA; a++)
+      for (dim_t b = 0; b < IB; b++)
+        worst = std::max(worst, std::fabs(K(b + IB * a, c) - A(a, c) * B(b, c)));
+  EXPECT_EQ(worst, 0.0);
+  EXPECT_EQ(kp.flops, (uint64_t)(IA * IB * C));
+}
+
+// AlsParams::cuda_no_tensor_alloc ("X is already resident") must never make a fit run on stale device data: a Tensor
+// rewritten in place, and a different Tensor object that happens to reuse the address of a freed one, are uploaded
+// again; an untouched Tensor is not (host/cals.cpp upload_tensor).
+TEST(Als, ResidentTensorIsNeverStale) {
+  const std::vector<dim_t> modes{12, 11, 10};
+  std::mt19937 gen(3);
+  std::uniform_real_distribution<double> dist(-1.0, 1.0);
+  Ktensor k0(3, modes);
+  k0.fill([&] { return dist(gen); });
+  auto fit = [&](const Tensor &X, bool flag) {
+    cals::AlsParams p;
+    p.max_iterations = 4;
+    p.force_max_iter = true;
+    p.suppress_lut_warning = true;
+    p.cuda_no_tensor_alloc = flag;
+    Ktensor k(k0);
+    cals::cp_als(X, k, p);
+    return k.get_approximation_error();
+  };
+  Tensor X(modes);
+  X.fill([&] { return dist(gen); });
+  const double e1 = fit(X, false);
+  EXPECT_EQ(fit(X, true), e1); // untouched: the resident copy is used and gives the same answer
+  for (dim_t i = 0; i < X.get_n_elements(); i++) // rewritten in place through operator[] (no uid bump)
+    X[i] = dist(gen);
+  const double e2_flag = fit(X, true);
+  const double e2 = fit(X, false);
+  EXPECT_EQ(e2_flag, e2);
+  EXPECT_NE(e2, e1);
+  double *addr = nullptr;
+  double e3_flag = 0.0, e3 = 0.0;
+  for (int round = 0; round < 2; round++) { // temporaries of the same size: the allocator reuses the block
+    Tensor Y(modes);
+    Y.fill([&] { return dist(gen); });
+    if (round == 0) {
+      addr = Y.get_data();
+      fit(Y, false);
+    } else {
+      e3_flag = fit(Y, true);
+      e3 = fit(Y, false);
+      if (Y.get_data() != addr)
+        std::printf("note: allocator did not reuse the address; the check is still valid\n");
+    }
+  }
+  EXPECT_EQ(e3_flag, e3);
 }
 
 int main(int argc, char **argv) {

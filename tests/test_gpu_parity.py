@@ -50,6 +50,31 @@ def test_norms(engine):
         assert rel_err(engine.jk_norms(), oracle.jk_norms(X)) <= 1e-12
 
 
+def test_khatri_rao_hook(engine):
+    """mttkrp::khatri_rao(A, B) (reference src/utils/mttkrp.cpp:78-103): K[ib + IB*ia, c] = A[ia, c] * B[ib, c]."""
+    rng = np.random.default_rng(12)
+    for IA, IB, C in [(1, 1, 1), (7, 5, 3), (33, 64, 17), (200, 200, 21), (3, 1031, 2)]:
+        A, B = rng.uniform(-1, 1, size=(IA, C)), rng.uniform(-1, 1, size=(IB, C))
+        want = np.einsum("ac,bc->abc", A, B).reshape(IA * IB, C)  # row index = ia * IB + ib
+        got = engine.khatri_rao(A, B)
+        assert got.shape == want.shape and np.array_equal(got, want)  # one multiplication per entry: exact
+
+
+def test_jackknife_flag_on_another_mode_is_refused(pkg):
+    """Leave-one-out norms exist for mode 0 only (reference src/utils/utils.cpp:103-152, :40-51); a flag on another mode
+    would silently use the norm of the wrong slice -- it is rejected at enqueue time."""
+    rng = np.random.default_rng(13)
+    X = rng.uniform(-1, 1, size=(6, 5, 4))
+    ms = caseio.random_models(rng, X.shape, [2])
+    with pkg.Engine(0) as eng:
+        eng.set_tensor(X)
+        eng.configure(2, 3, 1e-7)
+        eng.clear_models()
+        with pytest.raises(pkg.CalsB200Error, match="mode 0"):
+            eng.enqueue(ms[0].factors, 1, 2)
+        assert eng.enqueue(ms[0].factors, 0, 5) == 0
+
+
 GOLDEN_CASES = ["forced_3d_k1", "forced_3d_k2", "forced_3d_k5", "forced_4d_queue", "jackknife_3d", "evict_first_3d"]
 
 

@@ -227,6 +227,44 @@ def test_single_slab_run_equals_plain_run(pkg):
             assert np.array_equal(a.lam, b.lam) and a.error == b.error
 
 
+@pytest.mark.gpu
+def test_single_slab_run_forwards_update_method_and_line_search(pkg):
+    """cp_cals_sliced honours CalsParams::update_method and line_search* exactly like cp_cals and the C++ run_sliced
+    (it used to run an unconstrained ALS without line search, silently)."""
+    import importlib
+    import caseio
+    from helpers import to_ktensors
+    d = importlib.import_module("cp_cals_b200.distributed")
+    rng = np.random.default_rng(78)
+    modes = (18, 14, 22)
+    gen = [rng.uniform(0, 1, size=(i, 3)) for i in modes]
+    X = caseio.ktensor_to_tensor(gen, np.ones(3)) + 0.02 * rng.uniform(0, 1, size=modes)
+    ms = caseio.random_models(rng, modes, [3, 2, 5])
+    for m in ms:
+        m.factors = [np.abs(F) for F in m.factors]
+    cases = [dict(update_method="nnls"),
+             dict(line_search=True, line_search_interval=3, line_search_method="no-error-checking")]
+    for extra in cases:
+        p = pkg.CalsParams(max_iterations=7, buffer_size=10, force_max_iter=True, **extra)
+        plain = to_ktensors(pkg, ms)
+        rep0 = pkg.cp_cals(X, plain, p)
+        sliced = to_ktensors(pkg, ms)
+        rep = d.cp_cals_sliced(X, modes, 2, sliced, p)
+        assert rep.iter == rep0.iter
+        for a, b in zip(plain, sliced):
+            assert all(np.array_equal(x, y) for x, y in zip(a.factors, b.factors)), extra
+            assert np.array_equal(a.lam, b.lam) and a.error == b.error
+        if "update_method" in extra:
+            assert all((F >= 0).all() for k in sliced for F in k.factors)
+            unconstrained = to_ktensors(pkg, ms)
+            pkg.cp_cals(X, unconstrained, pkg.CalsParams(max_iterations=7, buffer_size=10, force_max_iter=True))
+            assert any(not np.array_equal(a.factors[0], b.factors[0]) for a, b in zip(sliced, unconstrained))
+    # the combination the sliced engine does not implement is refused, not emulated
+    with pytest.raises(pkg.CalsB200Error):
+        d.cp_cals_sliced(X, modes, 2, to_ktensors(pkg, ms),
+                         pkg.CalsParams(max_iterations=3, buffer_size=10, update_method="nnls", line_search=True))
+
+
 def _sliced_worker(rank, world, port, out_dir):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     sys.path.insert(0, os.path.join(ROOT, "oracle"))

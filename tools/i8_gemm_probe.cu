@@ -1,4 +1,4 @@
-// Stand-alone check of csrc/pair_i8.cuh at the size of BASELINE config 2: T = X_(0)^T A_0 with R = 40000 rows, K = 200,
+// Stand-alone check of tools/pair_i8_probe.cuh (a probe, not product code) at the size of BASELINE config 2: T = X_(0)^T A_0 with R = 40000 rows, K = 200,
 // C = 2100 columns, sliced on the device, contracted on the INT8 tensor cores, compared with long-double dot products
 // on sampled entries, timed with CUDA events.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Icp-cals_b200/csrc -o tools/i8_gemm_probe tools/i8_gemm_probe.cu -lcuda
@@ -7,7 +7,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "pair_i8.cuh"
+#include "pair_i8_probe.cuh"
 
 using namespace calsb200;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("{\"error\": \"%s at line %d\"}\n", cudaGetErrorString(e_), __LINE__); exit(1);} } while (0)

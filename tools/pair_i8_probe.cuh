@@ -5,8 +5,11 @@
 // ("level"), and the epilogue recombines  T = 2^(ea + eb) * sum_s 2^(-7(s+2)) D_s  in FP64.
 // With SL = 8 the neglected products are below 2^-56 of |x|max |a|max per term, i.e. below FP64 rounding of the sum.
 //
-// Same role as pair_gemm_kernel (pairnode.cuh; reference: the contraction inside mttkrp::mttkrp, src/utils/mttkrp.cpp);
-// selected with CALS_B200_PAIR_I8=1 for contracted extents up to 256.  Feasibility numbers: profiles/i8_probe_r01.json.
+// PROBE ONLY -- not part of the product library: nothing under cp-cals_b200/ includes this file, and libcals_b200.so
+// computes every contraction on the FP64 tensor cores (DMMA).  It computes what pair_gemm_kernel (csrc/pairnode.cuh)
+// computes and is driven by tools/i8_gemm_probe.cu alone.  Round-1 measurement (profiles/i8_gemm_probe_r01.json): 7 slices
+// 0.86 ms against the DMMA kernel's 0.97 ms at BASELINE config 2, before the per-mode re-slicing of the factors -- below
+// the 1.15x step gain that would justify a weaker accuracy contract, so the path was not wired into the engine.
 #pragma once
 #include <cstdint>
 #include <cuda.h>
