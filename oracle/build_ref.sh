@@ -10,6 +10,14 @@
 #
 # Outputs:  oracle/_ref/libcals_ref.so   the reference library
 #           oracle/_ref/cals_ref         oracle/ref_tool.cpp linked against it
+#           oracle/_ref/libcals_ref_rel{3,4}.so + cals_ref_rel{3,4}
+#                                        the same sources with the reference's RELEASE flags (CMake Release adds
+#                                        -O3 -DNDEBUG; CMakeLists.txt:210-211 adds -ffast-math -march=native) for the
+#                                        timed CPU arm of bench.py only.  -march=native cannot travel (this container
+#                                        builds, another host of the pool runs), so two portable levels are built and
+#                                        caseio.ref_binary(release=True) picks x86-64-v4 when the running CPU has
+#                                        AVX-512, x86-64-v3 otherwise.  Golden vectors and parity tests keep the
+#                                        no-fast-math build above.
 # No reference source is copied into the repo.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -38,4 +46,19 @@ g++ -shared -fopenmp -o "$OUT/libcals_ref.so" "${OBJS[@]}" "$BLAS" -Wl,-rpath,"$
 g++ "${CXXFLAGS[@]}" "$HERE/ref_tool.cpp" -o "$OUT/cals_ref" -L"$OUT" -lcals_ref "$BLAS" \
     -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$SP"
 rm -f "${OBJS[@]}"
-echo "build_ref: built $OUT/cals_ref against $BLAS"
+for lvl in 3 4; do
+  RFLAGS=(-std=c++17 -O3 -ffast-math -march=x86-64-v$lvl -fopenmp -fPIC -w -DCALS_OPENBLAS=1 -DWITH_TIME=1 -DNDEBUG
+          "-DSOURCE_DIR=\"$REF\"" -I"$HERE/ref_shim" -I"$REF/include" -I"$REF/include/utils" -I"$REF/extern")
+  OBJS=()
+  for s in "${SRCS[@]}"; do
+    o="$OUT/rel${lvl}_$(echo "$s" | tr '/' '_').o"
+    g++ "${RFLAGS[@]}" -c "$REF/$s" -o "$o" &
+    OBJS+=("$o")
+  done
+  wait
+  g++ -shared -fopenmp -o "$OUT/libcals_ref_rel$lvl.so" "${OBJS[@]}" "$BLAS" -Wl,-rpath,"$SP"
+  g++ "${RFLAGS[@]}" "$HERE/ref_tool.cpp" -o "$OUT/cals_ref_rel$lvl" -L"$OUT" -lcals_ref_rel$lvl "$BLAS" \
+      -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$SP"
+  rm -f "${OBJS[@]}"
+done
+echo "build_ref: built $OUT/cals_ref (+ cals_ref_rel3, cals_ref_rel4 with the reference's Release flags) against $BLAS"

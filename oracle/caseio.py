@@ -74,6 +74,23 @@ def ref_available() -> bool:
     return os.path.exists(REF_BIN)
 
 
+def ref_binary(release: bool = False) -> str:
+    """Path of the reference harness.  release=True: the build with the reference's Release flags
+    (-O3 -ffast-math, oracle/build_ref.sh) at the highest x86-64 level the running CPU supports -- for TIMING only
+    (bench.py's CPU arm); parity work uses the plain build."""
+    if release:
+        try:
+            with open("/proc/cpuinfo") as f:
+                flags = f.read()
+        except OSError:
+            flags = ""
+        for lvl, need in ((4, "avx512f"), (3, "avx2")):
+            path = os.path.join(HERE, "_ref", "cals_ref_rel%d" % lvl)
+            if need in flags and os.path.exists(path):
+                return path
+    return REF_BIN
+
+
 def write_case(path, X, models, *, max_iter, tol=1e-7, buffer_size=None, force_max_iter=False,
                always_evict_first=False, threads=1, algo=ALGO_CALS, mttkrp_method=METHOD_AUTO, nnls=False,
                line_search=False, ls_method=0, ls_interval=5, ls_step=0.0):
@@ -123,11 +140,17 @@ def read_result(path, n_modes) -> RefResult:
     return RefResult(models, seconds, wall, it, nk, cs, xn)
 
 
-def run_reference(X, models, *, env_extra=None, timeout=1800, **kw) -> RefResult:
+def run_reference(X, models, *, env_extra=None, timeout=1800, release=False, **kw) -> RefResult:
     """Run the unmodified reference (oracle/_ref/cals_ref) on a case and return its results."""
     if not ref_available():
         raise FileNotFoundError("oracle/_ref/cals_ref not built; run oracle/build_ref.sh")
+    binary = ref_binary(release)
     env = dict(os.environ)
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference sets its own thread counts from the case file
+    # (set_threads), but the BLAS pool is sized from the environment when the library loads: make both say `threads`.
+    th = str(int(kw.get("threads", 1)))
+    env["OMP_NUM_THREADS"] = th
+    env["OPENBLAS_NUM_THREADS"] = th
     # The wheel OpenBLAS is a pthreads build nested under the reference's OpenMP loops: keep the waiters passive
     # (SURVEY.md section 8c "known threading hazard"); results are unaffected.
     env.setdefault("OMP_WAIT_POLICY", "passive")
@@ -136,7 +159,7 @@ def run_reference(X, models, *, env_extra=None, timeout=1800, **kw) -> RefResult
     with tempfile.TemporaryDirectory() as td:
         pin, pout = os.path.join(td, "case.in"), os.path.join(td, "case.out")
         write_case(pin, X, models, **kw)
-        p = subprocess.run([REF_BIN, pin, pout], env=env, capture_output=True, text=True, timeout=timeout)
+        p = subprocess.run([binary, pin, pout], env=env, capture_output=True, text=True, timeout=timeout)
         if p.returncode != 0:
             raise RuntimeError("cals_ref failed: %s\n%s" % (p.returncode, p.stderr[-2000:]))
         res = read_result(pout, X.ndim)

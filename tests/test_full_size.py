@@ -8,14 +8,92 @@ properties instead of element-wise comparison of everything.
     the error never increases from one ALS iteration to the next.
   * jackknife (config 3 shape): a flagged model == ALS on the row-deleted tensor (reference tests/cals/test_cals.cpp:181-297).
 """
+import os
+
 import numpy as np
 import pytest
 
 import caseio
 import oracle
-from helpers import RTOL, rel_err, to_ktensors
+from helpers import RTOL, assert_models_close, rel_err, to_ktensors
 
 pytestmark = pytest.mark.gpu
+
+needs_ref = pytest.mark.skipif(not caseio.ref_available(), reason="oracle/_ref/cals_ref (the unmodified reference, built "
+                               "by oracle/build_ref.sh where /root/reference exists) did not travel to this box")
+
+
+def _driver_inputs(modes, ranks, seed):
+    """Inputs as the reference driver makes them (src/examples/driver.cpp:133-153): X uniform(-1,1), models uniform(-1,1)
+    then Ktensor::normalize()."""
+    rng = np.random.default_rng(seed)
+    X = np.asfortranarray(rng.uniform(-1.0, 1.0, size=modes))
+    return X, caseio.random_models(rng, modes, ranks)
+
+
+def _against_reference(pkg, eng, X, ms, K, what, methods=("auto", "mttkrp")):
+    """north_star's correctness clause at full size: from identical initial factors, after a fixed iteration count, every
+    factor matrix, lambda and fit within 1e-9 of the UNMODIFIED reference's CPU cals::cp_cals (pattern:
+    reference tests/cals/test_cals.cpp:13-86).  Both mttkrp_method settings of this path (pair nodes / one MTTKRP per
+    mode) are held to it."""
+    C = sum(m.rank for m in ms)
+    ref = caseio.run_reference(X, ms, max_iter=K, force_max_iter=True, buffer_size=C, threads=os.cpu_count() or 1)
+    assert ref.iters == K and ref.n_ktensors == len(ms)
+    worst = 0.0
+    for method in methods:
+        kts = to_ktensors(pkg, ms)
+        rep = pkg.cp_cals(X, kts, pkg.CalsParams(max_iterations=K, buffer_size=C, force_max_iter=True,
+                                                 mttkrp_method=method), engine=eng)
+        assert (rep.iter, rep.n_ktensors, rep.ktensor_comp_sum) == (ref.iters, ref.n_ktensors, ref.comp_sum)
+        assert rep.pair_node == (method != "mttkrp" and X.ndim in (3, 4))
+        assert abs(rep.X_norm - ref.x_norm) <= 1e-12 * ref.x_norm
+        assert_models_close(kts, ref.models, ref.x_norm, rtol=RTOL, what="%s K=%d %s:" % (what, K, method))
+        for g, r in zip(kts, ref.models):  # fit = 1 - |err| / ||X|| (include/ktensor.h:178-183), per model
+            assert abs(g.fit - (1.0 - abs(r.error) / ref.x_norm)) <= RTOL
+            assert abs(g.fit_diff - r.fit_diff) <= RTOL
+            worst = max(worst, max(rel_err(a, b) for a, b in zip(g.factors, r.factors)))
+    return worst
+
+
+@needs_ref
+@pytest.mark.parametrize("K", [1, 2, 3])
+def test_config2_all_models_vs_reference(pkg, K):
+    """BASELINE config 2 in full -- 200^3 tensor, all 200 models (ranks 1..20 x10), buffer 2100 -- after K = 1, 2, 3
+    forced ALS iterations (i.e. per iteration) against the unmodified reference."""
+    X, ms = _driver_inputs((200, 200, 200), [r for r in range(1, 21) for _ in range(10)], 2002)
+    with pkg.Engine(0) as eng:
+        worst = _against_reference(pkg, eng, X, ms, K, "config 2")
+    print("config 2, K=%d: worst factor rel err vs reference %.2e" % (K, worst))
+
+
+@needs_ref
+@pytest.mark.parametrize("K", [1, 2])
+def test_config4_all_models_vs_reference(pkg, K):
+    """BASELINE config 4 in full -- 80^4 tensor, 150 models (ranks 1..30 x5), buffer 2325.  The reference materialises
+    its 9.5 GB Khatri-Rao workspace for this (src/cals.cpp:78-88); the GPU box has the memory."""
+    X, ms = _driver_inputs((80, 80, 80, 80), [r for r in range(1, 31) for _ in range(5)], 4004)
+    with pkg.Engine(0) as eng:
+        worst = _against_reference(pkg, eng, X, ms, K, "config 4")
+    print("config 4, K=%d: worst factor rel err vs reference %.2e" % (K, worst))
+
+
+@needs_ref
+def test_config3_all_submodels_vs_reference(pkg):
+    """BASELINE config 3 shape (299 x 301 x 41): all 299 leave-one-out sub-models of one rank-5 base model, K = 3, against
+    the reference's jackknife branches (src/cals.cpp:198-200 norms, :250-251 zeroed fibre, :291-293 error)."""
+    rng = np.random.default_rng(3003)
+    modes, R, K = (299, 301, 41), 5, 3
+    gen = [rng.uniform(0, 1, size=(i, R)) for i in modes]
+    X = np.asfortranarray(caseio.ktensor_to_tensor(gen, np.ones(R)) + 0.01 * rng.standard_normal(modes))
+    base = caseio.random_models(rng, modes, [R])[0]
+    ms = []
+    for i in range(modes[0]):
+        fs = [F.copy() for F in base.factors]
+        fs[0][i, :] = 0.0  # Ktensor::set_jk_fiber(0.0) as jk_cp_cals leaves its inputs (src/utils/utils.cpp:40-51)
+        ms.append(caseio.Model(factors=fs, lam=base.lam.copy(), jk_mode=0, jk_fiber=i))
+    with pkg.Engine(0) as eng:
+        worst = _against_reference(pkg, eng, X, ms, K, "config 3 jackknife")
+    print("config 3, %d sub-models, K=%d: worst factor rel err vs reference %.2e" % (len(ms), K, worst))
 
 
 def _subset_check(pkg, eng, X, fs, n_check, rng, tol=1e-11):
