@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda.h>
@@ -118,6 +119,7 @@ struct cals_b200_ctx {
   SchedState *d_st = nullptr;
   int *d_live = nullptr, *d_live_tmp = nullptr, *d_gather = nullptr, *d_evict = nullptr;
   double *d_gram = nullptr, *d_lambda = nullptr;
+  long long *d_update_prof = nullptr; // CALS_B200_UPDATE_PROF (never freed: tuning aid)
   // line search (CalsParams::line_search*, reference include/cals.h:153-156)
   int ls_enabled = 0, ls_method = 0, ls_interval = 5;
   double ls_step = 0.0;
@@ -147,6 +149,8 @@ struct cals_b200_ctx {
   std::vector<int> run_sig; // (dims, buffer_cols, ranks): allocations are reused while this does not change
   double *norm_partial = nullptr;
   size_t norm_partial_cap = 0;
+  double *x_stage = nullptr; // dense upload target of tensors whose fastest extent is odd (padded into Xp by a kernel)
+  size_t x_stage_cap = 0;
 
   // slab-mode exchange over peer memory (comm.cuh)
   int comm_rank = 0, comm_world = 1;
@@ -218,6 +222,28 @@ void free_all(std::vector<void *> &v) {
   for (void *p : v)
     cudaFree(p);
   v.clear();
+}
+
+// Host-side copies between the callers' matrices and the pinned staging blocks: with hundreds of models (BASELINE
+// config 3: 1196 models, 37 MB each way) one thread copying column by column costs more than the PCIe transfer itself,
+// so large batches are split over a few threads (contiguous ranges of models; every model's bytes are disjoint).
+template <typename F> void parallel_models(size_t n_models, size_t bytes, F &&fn) {
+  unsigned hw = std::thread::hardware_concurrency();
+  const size_t want = std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)8, bytes / ((size_t)4 << 20), n_models});
+  if (want <= 1) {
+    fn((size_t)0, n_models);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t per = (n_models + want - 1) / want;
+  for (size_t t = 1; t < want; t++) {
+    const size_t lo = std::min(n_models, t * per), hi = std::min(n_models, (t + 1) * per);
+    if (lo < hi)
+      th.emplace_back([&fn, lo, hi] { fn(lo, hi); });
+  }
+  fn((size_t)0, std::min(n_models, per));
+  for (auto &t : th)
+    t.join();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -648,7 +674,7 @@ int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchan
   if (skip_reduce) // the update kernel sums the partial tiles itself
     return 0;
   const int cols = C_override > 0 ? C_override : b.cols;
-  dim3 rg((cols + 31) / 32, (b.mg[n].In + 31) / 32);
+  dim3 rg((cols + 31) / 32, (b.mg[n].In + REDUCE_ROWS - 1) / REDUCE_ROWS);
   mttkrp_reduce_kernel<8 * WM, TILE_N><<<rg, 256, 0, c->stream>>>(
       b.mg[n], c->d_st, b.plans.plan[n], b.ws, out, G, C_override, exchange ? exchange_data(c) : nullptr,
       (unsigned long long)c->xcap, c->seq_base, c->geo.n_modes);
@@ -807,14 +833,24 @@ int install_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const d
   c->have_tensor = false;
 
   double *dense = nullptr;
-  bool dense_owned = false;
   if (src_on_device) {
     dense = const_cast<double *>(src);
   } else if (c->ldX0 == I0) {
     // the upload lands directly in Xp
   } else {
-    CU_TRY(c, cudaMalloc((void **)&dense, (size_t)nX * 8));
-    dense_owned = true;
+    // odd fastest extent: the dense upload goes to a staging block that is kept from call to call (no allocation, no
+    // synchronisation on the upload path) and is padded into Xp by a kernel
+    if (c->x_stage_cap < (size_t)nX) {
+      if (c->x_stage) {
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->x_stage);
+      }
+      c->x_stage = nullptr;
+      c->x_stage_cap = 0;
+      CU_TRY(c, cudaMalloc((void **)&c->x_stage, (size_t)nX * 8));
+      c->x_stage_cap = (size_t)nX;
+    }
+    dense = c->x_stage;
     CU_TRY(c, cudaMemcpyAsync(dense, src, (size_t)nX * 8, cudaMemcpyHostToDevice, c->stream));
   }
   if (!c->Xp)
@@ -863,10 +899,6 @@ int install_tensor(cals_b200_ctx *c, int n_modes, const uint64_t *modes, const d
     CU_TRY(c, cudaMemcpyAsync(c->h_norm, c->d_norm, 8, cudaMemcpyDeviceToHost, c->stream));
     c->x_norm_valid = false;
     c->x_norm_override = false;
-  }
-  if (dense_owned) {
-    CU_TRY(c, cudaStreamSynchronize(c->stream));
-    cudaFree(dense);
   }
   CU_TRY(c, cudaGetLastError());
   c->have_tensor = true;
@@ -1061,6 +1093,16 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   const bool tree = b.tree && c->variant == CALS_B200_MTTKRP_DMMA;
   auto node_of = [&](int n) { return tree ? b.node_of[n] : -1; };
 
+  // tuning aid: CALS_B200_UPDATE_PROF=1 prints the phase times of the update kernel's slowest CTA per mode after the run
+  static const bool update_prof = getenv("CALS_B200_UPDATE_PROF") != nullptr;
+  if (update_prof && !c->d_update_prof) {
+    CU_TRY(c, cudaMalloc((void **)&c->d_update_prof, (size_t)CALS_MAX_MODES * 8192 * 16 * sizeof(long long)));
+    CU_TRY(c, cudaMemset(c->d_update_prof, 0, (size_t)CALS_MAX_MODES * 8192 * 16 * sizeof(long long)));
+  }
+  if (max_live > 8192 && c->d_update_prof) {
+    cudaFree(c->d_update_prof);
+    c->d_update_prof = nullptr;
+  }
   // shared memory of the update kernel
   UpdateParams up[CALS_MAX_MODES];
   size_t up_smem[CALS_MAX_MODES];
@@ -1071,25 +1113,31 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     u.rows = geo.dims[n];
     u.ld = geo.ldF[n];
     const int R = c->max_rank;
-    size_t fixed = ((size_t)2 * R * R + 2 * R + 32) * 8;
+    size_t fixed = ((size_t)2 * R * R + 4 * R + 64 + 2 * STAT_SEGS * R) * 8; // H, Gramian / block inverses, column
+    // statistics, 1 / diag(L), diag(H), reduction scratch, statistics candidates
     const size_t budget = 200 * 1024;
     u.nnls = (c->flags & CALS_B200_NNLS) ? 1 : 0;
     u.nnls_warps = 0;
     if (u.nnls) { // per working warp: 5R + R*R doubles and 2R + 1 ints of scratch
       const size_t per_warp = ((size_t)5 * R + (size_t)R * R + (size_t)(2 * R + 2) / 2 + 1) * 8;
       int nw = UPDATE_THREADS / 32;
-      while (nw > 1 && fixed + nw * per_warp + (size_t)33 * R * 8 > budget)
+      while (nw > 1 && fixed + nw * per_warp + (size_t)36 * R * 8 > budget)
         nw >>= 1;
       u.nnls_warps = nw;
       fixed += nw * per_warp;
     }
-    if (fixed + (size_t)33 * R * 8 > budget)
+    if (fixed + (size_t)36 * R * 8 > budget)
       return fail(c, "rank %d too large for the shared-memory update kernel", R);
     int cr = round_up_int(u.rows, 32);
-    while (fixed + (size_t)(cr + 1) * R * 8 > budget)
+    // behind the staged chunk: tile lookup tables of the fused reduction, (R + chunk rows) ints
+    auto tables = [&](int rows_) { return (size_t)((R + rows_ + 1) / 2 + 1) * 8; };
+    while (fixed + (size_t)(cr + 4) * R * 8 + tables(cr) > budget)
       cr -= 32;
+    if (cr < 32)
+      return fail(c, "rank %d too large for the shared-memory update kernel", R);
     u.chunk_rows = cr;
-    u.chunk_pitch = cr + 1;
+    u.chunk_pitch = cr + 4; // = 4 mod 16 doubles: the DMMA fragment loads of the update kernel are bank-conflict free
+    u.table_off = (int)((fixed + (size_t)(cr + 4) * R * 8) / 8);
     u.max_rank = R;
     u.G = b.G;
     u.F[0] = b.fac.buf[0][n];
@@ -1110,7 +1158,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     u.rows_before = 0;
     for (int k = 0; k < n; k++)
       u.rows_before += geo.dims[k];
-    up_smem[n] = fixed + (size_t)(cr + 1) * R * 8;
+    u.prof = c->d_update_prof ? c->d_update_prof + (size_t)n * max_live * 16 : nullptr;
+    up_smem[n] = fixed + (size_t)(cr + 4) * R * 8 + tables(cr);
   }
   {
     size_t mx = 0;
@@ -1345,6 +1394,26 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   CU_TRY(c, cudaGetLastError());
   auto t1 = std::chrono::steady_clock::now();
 
+  if (update_prof && c->d_update_prof) {
+    std::vector<long long> h((size_t)N * max_live * 16);
+    cudaMemcpy(h.data(), c->d_update_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    for (int n = 0; n < N; n++) {
+      int worst = 0;
+      long long worst_t = -1;
+      for (int b2 = 0; b2 < max_live; b2++) {
+        const long long *r = &h[((size_t)n * max_live + b2) * 16];
+        if (r[9] - r[0] > worst_t) {
+          worst_t = r[9] - r[0];
+          worst = b2;
+        }
+      }
+      const long long *r = &h[((size_t)n * max_live + worst) * 16];
+      fprintf(stderr, "[update prof] mode %d slowest CTA %d rank %lld: H %lld | chol %lld (stage+sync %lld) | solve %lld | "
+                      "stats %lld | lambda %lld | scale %lld | gram %lld | publish %lld | tail %lld | total %lld cycles\n",
+              n, worst, r[15], r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[7] - r[6],
+              r[8] - r[7], r[9] - r[8], r[10] ? r[10] - r[9] : 0, (r[10] ? r[10] : r[9]) - r[0]);
+    }
+  }
   // scalars back
   CU_TRY(c, cudaMemcpy(&st, c->d_st, sizeof st, cudaMemcpyDeviceToHost));
   c->last_global_iter = st.global_iter;
@@ -1525,6 +1594,8 @@ int cals_b200_destroy(cals_b200_ctx *c) {
     cudaFreeHost(c->h_desc_pin);
   if (c->norm_partial)
     cudaFree(c->norm_partial);
+  if (c->x_stage)
+    cudaFree(c->x_stage);
   for (auto e : c->ev_pool)
     cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
@@ -1760,12 +1831,9 @@ int cals_b200_clear_models(cals_b200_ctx *c) {
   return 0;
 }
 
-int cals_b200_enqueue_model(cals_b200_ctx *c, uint64_t rank, const double *const *host_factors, int jk_mode,
-                            int64_t jk_fiber, int *model_id) {
-  if (!c || !host_factors)
-    return fail(c, "null argument");
-  if (!c->have_tensor)
-    return fail(c, "set the tensor before enqueueing models");
+// validation shared by the two enqueue entry points; on success fills `hm` (home_col = first free staging column)
+static int check_model(cals_b200_ctx *c, uint64_t rank, const double *const *host_factors, int jk_mode, int64_t jk_fiber,
+                       int home_col, HostModel *hm) {
   if (rank < 1 || rank > 4096)
     return fail(c, "rank %llu out of range", (unsigned long long)rank);
   const Geom &geo = c->geo;
@@ -1781,29 +1849,47 @@ int cals_b200_enqueue_model(cals_b200_ctx *c, uint64_t rank, const double *const
     return fail(c, "jk_fiber %lld out of range", (long long)jk_fiber);
   if (jk_mode >= 0 && c->slice_mode >= 0)
     return fail(c, "jackknife models are not supported on a sliced tensor (shard the sub-models instead)");
-  HostModel hm;
-  hm.rank = (int)rank;
-  hm.jk_mode = jk_mode < 0 ? -1 : jk_mode;
-  hm.jk_fiber = jk_mode < 0 ? 0 : (int)jk_fiber;
-  hm.home_col = c->queued_cols;
   for (int n = 0; n < geo.n_modes; n++)
     if (!host_factors[n])
       return fail(c, "factor %d is null", n);
+  hm->rank = (int)rank;
+  hm->jk_mode = jk_mode < 0 ? -1 : jk_mode;
+  hm->jk_fiber = jk_mode < 0 ? 0 : (int)jk_fiber;
+  hm->home_col = home_col;
+  return 0;
+}
+
+// copy one model's factors into the pinned input staging at its home columns (pitch ldF, pad row zeroed)
+static void stage_model(cals_b200_ctx *c, const HostModel &hm, const double *const *host_factors) {
+  const Geom &geo = c->geo;
   for (int n = 0; n < geo.n_modes; n++) {
     const int rows = geo.dims[n], ld = geo.ldF[n];
-    if (reserve_input_staging(c, n, (size_t)c->queued_cols + rank, true))
-      return 1;
-    double *dst = c->h_in[n] + (size_t)ld * c->queued_cols;
+    double *dst = c->h_in[n] + (size_t)ld * hm.home_col;
     if (ld == rows)
-      memcpy(dst, host_factors[n], (size_t)rows * rank * 8);
+      memcpy(dst, host_factors[n], (size_t)rows * hm.rank * 8);
     else
-      for (uint64_t j = 0; j < rank; j++) {
-        memcpy(dst + j * ld, host_factors[n] + j * rows, (size_t)rows * 8);
-        dst[j * ld + rows] = 0.0;
+      for (int j = 0; j < hm.rank; j++) {
+        memcpy(dst + (size_t)j * ld, host_factors[n] + (size_t)j * rows, (size_t)rows * 8);
+        dst[(size_t)j * ld + rows] = 0.0;
       }
   }
+}
+
+int cals_b200_enqueue_model(cals_b200_ctx *c, uint64_t rank, const double *const *host_factors, int jk_mode,
+                            int64_t jk_fiber, int *model_id) {
+  if (!c || !host_factors)
+    return fail(c, "null argument");
+  if (!c->have_tensor)
+    return fail(c, "set the tensor before enqueueing models");
+  HostModel hm;
+  if (check_model(c, rank, host_factors, jk_mode, jk_fiber, c->queued_cols, &hm))
+    return 1;
+  for (int n = 0; n < c->geo.n_modes; n++)
+    if (reserve_input_staging(c, n, (size_t)c->queued_cols + rank, true))
+      return 1;
+  stage_model(c, hm, host_factors);
   c->queued_cols += (int)rank;
-  c->hmodels.push_back(std::move(hm));
+  c->hmodels.push_back(hm);
   c->uploaded = false;
   if (model_id)
     *model_id = (int)c->hmodels.size() - 1;
@@ -1817,16 +1903,28 @@ int cals_b200_enqueue_models(cals_b200_ctx *c, uint64_t n_models, const uint64_t
   if (!c->have_tensor)
     return fail(c, "set the tensor before enqueueing models");
   const int N = c->geo.n_modes;
-  size_t cols = (size_t)c->queued_cols;
-  for (uint64_t m = 0; m < n_models; m++)
-    cols += ranks[m];
+  // validate everything first: a rejected model leaves the queue as it was
+  std::vector<HostModel> fresh((size_t)n_models);
+  int col = c->queued_cols;
+  size_t rows_sum = 0;
+  for (int n = 0; n < N; n++)
+    rows_sum += (size_t)c->geo.dims[n];
+  for (uint64_t m = 0; m < n_models; m++) {
+    if (check_model(c, ranks[m], host_factors + m * N, jk_modes ? jk_modes[m] : -1, jk_fibers ? jk_fibers[m] : 0, col,
+                    &fresh[m]))
+      return 1;
+    col += (int)ranks[m];
+  }
   for (int n = 0; n < N; n++) // one pinned allocation per mode for the whole queue
-    if (reserve_input_staging(c, n, cols, false))
+    if (reserve_input_staging(c, n, (size_t)col, false))
       return 1;
-  for (uint64_t m = 0; m < n_models; m++)
-    if (cals_b200_enqueue_model(c, ranks[m], host_factors + m * N, jk_modes ? jk_modes[m] : -1,
-                                jk_fibers ? jk_fibers[m] : 0, nullptr))
-      return 1;
+  parallel_models((size_t)n_models, rows_sum * (size_t)(col - c->queued_cols) * 8, [&](size_t lo, size_t hi) {
+    for (size_t m = lo; m < hi; m++)
+      stage_model(c, fresh[m], host_factors + m * N);
+  });
+  c->queued_cols = col;
+  c->hmodels.insert(c->hmodels.end(), fresh.begin(), fresh.end());
+  c->uploaded = false;
   return 0;
 }
 
@@ -1881,9 +1979,14 @@ int cals_b200_fetch_all(cals_b200_ctx *c, double *const *factors_out, double *co
   if (download_results(c))
     return 1;
   const int N = c->geo.n_modes;
-  for (int m = 0; m < (int)c->hdesc.size(); m++)
-    copy_model_out(c, m, factors_out ? factors_out + (size_t)m * N : nullptr, lambda_out ? lambda_out[m] : nullptr,
-                   stats ? stats + m : nullptr);
+  size_t rows_sum = 0;
+  for (int n = 0; n < N; n++)
+    rows_sum += (size_t)c->geo.dims[n];
+  parallel_models(c->hdesc.size(), factors_out ? rows_sum * (size_t)c->total_cols * 8 : 0, [&](size_t lo, size_t hi) {
+    for (size_t m = lo; m < hi; m++)
+      copy_model_out(c, (int)m, factors_out ? factors_out + m * N : nullptr, lambda_out ? lambda_out[m] : nullptr,
+                     stats ? stats + m : nullptr);
+  });
   return 0;
 }
 

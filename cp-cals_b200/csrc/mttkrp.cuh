@@ -203,12 +203,15 @@ struct PairCost {
     return nf * stage_full + (k - nf) * stage_tail;
   }
 };
-__host__ __device__ inline PairCost plan_pair_cost(const PlanShape &sh, int nm, int nn) {
+// g_last: valid n8 groups in the pair's last octet (8 = full).  Warps g_last..7 skip that octet's slot; a sub-partition
+// runs warps q and q + 4, so the busiest one (q = 0) issues nn + (g_last > 4 ? nn : nn - 1) slots per row group.
+__host__ __device__ inline PairCost plan_pair_cost(const PlanShape &sh, int nm, int nn, int g_last = 8) {
   PairCost pc;
   const int P_tiles = plan_p_tiles(sh);
   const int tail_groups = (sh.Ip - (P_tiles - 1) * KT + 7) / 8;
-  pc.stage_full = (long long)(KT / 8) * 2 * nm * nn + PLAN_STAGE_COST;
-  pc.stage_tail = (long long)tail_groups * 2 * nm * nn + PLAN_STAGE_COST;
+  const long long per_group = (long long)nm * (nn + (g_last > 4 ? nn : nn - 1));
+  pc.stage_full = (long long)(KT / 8) * per_group + PLAN_STAGE_COST;
+  pc.stage_tail = (long long)tail_groups * per_group + PLAN_STAGE_COST;
   pc.full_stages = (long long)(P_tiles - 1) * sh.S * sh.Iq;
   return pc;
 }
@@ -223,17 +226,19 @@ __host__ __device__ inline void mttkrp_make_plan(int *plan, const PlanShape &sh,
   const int pairs = m_tiles * n_tiles;
   const long long total = (long long)pairs * Tp;
   const int G_eff = (int)(total < (long long)G ? total : (long long)G);
+  const int g_tail = (C - 64 * (NO - 1) + 7) / 8; // valid n8 groups of the very last octet (1..8)
   int *cta_lo = plan + PLAN_HDR, *cta_seg0 = plan + PLAN_HDR + (G + 1), *pair_seg0 = plan + PLAN_HDR + (G + 1) + G;
   // total weight
   long long W = 0;
   for (int pi = 0; pi < pairs; pi++) {
     const int nt = pi / m_tiles, mt = pi - nt * m_tiles;
-    W += plan_pair_cost(sh, plan_wm(mt, In8, m_tiles), plan_nn(nt, NO, n_tiles)).prefix(Tp);
+    W += plan_pair_cost(sh, plan_wm(mt, In8, m_tiles), plan_nn(nt, NO, n_tiles), nt == n_tiles - 1 ? g_tail : 8)
+             .prefix(Tp);
   }
 
   int pi = 0, k = 0, seg = 0;
   long long cw = 0, done = 0;
-  PairCost pc = plan_pair_cost(sh, plan_wm(0, In8, m_tiles), plan_nn(0, NO, n_tiles));
+  PairCost pc = plan_pair_cost(sh, plan_wm(0, In8, m_tiles), plan_nn(0, NO, n_tiles), n_tiles == 1 ? g_tail : 8);
   for (int b = 0; b < G_eff; b++) {
     cta_lo[b] = (int)done;
     cta_seg0[b] = seg;
@@ -278,7 +283,7 @@ __host__ __device__ inline void mttkrp_make_plan(int *plan, const PlanShape &sh,
         k = 0;
         if (pi < pairs) {
           const int nt = pi / m_tiles, mt = pi - nt * m_tiles;
-          pc = plan_pair_cost(sh, plan_wm(mt, In8, m_tiles), plan_nn(nt, NO, n_tiles));
+          pc = plan_pair_cost(sh, plan_wm(mt, In8, m_tiles), plan_nn(nt, NO, n_tiles), nt == n_tiles - 1 ? g_tail : 8);
         }
       } else
         break;
@@ -360,6 +365,8 @@ __device__ __forceinline__ void mma_stage_n(double (&acc)[WM][WN][2], const doub
                                             const double (&wv)[WN], int ngroups, int r, int s, int nn) {
   static_assert(WN == 4, "dispatch below assumes 4 column groups per warp");
   switch (nn) {
+  case 0: // this warp's only column group of the tile starts beyond C
+    break;
   case 1:
     mma_stage_nm<WM, WN, NM, 1, SCALE>(acc, Xt, Bw, wv, ngroups, r, s);
     break;
@@ -570,7 +577,13 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
     const int n_here = min(min(OC - o0, Iq - iq0), hi - u); // same split of the range into chunk pieces as the producer
     // number of valid m8 row groups / n8 column groups of this pair (CTA-uniform)
     const int nm = plan_wm(mt, pv.In8, m_tiles);
-    const int nn = plan_nn(nt, pv.NO, n_tiles);
+    int nn = plan_nn(nt, pv.NO, n_tiles);
+    // Only the last octet of the last n-tile can reach beyond C.  A warp whose n8 group of that octet starts at or beyond
+    // C would multiply TMA zero-fill for a whole octet slot: it runs one slot less instead (per-warp, the barriers do not
+    // depend on it).  C = 263 then costs 9 instead of 10 slots per SM sub-partition -- what the per-GPU shards of a
+    // strong-scaled model set need; full octets are untouched.
+    if (64 * (plan_oct_start(nt, pv.NO, n_tiles) + nn - 1) + 8 * warp >= C)
+      nn--;
     if (pair != prev_pair) {
       if (prev_pair >= 0)
         flush();
@@ -644,47 +657,62 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
 
 // ------------------------------------------------------------------------------------------------------------------
 // Sum the partial tiles of every (m,n) pair in segment order and write G (In x C, column-major, ld = ldG).
-// One CTA per 32x32 patch of G; reads are coalesced along columns of the row-major tiles, writes along rows of G.
+// One CTA per 8 x 32 (rows x columns) patch of G, one output element per thread: reads are coalesced along columns of
+// the row-major tiles, four running sums keep four loads in flight per thread (a narrow shard has tens of segments per
+// pair and few output elements, so the pass is latency-bound), writes go through shared memory so that a warp stores
+// 8-row runs of G's columns.
 //
 // Slab mode: xbuf != nullptr -> the sum is this device's PARTIAL result and goes to the exchange buffer
 // xbuf + ((seq_base + global_iter * n_modes + mode + 1) & 1) * xcap, from where comm.cuh's exchange kernel of every
 // rank collects it.
+constexpr int REDUCE_ROWS = 8;
 template <int M_TILE, int N_TILE>
-__global__ void mttkrp_reduce_kernel(const MttkrpGeom g, const SchedState *__restrict__ st,
-                                     const int *__restrict__ plan, const double *__restrict__ ws,
-                                     double *__restrict__ G, int grid_ctas, int C_override, double *xbuf,
-                                     unsigned long long xcap, unsigned long long seq_base, int n_modes) {
+__global__ void __launch_bounds__(256)
+mttkrp_reduce_kernel(const MttkrpGeom g, const SchedState *__restrict__ st, const int *__restrict__ plan,
+                     const double *__restrict__ ws, double *__restrict__ G, int grid_ctas, int C_override, double *xbuf,
+                     unsigned long long xcap, unsigned long long seq_base, int n_modes) {
   const int C = C_override > 0 ? C_override : st->C;
   if (xbuf != nullptr) {
     const unsigned long long seq = seq_base + st->global_iter * (unsigned long long)n_modes + g.mode + 1;
     G = xbuf + (seq & 1ull) * xcap;
   }
-  const int c0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int c0 = blockIdx.x * 32, m0 = blockIdx.y * REDUCE_ROWS;
   if (c0 >= C)
     return;
-  __shared__ double t[32][33];
+  __shared__ double t[REDUCE_ROWS][33];
   const PlanView pv = plan_view(plan, grid_ctas);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 256 threads: ty in 0..7
-  for (int rr = ty; rr < 32; rr += 8) {
-    const int m = m0 + rr, c = c0 + tx;
+  {
+    const int m = m0 + ty, c = c0 + tx;
     double sum = 0.0;
     if (m < g.In && c < C) {
       const int mt = plan_tile_of(m >> 3, pv.In8, pv.m_tiles);
       const int nt = plan_tile_of(c >> 6, pv.NO, pv.n_tiles);
       const int pair = nt * pv.m_tiles + mt;
       const int s0 = pv.pair_seg0[pair], s1 = pv.pair_seg0[pair + 1];
-      const double *p = ws + (size_t)s0 * (M_TILE * N_TILE) + (m - 8 * plan_m8_start(mt, pv.In8, pv.m_tiles)) * N_TILE +
+      constexpr size_t TE = (size_t)M_TILE * N_TILE;
+      const double *p = ws + (size_t)s0 * TE + (m - 8 * plan_m8_start(mt, pv.In8, pv.m_tiles)) * N_TILE +
                         (c - 64 * plan_oct_start(nt, pv.NO, pv.n_tiles));
-      for (int k = s0; k < s1; k++, p += (size_t)(M_TILE * N_TILE))
-        sum += *p;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int k = s0;
+      for (; k + 4 <= s1; k += 4, p += 4 * TE) {
+        a0 += p[0];
+        a1 += p[TE];
+        a2 += p[2 * TE];
+        a3 += p[3 * TE];
+      }
+      for (; k < s1; k++, p += TE)
+        a0 += *p;
+      sum = (a0 + a1) + (a2 + a3);
     }
-    t[rr][tx] = sum;
+    t[ty][tx] = sum;
   }
   __syncthreads();
-  for (int cc = ty; cc < 32; cc += 8) {
-    const int m = m0 + tx, c = c0 + cc;
+  { // thread -> (column = threadIdx / 8, row = threadIdx % 8)
+    const int rr = threadIdx.x & (REDUCE_ROWS - 1), cc = threadIdx.x / REDUCE_ROWS;
+    const int m = m0 + rr, c = c0 + cc;
     if (m < g.In && c < C)
-      G[(size_t)c * g.ldG + m + g.g_row_off] = t[tx][cc];
+      G[(size_t)c * g.ldG + m + g.g_row_off] = t[rr][cc];
   }
 }
 

@@ -115,7 +115,9 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
     const int nt = (int)(t / m_tiles), mt = (int)(t - (long long)nt * m_tiles);
     const int m0 = mt * M_TILE, c0 = nt * N_TILE;
     const int nm = min(WM, (g.R - m0 + 7) >> 3);
-    const int nn = min(WN, (C - c0 + 63) >> 6);
+    int nn = min(WN, (C - c0 + 63) >> 6);
+    if (c0 + 64 * (nn - 1) + 8 * warp >= C) // this warp's n8 group of the last octet starts beyond C (see mttkrp.cuh)
+      nn--;
 #pragma unroll
     for (int i = 0; i < WM; i++)
 #pragma unroll
@@ -168,6 +170,14 @@ __device__ __forceinline__ double *leaf_output(double *G, const LeafExchange &x,
   return x.xbuf + (seq & 1ull) * x.xcap;
 }
 
+constexpr int LEAF_DEPTH = 16; // independent loads of T in flight per thread
+// Scheduling fence: the values must all be in registers here, so every load above has been issued before anything
+// below runs (the hardware issues in order; an FMA waiting for its operand would hold up the loads behind it).
+__device__ __forceinline__ void all_loaded(double (&v)[LEAF_DEPTH]) {
+  asm volatile("" ::"d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "d"(v[4]), "d"(v[5]), "d"(v[6]), "d"(v[7]), "d"(v[8]),
+               "d"(v[9]), "d"(v[10]), "d"(v[11]), "d"(v[12]), "d"(v[13]), "d"(v[14]), "d"(v[15]));
+}
+
 // G_fast[i1, c] = sum_{i2} T[i1 + E1*i2, c] * A_slow[i2, c].  One CTA per column and 256-row chunk of i1; thread = row.
 __global__ void __launch_bounds__(256)
 pair_leaf_slow_kernel(const PairGeom g, const SchedState *__restrict__ st, const FactorPtrs fac,
@@ -188,13 +198,17 @@ pair_leaf_slow_kernel(const PairGeom g, const SchedState *__restrict__ st, const
   const double *t = T + (size_t)c * g.ldT + i1;
   double sum = 0.0;
   int k = 0;
-  for (; k + 8 <= g.E2; k += 8) {
-    double v[8];
+  // LEAF_DEPTH loads are issued before the first one is consumed (all_loaded keeps the compiler from interleaving the
+  // FMAs with the loads, which it otherwise does at 4 loads in flight): with one CTA per column, a grid of a few hundred
+  // columns -- the per-GPU shard of a strong-scaled run -- streams T at (bytes in flight per CTA) / latency.
+  for (; k + LEAF_DEPTH <= g.E2; k += LEAF_DEPTH) {
+    double v[LEAF_DEPTH];
 #pragma unroll
-    for (int u = 0; u < 8; u++)
+    for (int u = 0; u < LEAF_DEPTH; u++)
       v[u] = __ldcs(t + (size_t)(k + u) * g.E1);
+    all_loaded(v);
 #pragma unroll
-    for (int u = 0; u < 8; u++)
+    for (int u = 0; u < LEAF_DEPTH; u++)
       sum += v[u] * wcol[k + u];
   }
   for (; k < g.E2; k++)
@@ -205,6 +219,7 @@ pair_leaf_slow_kernel(const PairGeom g, const SchedState *__restrict__ st, const
 // G_slow[i2, c] = sum_{i1} T[i1 + E1*i2, c] * A_fast[i1, c].  One CTA per column; a warp takes LEAF_ROWS values of i2 at a
 // time (independent loads in flight), lanes run over i1.
 constexpr int LEAF_ROWS = 4;
+static_assert(4 * LEAF_ROWS == LEAF_DEPTH, "the fast leaf batches four lane-strides of LEAF_ROWS rows");
 __global__ void __launch_bounds__(256)
 pair_leaf_fast_kernel(const PairGeom g, const SchedState *__restrict__ st, const FactorPtrs fac,
                       const double *__restrict__ T, double *__restrict__ G, const LeafExchange x) {
@@ -229,7 +244,24 @@ pair_leaf_fast_kernel(const PairGeom g, const SchedState *__restrict__ st, const
       t[u] = tc + (size_t)min(b2 + u, g.E2 - 1) * g.E1; // rows beyond E2 re-read the last row; their sums are dropped
       sum[u] = 0.0;
     }
-    for (int i1 = lane; i1 < g.E1; i1 += 32) {
+    int i1 = lane;
+    for (; i1 + 96 < g.E1; i1 += 128) { // four lane-strides of i1 x LEAF_ROWS rows = 16 loads in flight per thread
+      double v[LEAF_DEPTH];
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int u = 0; u < LEAF_ROWS; u++)
+          v[q * LEAF_ROWS + u] = __ldcs(t[u] + i1 + 32 * q);
+      all_loaded(v);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const double w = wcol[i1 + 32 * q];
+#pragma unroll
+        for (int u = 0; u < LEAF_ROWS; u++)
+          sum[u] += v[q * LEAF_ROWS + u] * w;
+      }
+    }
+    for (; i1 < g.E1; i1 += 32) {
       const double w = wcol[i1];
       double v[LEAF_ROWS];
 #pragma unroll

@@ -55,7 +55,14 @@ struct UpdateParams {
   int nnls_warps;           // warps of the CTA that work on rows (each owns a scratch block in shared memory)
   int rows_before;          // sum of the extents of the modes below this one (offset into a model's active sets)
   unsigned char *act_pool;  // per model: for every mode an I_n x R block, row-major, 1 = constrained to zero
+  int table_off;            // doubles from the start of shared memory to the tile lookup tables of the fused reduction
+  long long *prof;          // tuning aid (CALS_B200_UPDATE_PROF=1): 16 clock64() stamps per CTA, nullptr otherwise
 };
+#define CALS_PROF(slot)                                                                                                \
+  do {                                                                                                                 \
+    if (p.prof != nullptr && threadIdx.x == 0)                                                                         \
+      p.prof[(size_t)blockIdx.x * 16 + (slot)] = clock64();                                                            \
+  } while (0)
 
 __device__ __forceinline__ double block_sum(double v, double *scratch) {
   // scratch: >= 32 doubles of shared memory
@@ -317,6 +324,211 @@ __device__ int nnls_row(const double *H, int R, double tol, double *Srow, int pi
   return trouble;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Cholesky by ONE warp, in shared memory, while the other warps of the CTA stage the MTTKRP result.  Everything in this
+// kernel is written as compact loops on purpose: it runs once per (model, mode), so a CTA executes every instruction
+// only a few times and straight-line code runs at instruction-fetch speed (a fully unrolled register-resident
+// factorisation was measured at 50 k cycles for R = 20; these loops take a fraction of that).
+//
+// H = L L^T, left-looking: for column j every lane owns one row i >= j and forms
+//   s_i = H[i][j] - sum_{k<j} L[i][k] L[j][k]      (two running sums, loads only -- no store -> load chains)
+// the diagonal s_j comes from lane 0 by shuffle, one reciprocal square root per column, L[i][j] = s_i * rinv.
+// inv[j] = 1 / L[j][j].  The strict upper triangle of Hs keeps H.  Returns 1 when a pivot is not positive (dpotrf's
+// info > 0; the reference only logs it and carries on, src/utils/update.cpp:183-185).
+__device__ __forceinline__ int cholesky_warp(double *Hs, double *inv, int R, int lane) {
+  int fail = 0;
+#pragma unroll 1
+  for (int j = 0; j < R; j++) {
+    double rinv = 0.0;
+#pragma unroll 1
+    for (int i0 = j; i0 < R; i0 += 32) {
+      const int i = i0 + lane;
+      double a0 = 0.0, a1 = 0.0;
+      if (i < R) {
+        a0 = Hs[i + j * R];
+        const double *li = Hs + i, *lj = Hs + j;
+        int k = 0;
+#pragma unroll 2
+        for (; k + 2 <= j; k += 2) {
+          a0 -= li[k * R] * lj[k * R];
+          a1 -= li[(k + 1) * R] * lj[(k + 1) * R];
+        }
+        if (k < j)
+          a0 -= li[k * R] * lj[k * R];
+      }
+      const double si = a0 + a1;
+      if (i0 == j) { // the pass that holds the diagonal (lane 0)
+        const double d = __shfl_sync(0xffffffffu, si, 0);
+        if (!(d > 0.0))
+          fail = 1;
+        rinv = rsqrt(d);
+        if (lane == 0)
+          inv[j] = rinv;
+      }
+      if (i < R)
+        Hs[i + j * R] = si * rinv; // the diagonal becomes d * rsqrt(d) = sqrt(d)
+    }
+    __syncwarp();
+  }
+  return fail;
+}
+
+// Inverses of the 8 x 8 diagonal blocks of L, D_b = (L_bb)^-1 (lower triangular), written to the same positions of Di
+// (ld = R).  Lane (blk, c) owns column c of block blk, four blocks per pass; the depth is 7 steps whatever the rank.
+//   D[c][c] = inv[c],   D[i][c] = -inv[i] * sum_{k=c}^{i-1} L[i][k] D[k][c]
+__device__ __forceinline__ void diag_block_inverses_warp(const double *L, const double *inv, double *Di, int R, int lane) {
+  const int NB = (R + 7) >> 3;
+#pragma unroll 1
+  for (int b0 = 0; b0 < NB; b0 += 4) {
+    const int b = b0 + (lane >> 3), c = 8 * b + (lane & 7);
+    if (b < NB && c < R) {
+      double *x = Di + (size_t)c * R;
+      x[c] = inv[c];
+      const int i_end = min(8 * b + 8, R);
+#pragma unroll 1
+      for (int i = c + 1; i < i_end; i++) {
+        double acc = 0.0;
+#pragma unroll 1
+        for (int k = c; k < i; k++)
+          acc += L[i + k * R] * x[k];
+        x[i] = -acc * inv[i];
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// F = G H^-1 = (G L^-T) L^-1 for the rows staged in S (column-major, pitch = 4 mod 16 doubles so that the A fragments
+// are bank-conflict free), in place, as a blocked triangular solve on the FP64 tensor cores (mma.sync m8n8k4): with
+// 8-column blocks,
+//   forward   Y_b = (G_b - sum_{a<b} Y_a L_ba^T) D_b^T          b = 0 .. NB-1
+//   backward  X_b = (Y_b - sum_{a>b} X_a L_ab  ) D_b            b = NB-1 .. 0
+// Per-row substitution (thread per row) moves 16 bytes of shared memory per FMA and is bound by that pipe (measured
+// 18.7 k cycles for 200 x 20); a DMMA moves 2.  Only the 8 x 8 diagonal blocks are inverted, so every product has the
+// forward error of an 8 x 8 substitution.  Warp w owns the m8 row groups w, w + nw, ..; four of them are worked on at a
+// time (independent accumulators, one B fragment for all four).
+constexpr int SOLVE_MB = 4;
+__device__ __forceinline__ void solve_rows_dmma(double *S, int pitch, int nr, const double *L, const double *Di, int R,
+                                                int warp, int nw, int lane) {
+  const int r = lane >> 2, s = lane & 3;
+  const int MG = (nr + 7) >> 3, NB = (R + 7) >> 3;
+#pragma unroll 1
+  for (int mg0 = warp; mg0 < MG; mg0 += SOLVE_MB * nw) {
+    double *Srow[SOLVE_MB];
+    bool ok[SOLVE_MB];
+#pragma unroll
+    for (int g = 0; g < SOLVE_MB; g++) {
+      const int row = 8 * (mg0 + g * nw) + r;
+      ok[g] = (mg0 + g * nw) < MG && row < nr;
+      Srow[g] = S + (ok[g] ? row : 0);
+    }
+#pragma unroll 1
+    for (int dir = 0; dir < 2; dir++) { // 0: forward over L^T, 1: backward over L
+#pragma unroll 1
+      for (int bb = 0; bb < NB; bb++) {
+        const int b = dir == 0 ? bb : NB - 1 - bb;
+        double c0[SOLVE_MB], c1[SOLVE_MB];
+#pragma unroll
+        for (int g = 0; g < SOLVE_MB; g++)
+          c0[g] = c1[g] = 0.0;
+        // blocks already solved: a < b (forward), a > b (backward)
+        const int a_lo = dir == 0 ? 0 : b + 1, a_hi = dir == 0 ? b : NB;
+        const int nb = 8 * b + r; // this lane's column of the B fragment
+#pragma unroll 1
+        for (int k0 = 8 * a_lo; k0 < 8 * a_hi; k0 += 4) {
+          const int k = k0 + s;
+          // forward: B[k][n] = L[8b+n][k];  backward: B[k][n] = L[k][8b+n]
+          const double bf = (k < R && nb < R) ? (dir == 0 ? L[nb + k * R] : L[k + nb * R]) : 0.0;
+#pragma unroll
+          for (int g = 0; g < SOLVE_MB; g++)
+            dmma_m8n8k4(c0[g], c1[g], (ok[g] && k < R) ? Srow[g][k * pitch] : 0.0, bf);
+        }
+        // T = (G_b or Y_b) - C, written back in place (accumulator layout: row r, columns 2s, 2s + 1)
+        const int col = 8 * b + 2 * s;
+#pragma unroll
+        for (int g = 0; g < SOLVE_MB; g++)
+          if (ok[g]) {
+            if (col < R)
+              Srow[g][col * pitch] -= c0[g];
+            if (col + 1 < R)
+              Srow[g][(col + 1) * pitch] -= c1[g];
+          }
+        __syncwarp();
+        // times the inverse of the diagonal block: forward B[k][n] = D[n][k] (k <= n), backward B[k][n] = D[k][n] (k >= n)
+#pragma unroll
+        for (int g = 0; g < SOLVE_MB; g++)
+          c0[g] = c1[g] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+          const int kl = 4 * kk + s, k = 8 * b + kl;
+          double bf = 0.0;
+          if (k < R && nb < R) {
+            if (dir == 0 && kl <= r)
+              bf = Di[nb + k * R];
+            if (dir == 1 && kl >= r)
+              bf = Di[k + nb * R];
+          }
+#pragma unroll
+          for (int g = 0; g < SOLVE_MB; g++)
+            dmma_m8n8k4(c0[g], c1[g], (ok[g] && k < R) ? Srow[g][k * pitch] : 0.0, bf);
+        }
+        __syncwarp(); // every lane has read T before it is overwritten
+#pragma unroll
+        for (int g = 0; g < SOLVE_MB; g++)
+          if (ok[g]) {
+            if (col < R)
+              Srow[g][col * pitch] = c0[g];
+            if (col + 1 < R)
+              Srow[g][(col + 1) * pitch] = c1[g];
+          }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// Gs += F^T F for the rows staged in S, on the FP64 tensor cores: the 8 x 8 tiles of the lower block triangle
+// (ti >= tj) are dealt to the warps; a tile's k loop runs over the rows with two accumulator pairs.  The scalar version
+// (thread per entry) reads two shared-memory operands per FMA and is bound by that pipe (8.6 k cycles for 200 x 20).
+__device__ __forceinline__ void gram_dmma(const double *S, int pitch, int nr, double *Gs, int R, int warp, int nw,
+                                          int lane) {
+  const int r = lane >> 2, s = lane & 3, NT = (R + 7) >> 3;
+  const int n_tiles = NT * (NT + 1) / 2;
+#pragma unroll 1
+  for (int t = warp; t < n_tiles; t += nw) {
+    int ti = 0;
+    while ((ti + 1) * (ti + 2) / 2 <= t)
+      ti++;
+    const int tj = t - ti * (ti + 1) / 2;
+    const int ia = 8 * ti + r, jb = 8 * tj + r;
+    const bool oka = ia < R, okb = jb < R;
+    const double *pa = S + (size_t)(oka ? ia : 0) * pitch, *pb = S + (size_t)(okb ? jb : 0) * pitch;
+    double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+    int k0 = 0;
+#pragma unroll 2
+    for (; k0 + 8 <= nr; k0 += 8) {
+      const int k = k0 + s;
+      dmma_m8n8k4(c0, c1, oka ? pa[k] : 0.0, okb ? pb[k] : 0.0);
+      dmma_m8n8k4(d0, d1, oka ? pa[k + 4] : 0.0, okb ? pb[k + 4] : 0.0);
+    }
+#pragma unroll 1
+    for (; k0 < nr; k0 += 4) {
+      const int k = k0 + s;
+      const bool okk = k < nr;
+      dmma_m8n8k4(c0, c1, (oka && okk) ? pa[k] : 0.0, (okb && okk) ? pb[k] : 0.0);
+    }
+    const int gi = 8 * ti + r, gj = 8 * tj + 2 * s;
+    if (gi < R) {
+      if (gj < R)
+        Gs[gi + gj * R] += c0 + d0;
+      if (gj + 1 < R)
+        Gs[gi + (gj + 1) * R] += c1 + d1;
+    }
+  }
+}
+
+constexpr int STAT_SEGS = 8; // row segments per column in the column statistics
+
 template <bool NNLS>
 __global__ void __launch_bounds__(UPDATE_THREADS, 2)
 model_update_kernel(const UpdateParams p) {
@@ -328,39 +540,57 @@ model_update_kernel(const UpdateParams p) {
   const int R = md.rank, col = md.col, cur = st->cur;
   const int rows = p.rows, ld = p.ld, n = p.mode, N = p.n_modes;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
   const int iters = md.iters;
 
+  CALS_PROF(0);
   extern __shared__ double sm[];
-  double *Hs = sm;                 // R x R : H, then its Cholesky factor (lower)
-  double *Gs = Hs + R * R;         // R x R : new Gramian of mode n
+  double *Hs = sm;                 // R x R : H; the Cholesky factor takes its lower triangle, the strict upper keeps H
+  double *Gs = Hs + R * R;         // R x R : inverses of L's diagonal blocks during pass 1, then the new Gramian
   double *cstat = Gs + R * R;      // 2R : per column reduction value / index ; then lambda, 1/lambda
-  double *red = cstat + 2 * R;     // 32
-  double *S = red + 32;            // chunk_rows x R, pitch chunk_pitch
+  double *inv = cstat + 2 * R;     // R : 1 / L[j][j]
+  double *hdiag = inv + R;         // R : diagonal of H (overwritten in Hs by the factorisation)
+  double *red = hdiag + R;         // 64
+  double *cand = red + 64;         // 2 * STAT_SEGS * R : per (column, row segment) candidates of the column statistics
+  double *S = cand + 2 * STAT_SEGS * R; // chunk_rows x R, pitch chunk_pitch
   const int pitch = p.chunk_pitch, CR = p.chunk_rows;
   // NNLS scratch (only allocated when p.nnls): per working warp 5R + R*R doubles and 2R + 1 ints, behind S
   double *nn_base = S + (size_t)pitch * p.max_rank;
+  // tile lookup tables of the fused partial-tile reduction: R + chunk_rows ints at the very end of the allocation
+  int *cinfo = reinterpret_cast<int *>(sm + p.table_off);
+  int *rinfo = cinfo + p.max_rank;
 
   double *grams = p.gram_pool + md.gram_off;
   const double *Gm = p.G + (size_t)col * ld;
   double *Fm = p.F[cur] + (size_t)col * ld;
+  const bool fused = p.plan != nullptr;
+  const PlanView pv = fused ? plan_view(p.plan, p.plan_ctas) : PlanView{};
 
   // ---- H = hadamard of the other Gramians ----
+#pragma unroll 1
   for (int e = tid; e < R * R; e += nthr) {
     double h = 1.0;
+#pragma unroll 1
     for (int k = 0; k < N; k++)
       if (k != n)
         h *= grams[(size_t)k * R * R + e];
     Hs[e] = h;
     Gs[e] = 0.0;
+    const int i = e % R;
+    if (i * R + i == e)
+      hdiag[i] = h;
   }
-  for (int e = tid; e < 2 * R; e += nthr)
-    cstat[e] = (e < R) ? -1.0 : 0.0; // value (sum of squares starts at 0 below; max-abs starts at -1), index
+  for (int e = tid; e < 2 * R; e += nthr) // value: a sum of squares starts at 0, a max-abs at -1; then the index
+    cstat[e] = (e < R) ? (iters == 1 ? 0.0 : -1.0) : 0.0;
+  if (fused) // (n-tile, column in tile) of every column of the model
+    for (int j = tid; j < R; j += nthr) {
+      const int cg = col + j;
+      const int nt = plan_tile_of(cg >> 6, pv.NO, pv.n_tiles);
+      cinfo[j] = (nt << 8) | (cg - 64 * plan_oct_start(nt, pv.NO, pv.n_tiles));
+    }
   __syncthreads();
-  if (iters == 1)
-    for (int e = tid; e < R; e += nthr)
-      cstat[e] = 0.0;
+  CALS_PROF(1);
 
-  // ---- Cholesky, right-looking, in shared memory (unconstrained update only; NNLS needs H itself) ----
   int chol_fail = 0;
   double nnls_tol = 0.0;
   if (NNLS) { // tol = 10 * eps * ||H||_1 * R   (reference src/utils/update.cpp:65-66; one_norm = max column sum)
@@ -374,80 +604,93 @@ model_update_kernel(const UpdateParams p) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
       mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((tid & 31) == 0)
-      red[tid >> 5] = mx;
+    if (lane == 0)
+      red[warp] = mx;
     __syncthreads();
     mx = red[0];
-    for (int wv = 1; wv < (nthr >> 5); wv++)
+    for (int wv = 1; wv < nw; wv++)
       mx = fmax(mx, red[wv]);
     nnls_tol = 10 * 2.2204e-16 * mx * (double)R;
     __syncthreads();
   }
-  for (int j = 0; j < (NNLS ? 0 : R); j++) {
-    __syncthreads();
-    const double d = Hs[j + j * R];
-    if (!(d > 0.0))
-      chol_fail = 1; // LAPACK would stop here (info = j+1); the reference only logs it and carries on
-    const double sd = sqrt(d);
-    __syncthreads();
-    if (tid == 0)
-      Hs[j + j * R] = sd;
-    for (int i = j + 1 + tid; i < R; i += nthr)
-      Hs[i + j * R] /= sd;
-    __syncthreads();
-    // trailing update of the lower triangle: H[i][k] -= L[i][j] * L[k][j],  j < k <= i < R
-    const int t = R - j - 1;
-    for (int e = tid; e < t * t; e += nthr) {
-      const int i = j + 1 + e % t, k = j + 1 + e / t;
-      if (k <= i)
-        Hs[i + k * R] -= Hs[i + j * R] * Hs[k + j * R];
-    }
-  }
-  __syncthreads();
 
   const bool jk_here = (md.jk_mode == n);
   const int jk_row = md.jk_fiber;
   const bool single = rows <= CR;
 
-  // ---- pass 1: solve rows, jackknife row, column statistics ----
+  // ---- pass 1: Cholesky || staging, solve rows, jackknife row, column statistics ----
+#pragma unroll 1
   for (int r0 = 0; r0 < rows; r0 += CR) {
     const int nr = min(CR, rows - r0);
-    __syncthreads();
-    if (p.plan != nullptr) {
-      // columns fastest: a warp reads runs of R consecutive doubles of a row-major partial tile
-      const PlanView pv = plan_view(p.plan, p.plan_ctas);
-      for (int e = tid; e < nr * R; e += nthr) {
-        const int j = e % R, rr = e / R;
-        const int m = r0 + rr, cg = col + j;
-        const int mt = plan_tile_of(m >> 3, pv.In8, pv.m_tiles);
-        const int nt = plan_tile_of(cg >> 6, pv.NO, pv.n_tiles);
-        const int pair = nt * pv.m_tiles + mt;
-        const int s0 = pv.pair_seg0[pair], s1 = pv.pair_seg0[pair + 1];
-        const double *q = p.ws + (size_t)s0 * p.tile_elems +
-                          (size_t)(m - 8 * plan_m8_start(mt, pv.In8, pv.m_tiles)) * p.n_tile +
-                          (cg - 64 * plan_oct_start(nt, pv.NO, pv.n_tiles));
-        double sum = 0.0;
-        for (int k = s0; k < s1; k++, q += p.tile_elems)
-          sum += *q;
-        S[rr + j * pitch] = sum;
+    if (r0 > 0)
+      __syncthreads(); // S and rinfo are free again
+    if (fused) {       // (m-tile, row in tile) of every row of the chunk
+      for (int rr = tid; rr < nr; rr += nthr) {
+        const int mrow = r0 + rr;
+        const int mt = plan_tile_of(mrow >> 3, pv.In8, pv.m_tiles);
+        rinfo[rr] = (mt << 8) | (mrow - 8 * plan_m8_start(mt, pv.In8, pv.m_tiles));
       }
-      if (n == N - 1) { // keep G for the error term
-        __syncthreads();
-        double *Gw = p.G_out + (size_t)col * ld;
-        for (int e = tid; e < nr * R; e += nthr) {
-          const int rr = e % nr, j = e / nr;
-          Gw[(size_t)j * ld + r0 + rr] = S[rr + j * pitch];
+      __syncthreads();
+    }
+    // Stage rows [r0, r0 + nr) of the MTTKRP result into S.  In the first chunk warp 0 factors H meanwhile (and inverts
+    // the diagonal blocks of L); the other warps stage.
+    const bool overlap = r0 == 0 && !NNLS;
+    if (overlap && warp == 0) {
+      chol_fail = cholesky_warp(Hs, inv, R, lane);
+      diag_block_inverses_warp(Hs, inv, Gs, R, lane);
+      CALS_PROF(2);
+    } else if (fused) {
+      // Fused reduction: the result is not read from G but summed here, per (m,n) pair in segment order with four
+      // running sums, from the partial tiles the DMMA kernel has just written; for the last mode the sum also goes to
+      // G (the error term needs it after the solve).  Columns fastest: runs of R doubles of a row-major tile.
+      const int t0 = overlap ? tid - 32 : tid, tn = overlap ? nthr - 32 : nthr;
+      double *Gw = p.G_out + (size_t)col * ld;
+      const int dj = tn % R, dr = tn / R;
+      int j = t0 % R, rr = t0 / R;
+#pragma unroll 1
+      while (rr < nr) {
+        const int ci = cinfo[j], ri = rinfo[rr];
+        const int pair = (ci >> 8) * pv.m_tiles + (ri >> 8);
+        const int s0 = pv.pair_seg0[pair], s1 = pv.pair_seg0[pair + 1];
+        const double *q = p.ws + (size_t)s0 * p.tile_elems + (size_t)(ri & 255) * p.n_tile + (ci & 255);
+        const size_t te = (size_t)p.tile_elems;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = s0;
+#pragma unroll 1
+        for (; k + 4 <= s1; k += 4, q += 4 * te) {
+          a0 += q[0];
+          a1 += q[te];
+          a2 += q[2 * te];
+          a3 += q[3 * te];
+        }
+#pragma unroll 1
+        for (; k < s1; k++, q += te)
+          a0 += *q;
+        const double sum = (a0 + a1) + (a2 + a3);
+        S[rr + j * pitch] = sum;
+        if (n == N - 1) // keep G for the error term
+          Gw[(size_t)j * ld + r0 + rr] = sum;
+        j += dj;
+        rr += dr;
+        if (j >= R) {
+          j -= R;
+          rr++;
         }
       }
     } else {
-      for (int e = tid; e < nr * R; e += nthr) {
-        const int rr = e % nr, j = e / nr;
-        S[rr + j * pitch] = Gm[(size_t)j * ld + r0 + rr];
+      const int w0 = overlap ? warp - 1 : warp, wn = overlap ? nw - 1 : nw;
+#pragma unroll 1
+      for (int j = w0; j < R; j += wn) {
+        const double *gj = Gm + (size_t)j * ld + r0;
+        double *sj = S + j * pitch;
+#pragma unroll 2
+        for (int rr = lane; rr < nr; rr += 32)
+          sj[rr] = gj[rr];
       }
     }
     __syncthreads();
+    CALS_PROF(3);
     if (NNLS) { // warp per row, active sets warm-started from the previous iteration
-      const int warp = tid >> 5, lane = tid & 31;
       if (warp < p.nnls_warps) {
         const size_t per_warp = (size_t)5 * R + (size_t)R * R + (size_t)(2 * R + 2) / 2 + 1; // doubles
         double *wb = nn_base + per_warp * warp;
@@ -468,81 +711,77 @@ model_update_kernel(const UpdateParams p) {
           chol_fail = 1;
       }
     } else {
-      for (int rr = tid; rr < nr; rr += nthr) {
-        double *row = S + rr;
-        // y L^T = g   (forward, right-looking)
-        for (int j = 0; j < R; j++) {
-          const double y = row[j * pitch] / Hs[j + j * R];
-          row[j * pitch] = y;
-          for (int k = j + 1; k < R; k++)
-            row[k * pitch] -= y * Hs[k + j * R];
-        }
-        // x L = y     (backward, right-looking)
-        for (int j = R - 1; j >= 0; j--) {
-          const double x = row[j * pitch] / Hs[j + j * R];
-          row[j * pitch] = x;
-          for (int k = 0; k < j; k++)
-            row[k * pitch] -= x * Hs[j + k * R];
-        }
-      }
+      solve_rows_dmma(S, pitch, nr, Hs, Gs, R, warp, nw, lane);
     }
     __syncthreads();
+    CALS_PROF(4);
     if (jk_here && jk_row >= r0 && jk_row < r0 + nr) { // Ktensor::set_jk_fiber(0.0)
       for (int j = tid; j < R; j += nthr)
         S[(jk_row - r0) + j * pitch] *= 0.0;
       __syncthreads();
     }
-    // column statistics: warp per column
+    // Column statistics (Ktensor::normalize, src/ktensor.cpp:66-83): sum of squares at the model's first iteration, else
+    // the entry of largest magnitude with the first index on ties.  Thread (column, segment) scans one of STAT_SEGS
+    // row segments; the segments of a column are then combined in row order.
     {
-      const int warp = tid >> 5, lane = tid & 31, nw = nthr >> 5;
-      for (int j = warp; j < R; j += nw) {
+      const int seg = tid % STAT_SEGS, seg_len = (nr + STAT_SEGS - 1) / STAT_SEGS;
+      const int lo = seg * seg_len, hi = min(nr, lo + seg_len);
+#pragma unroll 1
+      for (int j = tid / STAT_SEGS; j < R; j += nthr / STAT_SEGS) {
         const double *cj = S + j * pitch;
+        double v = iters == 1 ? 0.0 : -1.0;
+        int bi = 0x7fffffff;
         if (iters == 1) {
-          double ss = 0.0;
-          for (int rr = lane; rr < nr; rr += 32)
-            ss += cj[rr] * cj[rr];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-            ss += __shfl_xor_sync(0xffffffffu, ss, o);
-          if (lane == 0)
-            cstat[j] += ss;
+#pragma unroll 2
+          for (int rr = lo; rr < hi; rr++)
+            v += cj[rr] * cj[rr];
         } else {
-          double best = -1.0;
-          int bi = 0x7fffffff;
-          for (int rr = lane; rr < nr; rr += 32) {
+#pragma unroll 2
+          for (int rr = lo; rr < hi; rr++) {
             const double a = fabs(cj[rr]);
-            if (a > best) { // strictly greater keeps the first index within this lane's (increasing) sequence
-              best = a;
+            if (a > v) { // strictly greater keeps the first index
+              v = a;
               bi = r0 + rr;
             }
           }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) {
-              best = ob;
-              bi = oi;
+        }
+        cand[(j * STAT_SEGS + seg) * 2] = v;
+        cand[(j * STAT_SEGS + seg) * 2 + 1] = (double)bi;
+      }
+      __syncthreads();
+      for (int j = tid; j < R; j += nthr) {
+        const double *cj = cand + (size_t)j * STAT_SEGS * 2;
+        if (iters == 1) {
+          double ss = 0.0;
+          for (int q = 0; q < STAT_SEGS; q++)
+            ss += cj[2 * q];
+          cstat[j] += ss;
+        } else {
+          double best = cstat[j], bidx = cstat[R + j]; // earlier chunks / segments win ties (first index, as idamax)
+          for (int q = 0; q < STAT_SEGS; q++)
+            if (cj[2 * q] > best) {
+              best = cj[2 * q];
+              bidx = cj[2 * q + 1];
             }
-          }
-          if (lane == 0 && best > cstat[j]) { // earlier chunks win ties (first index of the maximum, as idamax)
-            cstat[j] = best;
-            cstat[R + j] = (double)bi;
-          }
+          cstat[j] = best;
+          cstat[R + j] = bidx;
         }
       }
     }
     if (!single) {
       __syncthreads();
-      for (int e = tid; e < nr * R; e += nthr) {
-        const int rr = e % nr, j = e / nr;
-        Fm[(size_t)j * ld + r0 + rr] = S[rr + j * pitch];
-      }
+#pragma unroll 1
+      for (int j = warp; j < R; j += nw)
+        for (int rr = lane; rr < nr; rr += 32)
+          Fm[(size_t)j * ld + r0 + rr] = S[rr + j * pitch];
     }
   }
   __syncthreads();
+  CALS_PROF(5);
 
   // ---- lambda ----
+  for (int e = tid; e < R * R; e += nthr) // the block inverses are done with; from here on the new Gramian accumulates
+    Gs[e] = 0.0;
   for (int j = tid; j < R; j += nthr) {
     double lam;
     if (iters == 1)
@@ -556,53 +795,78 @@ model_update_kernel(const UpdateParams p) {
     cstat[R + j] = (lam != 0.0) ? 1.0 / lam : 1.0;
   }
   __syncthreads();
+  CALS_PROF(6);
 
   // ---- pass 2: scale, write factor, accumulate Gramian (and <F, G> per column for the error) ----
   const bool last_mode = (n == N - 1);
   double term3 = 0.0;
+#pragma unroll 1
   for (int r0 = 0; r0 < rows; r0 += CR) {
     const int nr = min(CR, rows - r0);
-    __syncthreads();
-    for (int e = tid; e < nr * R; e += nthr) {
-      const int rr = e % nr, j = e / nr;
-      const double raw = single ? S[rr + j * pitch] : Fm[(size_t)j * ld + r0 + rr];
-      const double v = raw * cstat[R + j];
-      S[rr + j * pitch] = v;
-      Fm[(size_t)j * ld + r0 + rr] = v;
-      if (last_mode)
-        term3 += cstat[j] * v * Gm[(size_t)j * ld + r0 + rr];
+    if (r0 > 0)
+      __syncthreads();
+#pragma unroll 1
+    for (int j = warp; j < R; j += nw) {
+      double *sj = S + j * pitch;
+      double *fj = Fm + (size_t)j * ld + r0;
+      const double *gj = Gm + (size_t)j * ld + r0;
+      const double lam = cstat[j], rl = cstat[R + j];
+#pragma unroll 2
+      for (int rr = lane; rr < nr; rr += 32) {
+        const double v = (single ? sj[rr] : fj[rr]) * rl;
+        sj[rr] = v;
+        fj[rr] = v;
+        if (last_mode)
+          term3 += lam * v * gj[rr];
+      }
     }
     __syncthreads();
-    for (int e = tid; e < R * R; e += nthr) {
-      const int i = e % R, j = e / R;
-      const double *ci = S + i * pitch, *cj = S + j * pitch;
-      double g = 0.0;
-      for (int rr = 0; rr < nr; rr++)
-        g += ci[rr] * cj[rr];
-      Gs[e] += g;
-    }
+    CALS_PROF(7);
+    gram_dmma(S, pitch, nr, Gs, R, warp, nw, lane);
   }
   __syncthreads();
-  for (int e = tid; e < R * R; e += nthr)
-    grams[(size_t)n * R * R + e] = Gs[e];
+  CALS_PROF(8);
+  for (int e = tid; e < R * R; e += nthr) { // mirror, then publish
+    const int i = e % R, j = e / R;
+    const double v = (i >> 3) >= (j >> 3) ? Gs[i + j * R] : Gs[j + i * R]; // tiles of the lower block triangle
+    grams[(size_t)n * R * R + e] = v;
+  }
   if (__syncthreads_or(chol_fail) && tid == 0)
     md.chol_info += 1;
+  CALS_PROF(9);
+  if (p.prof != nullptr && tid == 0)
+    p.prof[(size_t)blockIdx.x * 16 + 15] = R;
 
   if (!last_mode)
     return;
 
   // ---- fast error, fit, eviction decision ----
+  // P = hadamard of all Gramians = H (the other modes; still in the strict upper triangle of Hs and in hdiag) times the
+  // new Gramian of this mode
   double term2 = 0.0;
   for (int e = tid; e < R * R; e += nthr) {
     const int i = e % R, j = e / R;
-    double pe = Gs[e];
-    for (int k = 0; k < N - 1; k++)
-      pe *= grams[(size_t)k * R * R + e];
-    term2 += cstat[i] * cstat[j] * pe;
+    const double gn = (i >> 3) >= (j >> 3) ? Gs[i + j * R] : Gs[j + i * R];
+    const double h = i == j ? hdiag[i] : (i < j ? Hs[i + j * R] : Hs[j + i * R]);
+    term2 += cstat[i] * cstat[j] * (NNLS ? Hs[e] : h) * gn;
   }
-  term2 = block_sum(term2, red);
-  term3 = block_sum(term3, red);
+  // both sums with one pass through shared memory
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    term2 += __shfl_xor_sync(0xffffffffu, term2, o);
+    term3 += __shfl_xor_sync(0xffffffffu, term3, o);
+  }
+  if (lane == 0) {
+    red[warp] = term2;
+    red[32 + warp] = term3;
+  }
+  __syncthreads();
   if (tid == 0) {
+    term2 = term3 = 0.0;
+    for (int wv = 0; wv < nw; wv++) {
+      term2 += red[wv];
+      term3 += red[32 + wv];
+    }
     double xn = st->x_norm;
     if (md.jk_mode >= 0 && p.x_norms_jk)
       xn = p.x_norms_jk[md.jk_fiber];
@@ -614,6 +878,7 @@ model_update_kernel(const UpdateParams p) {
     md.fit = fit;
     if (!st->ls_enabled) // with line search the decision is taken after the extrapolation step (ls.cuh)
       decide_eviction(md, st);
+    CALS_PROF(10);
   }
 }
 

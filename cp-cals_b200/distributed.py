@@ -14,15 +14,19 @@ import numpy as np
 
 
 def shard_models(ranks: Sequence[int], n_parts: int) -> List[List[int]]:
-    """Deterministic split of a FIFO model list over n_parts shards: every model goes to the shard with the smallest
-    sum of ranks so far (ties: lowest shard index); inside a shard the queue order is kept.  Same rule as the C++
-    host layer (cals::detail::shard_models, cp-cals_b200/host/cals.cpp)."""
+    """Deterministic split of a FIFO model list over n_parts shards: largest rank first (ties: queue order), every model
+    goes to the shard with the smallest sum of ranks so far (ties: lowest shard index); inside a shard the queue order is
+    kept.  Largest-first keeps the shards within one small rank of each other -- the per-GPU column counts set the MTTKRP
+    tile fill, and the slowest shard sets the time of the job.  Same rule as the C++ host layer
+    (cals::detail::shard_models, cp-cals_b200/host/cals.cpp)."""
     parts: List[List[int]] = [[] for _ in range(max(1, n_parts))]
     load = [0] * len(parts)
-    for i, r in enumerate(ranks):
+    for i in sorted(range(len(ranks)), key=lambda i: (-int(ranks[i]), i)):
         best = min(range(len(parts)), key=lambda p: (load[p], p))
         parts[best].append(i)
-        load[best] += int(r)
+        load[best] += int(ranks[i])
+    for p in parts:
+        p.sort()
     return parts
 
 

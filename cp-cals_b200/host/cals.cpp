@@ -363,9 +363,15 @@ static RunResult run_sliced(const std::vector<int> &devices, int slice_mode, con
 }
 
 std::vector<std::vector<size_t>> shard_models(const std::vector<dim_t> &ranks, size_t n_parts) {
+  // Largest rank first (ties: queue order), each model to the shard with the smallest sum of ranks so far (ties: lowest
+  // shard index); inside a shard the queue order is kept.  Largest-first keeps the shards within one small rank of each
+  // other -- the per-GPU column counts set the MTTKRP tile fill, and the slowest shard sets the time of the job.
   std::vector<std::vector<size_t>> parts(std::max<size_t>(n_parts, 1));
   std::vector<dim_t> load(parts.size(), 0);
-  for (size_t i = 0; i < ranks.size(); i++) {
+  std::vector<size_t> order(ranks.size());
+  std::iota(order.begin(), order.end(), size_t(0));
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ranks[a] > ranks[b]; });
+  for (size_t i : order) {
     size_t best = 0;
     for (size_t p = 1; p < parts.size(); p++)
       if (load[p] < load[best])
@@ -373,6 +379,8 @@ std::vector<std::vector<size_t>> shard_models(const std::vector<dim_t> &ranks, s
     parts[best].push_back(i);
     load[best] += ranks[i];
   }
+  for (auto &p : parts)
+    std::sort(p.begin(), p.end());
   return parts;
 }
 

@@ -102,7 +102,8 @@ int main() {
                   seg_pair[seg] = pair;
                 }
                 int nt = pair / m_tiles, mt = pair - nt * m_tiles;
-                const PairCost pc = plan_pair_cost(sh, plan_wm(mt, In8, m_tiles), plan_nn(nt, NO, n_tiles));
+                const PairCost pc = plan_pair_cost(sh, plan_wm(mt, In8, m_tiles), plan_nn(nt, NO, n_tiles),
+                                                   nt == n_tiles - 1 ? (C - 64 * (NO - 1) + 7) / 8 : 8);
                 // the rest of this CTA's range inside this pair in one step (the cost model has a closed-form prefix)
                 const long long k0 = ch - (long long)pair * Tp;
                 long long k1 = (long long)hi - (long long)pair * Tp;

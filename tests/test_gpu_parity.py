@@ -20,6 +20,11 @@ MTTKRP_SHAPES = [
     ((20, 6, 5, 4, 3), 33),  # 5 modes
     ((64, 24, 50), 300),     # two n-tiles
     ((130, 17, 90), 513),    # several m-tiles, 3 n-tiles, K tail
+    # ragged last octet (csrc/mttkrp.cuh RaggedOctet): the units of a partly filled octet are dealt to all warps
+    ((200, 30, 20), 263),    # an 8-way shard of config 2: 5 octets, one valid n8 group in the last, 5 m8 groups per tile
+    ((56, 24, 10), 71),      # second octet of the only n-tile holds 7 columns; 7 m8 groups
+    ((24, 9, 5, 4), 137),    # 4 modes (slow outer weights of the units), third octet holds 9 columns
+    ((17, 16, 15), 1),       # a single column
 ]
 
 
@@ -204,6 +209,8 @@ def test_cp_cals_per_iteration_vs_oracle(pkg, modes, ranks, K, buffer):
     ((9, 8, 7, 6), [1, 2, 3, 4, 5], 5, None),                    # 4 modes: two pair nodes, (0,1) and (2,3)
     ((12, 9, 8, 7), [3, 1, 4, 1, 5, 9, 2, 6], 5, 12),            # 4 modes + queueing
     ((20, 44, 9, 31), list(range(1, 10)) * 8, 3, None),          # 4 modes, 360 columns, odd pitches in both layouts
+    ((40, 56, 24), [20] * 13 + [3], 3, None),                    # 263 columns: ragged last octet in MTTKRP and pair GEMM
+    ((30, 12, 9, 16), [7] * 10 + [1], 3, None),                  # 4 modes, 71 columns: ragged octet with slow outer modes
 ])
 def test_pair_node_equals_per_mode_mttkrp(pkg, modes, ranks, K, buffer):
     """Pair nodes (csrc/pairnode.cuh): 3-mode tensors take the MTTKRPs of modes 1 and 2 from T = X_(0)^T A_0, 4-mode
