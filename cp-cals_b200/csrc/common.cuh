@@ -76,6 +76,20 @@ __device__ __forceinline__ void decide_eviction(ModelDesc &md, SchedState *st) {
     md.iters = iters + 1;
 }
 
+// Programmatic dependent launch (sm_90+): the kernels of one CALS iteration form a chain; each is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so that its CTAs are scheduled -- block start-up, parameter and
+// descriptor fetch, the first instruction lines -- while its predecessor is still draining, and blocks here until the
+// predecessor has completed and its writes are visible.  Every thread of every kernel of the chain calls pdl_wait()
+// before it touches anything another kernel writes (no early return in front of it: a grid that completed without
+// waiting would let ITS successor run ahead of a still-running grand-predecessor).  Without the launch attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_trigger();
+}
+
 // Geometry shared by all kernels: extents and leading dimensions.
 struct Geom {
   int n_modes;

@@ -103,6 +103,7 @@ struct cals_b200_ctx {
   int timing = 0;
   int variant = CALS_B200_MTTKRP_DMMA;
   int pair_node = 1; // cals_b200_set_pair_node
+  bool pdl = false;  // programmatic dependent launch for the kernels of the iteration chain (set per run)
 
   // models
   std::vector<HostModel> hmodels;
@@ -172,6 +173,7 @@ struct cals_b200_ctx {
   bool dmma_attr_done[16] = {};
   bool pair_attr_done[16] = {};
   size_t update_attr_smem = 0;
+  size_t leaf_slow_attr = 0;
 };
 
 namespace {
@@ -244,6 +246,23 @@ template <typename F> void parallel_models(size_t n_models, size_t bytes, F &&fn
   fn((size_t)0, std::min(n_models, per));
   for (auto &t : th)
     t.join();
+}
+
+// Launch of a kernel of the iteration chain: with c->pdl the launch carries the programmatic-stream-serialization
+// attribute (common.cuh: pdl_wait / pdl_trigger), so the kernel's CTAs start while the previous kernel drains.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(cals_b200_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = c->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -532,12 +551,20 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
         for (int m = 0; m < N; m++)
           nd.pg.ldF[m] = geo.ldF[m];
         nd.slot = N == 3 ? -1 : N + k;
-        if (dev_alloc(c, &nd.T, (size_t)nd.pg.R * cols, b.allocs))
+        // + 2: the leaf kernels' bulk copies read 16-byte granules and may touch one double past the last row
+        if (dev_alloc(c, &nd.T, (size_t)nd.pg.R * cols + 2, b.allocs))
           return 1;
         b.node_of[mf] = b.node_of[mf + 1] = k;
       }
       b.n_nodes = n_nodes;
       b.tree = true;
+      for (int k = 0; k < n_nodes; k++) { // dynamic shared memory of the TMA-fed leaf kernel (ring of stages)
+        const size_t ss = leaf_slow_smem(b.node[k].pg.E2);
+        if (ss > c->leaf_slow_attr) {
+          CU_TRY(c, cudaFuncSetAttribute(pair_leaf_slow_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ss));
+          c->leaf_slow_attr = ss;
+        }
+      }
       if (N == 3) {
         PairGeom &pg = b.node[0].pg;
         pg.Ip = c->xd[0];
@@ -565,6 +592,9 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
   b.plans = PlanArgs{};
   b.plans.n_modes = n_plans;
   b.plans.G = c->sm_count;
+  if (dev_alloc(c, &b.plans.built_for, (size_t)CALS_MAX_MODES, b.allocs))
+    return 1;
+  CU_TRY(c, cudaMemsetAsync(b.plans.built_for, 0xff, CALS_MAX_MODES * sizeof(int), c->stream));
   for (int n = 0; n < n_plans; n++) {
     const int pairs_max = b.mg[n].m_tiles * n_tiles_max;
     tiles = std::max(tiles, (size_t)(c->sm_count + pairs_max + 2));
@@ -596,7 +626,8 @@ template <int WM> int launch_pair_gemm_wm(cals_b200_ctx *c, Buffers &b, bool att
     c->pair_attr_done[WM] = true;
   }
   if (!attr_only)
-    kern<<<c->sm_count, MTTKRP_THREADS, smem, c->stream>>>(b.pmaps, b.node[0].pg, c->d_st, b.node[0].T);
+    CU_TRY(c, launch_chain(c, kern, dim3(c->sm_count), dim3(MTTKRP_THREADS), (size_t)smem, b.pmaps, b.node[0].pg,
+                           (const SchedState *)c->d_st, b.node[0].T));
   return 0;
 }
 
@@ -629,10 +660,16 @@ int launch_pair_leaf(cals_b200_ctx *c, Buffers &b, int n, bool exchange) {
   x.n_modes = c->geo.n_modes;
   if (n == pg.mode_fast) {
     dim3 grid((unsigned)b.cols, (unsigned)((pg.E1 + 255) / 256));
-    pair_leaf_slow_kernel<<<grid, 256, (size_t)pg.E2 * 8, c->stream>>>(pg, c->d_st, b.fac, nd.T, b.G, x);
+    if (b.cols <= LEAF_TMA_MAX_COLS) // narrow grid: one TMA-fed stream per column
+      CU_TRY(c, launch_chain(c, pair_leaf_slow_tma_kernel, grid, dim3(LEAF_THREADS), leaf_slow_smem(pg.E2), pg,
+                             (const SchedState *)c->d_st, b.fac, (const double *)nd.T, b.G, x));
+    else
+      CU_TRY(c, launch_chain(c, pair_leaf_slow_kernel, grid, dim3(256), (size_t)pg.E2 * 8, pg,
+                             (const SchedState *)c->d_st, b.fac, (const double *)nd.T, b.G, x));
   } else {
     dim3 grid((unsigned)b.cols, 1);
-    pair_leaf_fast_kernel<<<grid, 256, (size_t)pg.E1 * 8, c->stream>>>(pg, c->d_st, b.fac, nd.T, b.G, x);
+    CU_TRY(c, launch_chain(c, pair_leaf_fast_kernel, grid, dim3(256), (size_t)pg.E1 * 8, pg, (const SchedState *)c->d_st,
+                           b.fac, (const double *)nd.T, b.G, x));
   }
   return 0;
 }
@@ -669,15 +706,16 @@ int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchan
   if (set_dmma_attr<WM>(c))
     return 1;
   const int G = c->sm_count;
-  kern<<<G, MTTKRP_THREADS, smem_bytes<WM>(), c->stream>>>(b.maps[n], b.mg[n], c->d_st, b.fac, b.plans.plan[n], b.ws,
-                                                            C_override);
+  CU_TRY(c, launch_chain(c, kern, dim3(G), dim3(MTTKRP_THREADS), (size_t)smem_bytes<WM>(), b.maps[n], b.mg[n],
+                         (const SchedState *)c->d_st, b.fac, (const int *)b.plans.plan[n], b.ws, C_override));
   if (skip_reduce) // the update kernel sums the partial tiles itself
     return 0;
   const int cols = C_override > 0 ? C_override : b.cols;
   dim3 rg((cols + 31) / 32, (b.mg[n].In + REDUCE_ROWS - 1) / REDUCE_ROWS);
-  mttkrp_reduce_kernel<8 * WM, TILE_N><<<rg, 256, 0, c->stream>>>(
-      b.mg[n], c->d_st, b.plans.plan[n], b.ws, out, G, C_override, exchange ? exchange_data(c) : nullptr,
-      (unsigned long long)c->xcap, c->seq_base, c->geo.n_modes);
+  CU_TRY(c, launch_chain(c, mttkrp_reduce_kernel<8 * WM, TILE_N>, rg, dim3(256), (size_t)0, b.mg[n],
+                         (const SchedState *)c->d_st, (const int *)b.plans.plan[n], (const double *)b.ws, out, G,
+                         C_override, exchange ? exchange_data(c) : (double *)nullptr, (unsigned long long)c->xcap,
+                         (unsigned long long)c->seq_base, c->geo.n_modes));
   return 0;
 }
 
@@ -1082,12 +1120,13 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   // (sliced tensor), there are no partial tiles (naive variant), or CALS_B200_NO_FUSED_REDUCE=1 asks for the two-kernel
   // path (kept for A/B measurements).
   static const bool fusion_off = getenv("CALS_B200_NO_FUSED_REDUCE") != nullptr;
-  // Only worth it when the MTTKRP itself is short (measured: +11 % at 100^3 x 220 columns, -1 % at 200^3 x 2100, where
-  // the separate, much wider reduce kernel is cheaper than lengthening the largest model's update CTA).
+  // Round 1 used it for small problems (+11 % at 100^3 x 220 columns with the reduce kernel of that time).  With the
+  // one-element-per-thread reduce kernel (eight loads in flight, grid over the whole output) the separate pass wins
+  // everywhere (config 1: 307.5 k vs 302 k model-iterations/s) -- a few update CTAs cannot pull tens of partial tiles
+  // per element as fast as the whole chip -- so the fused form only runs when CALS_B200_FUSED_REDUCE=1 asks for it.
   static const bool fusion_forced = getenv("CALS_B200_FUSED_REDUCE") != nullptr;
-  const bool small_problem = (double)c->nX * (double)c->buffer_cols <= 2.0e9;
   const bool fused_reduce = c->variant == CALS_B200_MTTKRP_DMMA && !(c->slice_mode >= 0 && c->comm_world > 1) &&
-                            !fusion_off && (small_problem || fusion_forced);
+                            !fusion_off && fusion_forced;
 
   // pair nodes: two modes share one contraction of the tensor (pairnode.cuh)
   const bool tree = b.tree && c->variant == CALS_B200_MTTKRP_DMMA;
@@ -1258,8 +1297,16 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   int launches_per_iteration = 0;
   auto enqueue_iteration = [&](bool count) -> int {
     int n_launch = 0;
-    sched_kernel<<<1, 32, 0, s>>>(sp);
-    move_kernel<<<move_grid, 256, 0, s>>>(geo, b.fac, c->d_st, c->d_gather, c->d_evict);
+    auto chain_ok = [&](cudaError_t e, const char *what) {
+      if (e != cudaSuccess)
+        fail(c, "launch of %s failed: %s", what, cudaGetErrorString(e));
+      return e == cudaSuccess;
+    };
+    sched_kernel<<<1, 32, 0, s>>>(sp); // first kernel of the iteration: plain stream order after the previous iteration
+    if (!chain_ok(launch_chain(c, move_kernel, move_grid, dim3(256), (size_t)0, geo, b.fac, (const SchedState *)c->d_st,
+                               (const int *)c->d_gather, (const int *)c->d_evict),
+                  "move_kernel"))
+      return -1;
     n_launch += 2;
     if (c->ls_enabled) {
       ls_snapshot_kernel<<<max_live, 256, 0, s>>>(lp);
@@ -1308,10 +1355,12 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
         e1 = mark();
         window(e0, e1, T_MTTKRP); // includes the exchange
       }
-      if (up[n].nnls)
-        model_update_kernel<true><<<max_live, UPDATE_THREADS, up_smem[n], s>>>(up[n]);
-      else
-        model_update_kernel<false><<<max_live, UPDATE_THREADS, up_smem[n], s>>>(up[n]);
+      if (!chain_ok(up[n].nnls ? launch_chain(c, model_update_kernel<true>, dim3(max_live), dim3(UPDATE_THREADS),
+                                              up_smem[n], up[n])
+                               : launch_chain(c, model_update_kernel<false>, dim3(max_live), dim3(UPDATE_THREADS),
+                                              up_smem[n], up[n]),
+                    "model_update_kernel"))
+        return -1;
       n_launch++;
       window(e1, mark(), T_UPDATE);
     }
@@ -1333,9 +1382,16 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   // kernels), with the sliced-tensor exchange (its sequence base changes from run to run) and with CALS_B200_NO_GRAPH=1.
   static const bool graphs_off = getenv("CALS_B200_NO_GRAPH") != nullptr;
   const bool use_graph = !c->timing && !exchange && !graphs_off;
+  // Programmatic dependent launch between the kernels of the chain: OFF unless CALS_B200_PDL=1.  Measured on the B200
+  // inside the replayed graph it costs throughput on every configuration (config 2: 85.3 k -> 82.4 k, its 8-way shard
+  // 52.7 k -> 48.1 k, config 1: 302 k -> 291 k model-iterations/s): the early-scheduled CTAs of the next kernel hold
+  // shared memory and registers on the SMs the running kernel still uses, and graph kernel nodes already launch
+  // back to back.  Never used with per-kernel timing, line search or the sliced-tensor exchange.
+  static const bool pdl_on = getenv("CALS_B200_PDL") != nullptr;
+  c->pdl = use_graph && pdl_on && !c->ls_enabled;
   if (use_graph) {
     std::vector<long long> key = {c->alloc_generation, (long long)c->flags, c->ls_enabled, c->ls_method, c->variant,
-                                  (long long)max_live, fused_reduce ? 1 : 0, tree ? 1 : 0};
+                                  (long long)max_live, fused_reduce ? 1 : 0, tree ? 1 : 0, c->pdl ? 1 : 0};
     const bool same_graph = c->iter_graph && c->iter_graph_key.size() == key.size() + 1 &&
                             std::equal(key.begin(), key.end(), c->iter_graph_key.begin());
     if (!same_graph) {
@@ -2100,6 +2156,7 @@ int cals_b200_mttkrp(cals_b200_ctx *c, int mode, uint64_t cols, const double *co
       repeats = 1;
     if (c->slice_mode >= 0) // rows outside this device's slab are not produced: the hook returns them as zeros
       cudaMemsetAsync(b.G, 0, (size_t)geo.ldF[mode] * cols * 8, c->stream);
+    c->pdl = false; // single launches in plain stream order
     mttkrp_plan_kernel<<<1, 32, 0, c->stream>>>(b.plans, (int)cols);
     rc = launch_mttkrp(c, b, mode, (int)cols, variant); // warm-up + result
     cudaEventRecord(e0, c->stream);

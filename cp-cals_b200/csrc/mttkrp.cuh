@@ -310,6 +310,7 @@ struct PlanArgs {
   PlanShape shape[CALS_MAX_MODES];
   int *plan[CALS_MAX_MODES];
   int G;
+  int *built_for; // [CALS_MAX_MODES] column count each plan table was last built for (-1: never); device memory
 };
 __global__ void mttkrp_plan_kernel(const PlanArgs a, int C) {
   const int n = threadIdx.x;
@@ -428,6 +429,7 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
   uint64_t *full_w = bars + 2 * X_STAGES, *empty_w = full_w + 2;
   uint64_t *full_b = empty_w + 2, *empty_b = full_b + 1;
 
+  pdl_enter();
   const int C = C_override > 0 ? C_override : st->C;
   const int cur = C_override > 0 ? 0 : st->cur;
   if (C <= 0)
@@ -658,7 +660,7 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
 // ------------------------------------------------------------------------------------------------------------------
 // Sum the partial tiles of every (m,n) pair in segment order and write G (In x C, column-major, ld = ldG).
 // One CTA per 8 x 32 (rows x columns) patch of G, one output element per thread: reads are coalesced along columns of
-// the row-major tiles, four running sums keep four loads in flight per thread (a narrow shard has tens of segments per
+// the row-major tiles, eight running sums keep eight loads in flight per thread (a narrow shard has tens of segments per
 // pair and few output elements, so the pass is latency-bound), writes go through shared memory so that a warp stores
 // 8-row runs of G's columns.
 //
@@ -671,6 +673,7 @@ __global__ void __launch_bounds__(256)
 mttkrp_reduce_kernel(const MttkrpGeom g, const SchedState *__restrict__ st, const int *__restrict__ plan,
                      const double *__restrict__ ws, double *__restrict__ G, int grid_ctas, int C_override, double *xbuf,
                      unsigned long long xcap, unsigned long long seq_base, int n_modes) {
+  pdl_enter();
   const int C = C_override > 0 ? C_override : st->C;
   if (xbuf != nullptr) {
     const unsigned long long seq = seq_base + st->global_iter * (unsigned long long)n_modes + g.mode + 1;
@@ -693,17 +696,16 @@ mttkrp_reduce_kernel(const MttkrpGeom g, const SchedState *__restrict__ st, cons
       constexpr size_t TE = (size_t)M_TILE * N_TILE;
       const double *p = ws + (size_t)s0 * TE + (m - 8 * plan_m8_start(mt, pv.In8, pv.m_tiles)) * N_TILE +
                         (c - 64 * plan_oct_start(nt, pv.NO, pv.n_tiles));
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       int k = s0;
-      for (; k + 4 <= s1; k += 4, p += 4 * TE) {
-        a0 += p[0];
-        a1 += p[TE];
-        a2 += p[2 * TE];
-        a3 += p[3 * TE];
+      for (; k + 8 <= s1; k += 8, p += 8 * TE) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          a[u] += p[u * TE];
       }
-      for (; k < s1; k++, p += TE)
-        a0 += *p;
-      sum = (a0 + a1) + (a2 + a3);
+      for (int u = 0; k < s1; k++, u++, p += TE)
+        a[u] += *p;
+      sum = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     }
     t[ty][tx] = sum;
   }

@@ -61,11 +61,14 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
   uint64_t *bars = (uint64_t *)(smem + PAIR_STAGES * Cfg::STAGE_BYTES);
   uint64_t *full = bars, *empty = bars + PAIR_STAGES;
 
+  pdl_enter();
   const int C = st->C, cur = st->cur;
   if (C <= 0)
     return;
   const int m_tiles = (g.R + M_TILE - 1) / M_TILE;
-  const int n_tiles = (C + N_TILE - 1) / N_TILE;
+  // column tiles: the 64-column octets are split evenly over ceil(NO / 4) tiles, as in the MTTKRP plan (263 columns = 5
+  // octets give tiles of 2 and 3 octets, not 4 and 1: a 1-octet tile keeps one column group per warp busy)
+  const int NO = (C + 63) >> 6, n_tiles = (NO + OCT_TILE - 1) / OCT_TILE;
   const long long tiles = (long long)m_tiles * n_tiles;
   const int P_tiles = (g.Ip + KT - 1) / KT;
   if ((long long)blockIdx.x >= tiles)
@@ -95,7 +98,7 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
         mbar_wait(&empty[sidx], ph);
         mbar_expect_tx(&full[sidx], Cfg::STAGE_BYTES);
         tma_load_2d(stage, &maps.X, &full[sidx], pt * KT, mt * M_TILE);
-        tma_load_2d(stage + Cfg::X_BYTES, tmB, &full[sidx], pt * KT, nt * N_TILE);
+        tma_load_2d(stage + Cfg::X_BYTES, tmB, &full[sidx], pt * KT, 64 * plan_oct_start(nt, NO, n_tiles));
         if (++sidx == PAIR_STAGES) {
           sidx = 0;
           ph ^= 1;
@@ -113,9 +116,10 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
   uint32_t ph = 0;
   for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int nt = (int)(t / m_tiles), mt = (int)(t - (long long)nt * m_tiles);
-    const int m0 = mt * M_TILE, c0 = nt * N_TILE;
+    const int m0 = mt * M_TILE, c0 = 64 * plan_oct_start(nt, NO, n_tiles);
     const int nm = min(WM, (g.R - m0 + 7) >> 3);
-    int nn = min(WN, (C - c0 + 63) >> 6);
+    const int nn_tile = plan_nn(nt, NO, n_tiles); // octets of this tile: only their columns are this CTA's to write
+    int nn = nn_tile;
     if (c0 + 64 * (nn - 1) + 8 * warp >= C) // this warp's n8 group of the last octet starts beyond C (see mttkrp.cuh)
       nn--;
 #pragma unroll
@@ -146,9 +150,9 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
 #pragma unroll
         for (int j = 0; j < WN; j++) {
           const int col = c0 + j * 64 + warp * 8 + 2 * s;
-          if (col < C)
+          if (j < nn_tile && col < C)
             T[(size_t)col * g.ldT + row] = acc[i][j][0];
-          if (col + 1 < C)
+          if (j < nn_tile && col + 1 < C)
             T[(size_t)(col + 1) * g.ldT + row] = acc[i][j][1];
         }
       }
@@ -170,18 +174,11 @@ __device__ __forceinline__ double *leaf_output(double *G, const LeafExchange &x,
   return x.xbuf + (seq & 1ull) * x.xcap;
 }
 
-constexpr int LEAF_DEPTH = 16; // independent loads of T in flight per thread
-// Scheduling fence: the values must all be in registers here, so every load above has been issued before anything
-// below runs (the hardware issues in order; an FMA waiting for its operand would hold up the loads behind it).
-__device__ __forceinline__ void all_loaded(double (&v)[LEAF_DEPTH]) {
-  asm volatile("" ::"d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "d"(v[4]), "d"(v[5]), "d"(v[6]), "d"(v[7]), "d"(v[8]),
-               "d"(v[9]), "d"(v[10]), "d"(v[11]), "d"(v[12]), "d"(v[13]), "d"(v[14]), "d"(v[15]));
-}
-
 // G_fast[i1, c] = sum_{i2} T[i1 + E1*i2, c] * A_slow[i2, c].  One CTA per column and 256-row chunk of i1; thread = row.
 __global__ void __launch_bounds__(256)
 pair_leaf_slow_kernel(const PairGeom g, const SchedState *__restrict__ st, const FactorPtrs fac,
                       const double *__restrict__ T, double *__restrict__ G, const LeafExchange x) {
+  pdl_enter();
   const int C = st->C, cur = st->cur;
   const int c = blockIdx.x;
   if (c >= C)
@@ -198,17 +195,13 @@ pair_leaf_slow_kernel(const PairGeom g, const SchedState *__restrict__ st, const
   const double *t = T + (size_t)c * g.ldT + i1;
   double sum = 0.0;
   int k = 0;
-  // LEAF_DEPTH loads are issued before the first one is consumed (all_loaded keeps the compiler from interleaving the
-  // FMAs with the loads, which it otherwise does at 4 loads in flight): with one CTA per column, a grid of a few hundred
-  // columns -- the per-GPU shard of a strong-scaled run -- streams T at (bytes in flight per CTA) / latency.
-  for (; k + LEAF_DEPTH <= g.E2; k += LEAF_DEPTH) {
-    double v[LEAF_DEPTH];
+  for (; k + 8 <= g.E2; k += 8) {
+    double v[8];
 #pragma unroll
-    for (int u = 0; u < LEAF_DEPTH; u++)
+    for (int u = 0; u < 8; u++)
       v[u] = __ldcs(t + (size_t)(k + u) * g.E1);
-    all_loaded(v);
 #pragma unroll
-    for (int u = 0; u < LEAF_DEPTH; u++)
+    for (int u = 0; u < 8; u++)
       sum += v[u] * wcol[k + u];
   }
   for (; k < g.E2; k++)
@@ -219,10 +212,10 @@ pair_leaf_slow_kernel(const PairGeom g, const SchedState *__restrict__ st, const
 // G_slow[i2, c] = sum_{i1} T[i1 + E1*i2, c] * A_fast[i1, c].  One CTA per column; a warp takes LEAF_ROWS values of i2 at a
 // time (independent loads in flight), lanes run over i1.
 constexpr int LEAF_ROWS = 4;
-static_assert(4 * LEAF_ROWS == LEAF_DEPTH, "the fast leaf batches four lane-strides of LEAF_ROWS rows");
 __global__ void __launch_bounds__(256)
 pair_leaf_fast_kernel(const PairGeom g, const SchedState *__restrict__ st, const FactorPtrs fac,
                       const double *__restrict__ T, double *__restrict__ G, const LeafExchange x) {
+  pdl_enter();
   const int C = st->C, cur = st->cur;
   const int c = blockIdx.x;
   if (c >= C)
@@ -244,24 +237,7 @@ pair_leaf_fast_kernel(const PairGeom g, const SchedState *__restrict__ st, const
       t[u] = tc + (size_t)min(b2 + u, g.E2 - 1) * g.E1; // rows beyond E2 re-read the last row; their sums are dropped
       sum[u] = 0.0;
     }
-    int i1 = lane;
-    for (; i1 + 96 < g.E1; i1 += 128) { // four lane-strides of i1 x LEAF_ROWS rows = 16 loads in flight per thread
-      double v[LEAF_DEPTH];
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-#pragma unroll
-        for (int u = 0; u < LEAF_ROWS; u++)
-          v[q * LEAF_ROWS + u] = __ldcs(t[u] + i1 + 32 * q);
-      all_loaded(v);
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const double w = wcol[i1 + 32 * q];
-#pragma unroll
-        for (int u = 0; u < LEAF_ROWS; u++)
-          sum[u] += v[q * LEAF_ROWS + u] * w;
-      }
-    }
-    for (; i1 < g.E1; i1 += 32) {
+    for (int i1 = lane; i1 < g.E1; i1 += 32) {
       const double w = wcol[i1];
       double v[LEAF_ROWS];
 #pragma unroll
@@ -280,6 +256,101 @@ pair_leaf_fast_kernel(const PairGeom g, const SchedState *__restrict__ st, const
         out[b2 + u] = sum[u];
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Slow leaf for NARROW grids (at most LEAF_TMA_MAX_COLS columns: the per-GPU shard of a strong-scaled model set,
+// BASELINE config 1): one column of T per CTA, streamed through a ring of shared-memory stages filled by 1-D TMA bulk
+// copies (cp.async.bulk + mbarrier complete_tx).  With one CTA per column and a few hundred columns the whole grid is
+// one wave and every CTA is a single sequential stream; the per-thread loads of pair_leaf_slow_kernel keep too few bytes
+// in flight for that (measured at 255 columns of 200 x 200: 42 us, this kernel 22 us, HBM floor 13 us).  On wide grids
+// the plain kernel is faster (config 2: 118 us against 167 us for the pair), as is the plain fast leaf at every width
+// (measured), so those stay.
+//
+// A bulk copy needs 16-byte aligned source, destination and size, rows of T start at any multiple of 8 bytes (odd
+// E1): a row that starts at an odd element index is copied from one element earlier and read with an offset of 1.
+constexpr int LEAF_STAGES = 4;
+constexpr int LEAF_TMA_MAX_COLS = 592; // 4 CTAs per SM: above this the plain kernel fills the machine by itself
+constexpr int LEAF_THREADS = 256;
+constexpr int LEAF_SLOW_ROWS = 8;        // rows of i2 per stage in the slow leaf
+constexpr int LEAF_SLOW_PITCH = 256 + 2; // doubles per staged row slice (even, room for the alignment shift)
+
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+inline size_t leaf_slow_smem(int E2) {
+  return (size_t)((E2 + 1) & ~1) * 8 + (size_t)LEAF_STAGES * LEAF_SLOW_ROWS * LEAF_SLOW_PITCH * 8 + 64;
+}
+
+// G_fast[i1, c] = sum_{i2} T[i1 + E1*i2, c] * A_slow[i2, c].  grid = (columns, ceil(E1 / 256)); thread = one i1.
+__global__ void __launch_bounds__(LEAF_THREADS)
+pair_leaf_slow_tma_kernel(const PairGeom g, const SchedState *__restrict__ st, const FactorPtrs fac,
+                      const double *__restrict__ T, double *__restrict__ G, const LeafExchange x) {
+  pdl_enter();
+  const int C = st->C, cur = st->cur;
+  const int c = blockIdx.x;
+  if (c >= C)
+    return;
+  G = leaf_output(G, x, st, g.mode_fast);
+  extern __shared__ __align__(128) unsigned char leaf_smem[];
+  const int E2p = (g.E2 + 1) & ~1;
+  double *wcol = (double *)leaf_smem;                    // E2 weights
+  double *ring = wcol + E2p;                             // [LEAF_STAGES][LEAF_SLOW_ROWS][LEAF_SLOW_PITCH]
+  uint64_t *full = (uint64_t *)(ring + LEAF_STAGES * LEAF_SLOW_ROWS * LEAF_SLOW_PITCH);
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.y * 256, n_i1 = min(256, g.E1 - i0);
+  const size_t col_base = (size_t)c * g.ldT + i0; // element index of (i1 = i0, i2 = 0) in T
+  const int n_chunks = (g.E2 + LEAF_SLOW_ROWS - 1) / LEAF_SLOW_ROWS;
+  if (tid == 0) {
+    for (int q = 0; q < LEAF_STAGES; q++)
+      mbar_init(&full[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const double *W = fac.buf[cur][g.mode_slow] + (size_t)c * g.ldF[g.mode_slow] + g.off_slow;
+  for (int k = tid; k < g.E2; k += blockDim.x)
+    wcol[k] = W[k];
+  __syncthreads();
+  auto issue = [&](int chunk) { // thread 0: all row slices of one chunk into stage chunk % LEAF_STAGES
+    const int q = chunk % LEAF_STAGES, k0 = chunk * LEAF_SLOW_ROWS, nk = min(LEAF_SLOW_ROWS, g.E2 - k0);
+    uint32_t total = 0;
+    for (int r = 0; r < nk; r++) {
+      const size_t idx = col_base + (size_t)(k0 + r) * g.E1;
+      total += (uint32_t)(((n_i1 + (int)(idx & 1)) * 8 + 15) & ~15);
+    }
+    mbar_expect_tx(&full[q], total);
+    for (int r = 0; r < nk; r++) {
+      const size_t idx = col_base + (size_t)(k0 + r) * g.E1;
+      const int off = (int)(idx & 1);
+      bulk_load_1d(ring + ((size_t)q * LEAF_SLOW_ROWS + r) * LEAF_SLOW_PITCH, T + (idx - off),
+                   (uint32_t)(((n_i1 + off) * 8 + 15) & ~15), &full[q]);
+    }
+  };
+  if (tid == 0)
+    for (int q = 0; q < LEAF_STAGES - 1 && q < n_chunks; q++)
+      issue(q);
+  double sum = 0.0;
+  for (int ch = 0; ch < n_chunks; ch++) {
+    if (tid == 0 && ch + LEAF_STAGES - 1 < n_chunks)
+      issue(ch + LEAF_STAGES - 1); // its stage was consumed in iteration ch - 1 (barrier below)
+    const int q = ch % LEAF_STAGES, k0 = ch * LEAF_SLOW_ROWS, nk = min(LEAF_SLOW_ROWS, g.E2 - k0);
+    mbar_wait(&full[q], (uint32_t)((ch / LEAF_STAGES) & 1));
+    if (tid < n_i1) {
+      const double *stg = ring + (size_t)q * LEAF_SLOW_ROWS * LEAF_SLOW_PITCH + tid;
+#pragma unroll
+      for (int r = 0; r < LEAF_SLOW_ROWS; r++)
+        if (r < nk) {
+          const int off = (int)((col_base + (size_t)(k0 + r) * g.E1) & 1);
+          sum += stg[r * LEAF_SLOW_PITCH + off] * wcol[k0 + r];
+        }
+    }
+    __syncthreads();
+  }
+  if (tid < n_i1)
+    G[(size_t)c * g.ldF[g.mode_fast] + i0 + tid + g.off_fast] = sum;
 }
 
 } // namespace calsb200

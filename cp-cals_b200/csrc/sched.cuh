@@ -35,6 +35,7 @@ constexpr int ITER_LOG_CAP = 65536;
 // lane fills the gather list of its own model.  Then one thread per mode rebuilds that mode's MTTKRP plan if the column
 // count changed.
 __global__ void __launch_bounds__(32) sched_kernel(const SchedParams p) {
+  pdl_enter();
   SchedState *st = p.st;
   const int lane = threadIdx.x;
   __shared__ int sh_col, sh_nlive, sh_changed, sh_done, sh_C_before;
@@ -163,9 +164,14 @@ __global__ void __launch_bounds__(32) sched_kernel(const SchedParams p) {
     }
   }
   __syncwarp();
+  // A plan depends on the column count only, so it survives from run to run: a re-run with the same queue (every
+  // benchmark step, every call of a parameter sweep) finds its tables in place instead of spending ~0.1 ms of a single
+  // thread per mode on rebuilding them.
   const int C_now = sh_col;
-  if (C_now != sh_C_before && C_now > 0 && lane < p.plans.n_modes)
+  if (C_now > 0 && lane < p.plans.n_modes && p.plans.built_for[lane] != C_now) {
     mttkrp_make_plan(p.plans.plan[lane], p.plans.shape[lane], C_now, p.plans.G);
+    p.plans.built_for[lane] = C_now;
+  }
 }
 
 // Column mover.  grid = (ceil(buffer_cols / COLS_PER_CTA), n_modes, 2): z == 0 copies evicted columns old buffer ->
@@ -174,6 +180,7 @@ constexpr int MOVE_COLS = 4;
 __global__ void __launch_bounds__(256)
 move_kernel(const Geom geo, const FactorPtrs fac, const SchedState *__restrict__ st,
             const int *__restrict__ gather_src, const int *__restrict__ evict_dst) {
+  pdl_enter();
   if (!st->changed)
     return;
   const int n = blockIdx.y;

@@ -532,6 +532,7 @@ constexpr int STAT_SEGS = 8; // row segments per column in the column statistics
 template <bool NNLS>
 __global__ void __launch_bounds__(UPDATE_THREADS, 2)
 model_update_kernel(const UpdateParams p) {
+  pdl_enter();
   SchedState *st = p.st;
   if ((int)blockIdx.x >= st->n_live)
     return;

@@ -4,6 +4,9 @@
     tools/ncu_summary.py full  <report.ncu-rep> <out.json>     selected counters of every captured launch
     tools/ncu_summary.py list  <launches.csv>   <out.json>     per-kernel totals and shares of a launch list
                                                                (ncu --metrics gpu__time_duration.sum --csv)
+    tools/ncu_summary.py traffic <report.ncu-rep> <fingerprint file> <out.json>
+                                                               DRAM bytes per launch of the config-2 contractions,
+                                                               stamped with the kernel fingerprint (tools/refresh_traffic.sh)
 Runs where ncu is installed (no GPU needed: it only reads the report).
 """
 import csv
@@ -101,5 +104,36 @@ def launch_list(path, out):
         print("%-40s %6d launches %10.3f ms  %5.1f%%" % (k["kernel"], k["launches"], k["total_ms"], 100 * k["share"]))
 
 
+def traffic(report, fingerprint_file, out):
+    """profiles/traffic_r02.json: what bench.py's roofline.traffic reads (only while the fingerprint matches)."""
+    import datetime
+    import os
+    tmp = out + ".full.tmp"
+    full(report, tmp)
+    launches = json.load(open(tmp))["launches"]
+    os.remove(tmp)
+    fp = open(fingerprint_file).read().strip()
+    kernels, seen = [], set()
+    for l in launches:
+        name = l["kernel"]
+        if name in seen or "dram_bytes_per_launch" not in l:
+            continue
+        seen.add(name)
+        kernels.append({"kernel": name, "workload": "config2", "dram_bytes_per_launch": l["dram_bytes_per_launch"],
+                        "dram_read": l["dram__bytes_read.sum"], "dram_write": l["dram__bytes_write.sum"],
+                        "duration": l.get("gpu__time_duration.sum"),
+                        "dmma_pipe_pct": l.get("sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active"),
+                        "grid": l["grid"], "block": l["block"]})
+    json.dump({"kernel_fingerprint": fp, "captured": datetime.date.today().isoformat(),
+               "how": "tools/refresh_traffic.sh: ncu --set full --clock-control none of tools/ncu_target_cfg.py 2 1 3 "
+                      "(BASELINE config 2, 200 models, C = 2100), one launch per kernel; dram__bytes_read.sum + "
+                      "dram__bytes_write.sum", "kernels": kernels}, open(out, "w"), indent=1)
+    print("wrote", out, fp, [(k["kernel"], k["dram_bytes_per_launch"]) for k in kernels])
+
+
 if __name__ == "__main__":
-    {"full": full, "list": launch_list}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    cmd = sys.argv[1]
+    if cmd == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"full": full, "list": launch_list}[cmd](sys.argv[2], sys.argv[3])
