@@ -166,6 +166,7 @@ struct cals_b200_ctx {
   // one CALS iteration captured as a CUDA graph (the launch parameters do not change between iterations, nor between
   // runs that reuse the same allocations and options)
   cudaGraphExec_t iter_graph = nullptr;
+  cudaGraphExec_t batch_graph = nullptr; // the same, several iterations per launch
   std::vector<long long> iter_graph_key;
   long long alloc_generation = 0; // bumped whenever prepare_run (re)allocates
 
@@ -772,7 +773,10 @@ int ensure_dummy_state(cals_b200_ctx *c) {
 void drop_iteration_graph(cals_b200_ctx *c) {
   if (c->iter_graph)
     cudaGraphExecDestroy(c->iter_graph);
+  if (c->batch_graph)
+    cudaGraphExecDestroy(c->batch_graph);
   c->iter_graph = nullptr;
+  c->batch_graph = nullptr;
   c->iter_graph_key.clear();
 }
 
@@ -1387,11 +1391,16 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   // 52.7 k -> 48.1 k, config 1: 302 k -> 291 k model-iterations/s): the early-scheduled CTAs of the next kernel hold
   // shared memory and registers on the SMs the running kernel still uses, and graph kernel nodes already launch
   // back to back.  Never used with per-kernel timing, line search or the sliced-tensor exchange.
+  static const int graph_batch = [] { // CALS iterations per graph launch when the pass count is known (tuning knob)
+    const char *e = getenv("CALS_B200_GRAPH_BATCH");
+    const int v = e ? atoi(e) : 5;
+    return v < 1 ? 1 : (v > 64 ? 64 : v);
+  }();
   static const bool pdl_on = getenv("CALS_B200_PDL") != nullptr;
   c->pdl = use_graph && pdl_on && !c->ls_enabled;
   if (use_graph) {
     std::vector<long long> key = {c->alloc_generation, (long long)c->flags, c->ls_enabled, c->ls_method, c->variant,
-                                  (long long)max_live, fused_reduce ? 1 : 0, tree ? 1 : 0, c->pdl ? 1 : 0};
+                                  (long long)max_live, fused_reduce ? 1 : 0, tree ? 1 : 0, c->pdl ? 1 : 0, graph_batch};
     const bool same_graph = c->iter_graph && c->iter_graph_key.size() == key.size() + 1 &&
                             std::equal(key.begin(), key.end(), c->iter_graph_key.begin());
     if (!same_graph) {
@@ -1405,19 +1414,25 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
       for (int k = 0; tree && k < b.n_nodes; k++)
         if (b.node[k].slot >= 0 && ensure_dmma_attr(c, b.wm[b.node[k].slot]))
           return 1;
-      cudaGraph_t graph = nullptr;
-      CU_TRY(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      const int rc = enqueue_iteration(true);
-      cudaError_t ce = cudaStreamEndCapture(s, &graph);
-      if (rc < 0 || ce != cudaSuccess) {
-        if (graph)
-          cudaGraphDestroy(graph);
-        return rc < 0 ? 1 : fail(c, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+      // two graphs: one CALS iteration, and GRAPH_BATCH iterations back to back (used while the number of passes still
+      // to run is known to be at least that, see below)
+      for (int which = 0; which < 2; which++) {
+        cudaGraph_t graph = nullptr;
+        CU_TRY(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        for (int k = 0; k < (which == 0 ? 1 : graph_batch) && rc >= 0; k++)
+          rc = enqueue_iteration(true);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc < 0 || ce != cudaSuccess) {
+          if (graph)
+            cudaGraphDestroy(graph);
+          return rc < 0 ? 1 : fail(c, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+        }
+        ce = cudaGraphInstantiate(which == 0 ? &c->iter_graph : &c->batch_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess)
+          return fail(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
       }
-      ce = cudaGraphInstantiate(&c->iter_graph, graph, 0);
-      cudaGraphDestroy(graph);
-      if (ce != cudaSuccess)
-        return fail(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
       c->iter_graph_key = key;
       c->iter_graph_key.push_back(launches_per_iteration);
     } else {
@@ -1425,8 +1440,20 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     }
   }
 
+  // Forced iteration count with the whole queue resident from the first pass (the benchmark protocol, parameter sweeps):
+  // the loop runs exactly max_iter + 1 passes (the last one only evicts), so the host can replay batches of passes per
+  // graph launch and stop on the dot instead of running RA - 1 empty passes ahead of the `done` flag.
+  long long known_passes = -1, n_submits = 0;
+  if ((c->flags & CALS_B200_FORCE_MAX_ITER) && !(c->flags & CALS_B200_ALWAYS_EVICT_FIRST) &&
+      c->total_cols <= c->buffer_cols && !c->ls_enabled)
+    known_passes = (long long)c->max_iter + 1;
   for (;; it++) {
-    if (use_graph) {
+    if (use_graph && known_passes > 0 && it + graph_batch <= known_passes && graph_batch > 1) {
+      CU_TRY(c, cudaGraphLaunch(c->batch_graph, s));
+      launches += (uint64_t)launches_per_iteration * graph_batch;
+      mttkrp_launches += (uint64_t)N * (graph_batch - 1);
+      it += graph_batch - 1;
+    } else if (use_graph) {
       CU_TRY(c, cudaGraphLaunch(c->iter_graph, s));
       launches += launches_per_iteration;
     } else {
@@ -1436,9 +1463,12 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
       launches += rc;
     }
     mttkrp_launches += N;
-    CU_TRY(c, cudaEventRecord(ring[it % RA], s));
-    if (it >= RA - 1)
-      CU_TRY(c, cudaEventSynchronize(ring[(it + 1) % RA]));
+    CU_TRY(c, cudaEventRecord(ring[n_submits % RA], s));
+    if (n_submits >= RA - 1)
+      CU_TRY(c, cudaEventSynchronize(ring[(n_submits + 1) % RA]));
+    n_submits++;
+    if (known_passes > 0 && use_graph && it + 1 >= known_passes)
+      break; // every pass has been enqueued; the synchronisation below waits for the last one
     if (*(volatile int *)&c->h_flags[0])
       break;
     if (c->timing && ev_next > 100000) {
