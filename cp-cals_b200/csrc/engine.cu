@@ -1156,31 +1156,32 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     u.rows = geo.dims[n];
     u.ld = geo.ldF[n];
     const int R = c->max_rank;
-    size_t fixed = ((size_t)2 * R * R + 4 * R + 64 + 2 * STAT_SEGS * R) * 8; // H, Gramian / block inverses, column
-    // statistics, 1 / diag(L), diag(H), reduction scratch, statistics candidates
+    const int R8 = round_up_int(R, 8); // the small matrices and the staged chunk are zero-padded to a multiple of 8
+    size_t fixed = ((size_t)2 * R8 * R8 + 4 * R + 64 + 2 * STAT_SEGS * R) * 8; // H / L, block inverses / Gramian,
+    // column statistics, 1 / diag(L), diag(H), reduction scratch, statistics candidates
     const size_t budget = 200 * 1024;
     u.nnls = (c->flags & CALS_B200_NNLS) ? 1 : 0;
     u.nnls_warps = 0;
     if (u.nnls) { // per working warp: 5R + R*R doubles and 2R + 1 ints of scratch
       const size_t per_warp = ((size_t)5 * R + (size_t)R * R + (size_t)(2 * R + 2) / 2 + 1) * 8;
       int nw = UPDATE_THREADS / 32;
-      while (nw > 1 && fixed + nw * per_warp + (size_t)36 * R * 8 > budget)
+      while (nw > 1 && fixed + nw * per_warp + (size_t)36 * R8 * 8 > budget)
         nw >>= 1;
       u.nnls_warps = nw;
       fixed += nw * per_warp;
     }
-    if (fixed + (size_t)36 * R * 8 > budget)
+    if (fixed + (size_t)36 * R8 * 8 > budget)
       return fail(c, "rank %d too large for the shared-memory update kernel", R);
     int cr = round_up_int(u.rows, 32);
     // behind the staged chunk: tile lookup tables of the fused reduction, (R + chunk rows) ints
     auto tables = [&](int rows_) { return (size_t)((R + rows_ + 1) / 2 + 1) * 8; };
-    while (fixed + (size_t)(cr + 4) * R * 8 + tables(cr) > budget)
+    while (fixed + (size_t)(cr + 4) * R8 * 8 + tables(cr) > budget)
       cr -= 32;
     if (cr < 32)
       return fail(c, "rank %d too large for the shared-memory update kernel", R);
     u.chunk_rows = cr;
     u.chunk_pitch = cr + 4; // = 4 mod 16 doubles: the DMMA fragment loads of the update kernel are bank-conflict free
-    u.table_off = (int)((fixed + (size_t)(cr + 4) * R * 8) / 8);
+    u.table_off = (int)((fixed + (size_t)(cr + 4) * R8 * 8) / 8);
     u.max_rank = R;
     u.G = b.G;
     u.F[0] = b.fac.buf[0][n];
@@ -1202,7 +1203,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     for (int k = 0; k < n; k++)
       u.rows_before += geo.dims[k];
     u.prof = c->d_update_prof ? c->d_update_prof + (size_t)n * max_live * 16 : nullptr;
-    up_smem[n] = fixed + (size_t)(cr + 4) * R * 8 + tables(cr);
+    up_smem[n] = fixed + (size_t)(cr + 4) * R8 * 8 + tables(cr);
   }
   {
     size_t mx = 0;

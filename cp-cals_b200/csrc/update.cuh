@@ -114,7 +114,7 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 
 // Solve H_pp x = y_p for the passive set (dposv('L'), reference src/utils/update.cpp:18-46).  Returns the size of the
 // passive set, or -1 when the Cholesky meets a non-positive pivot (CholFail).
-__device__ int nnls_solve_passive(const double *H, int R, const NnlsScratch &q, int lane) {
+__device__ int nnls_solve_passive(const double *H, int ldh, int R, const NnlsScratch &q, int lane) {
   __syncwarp();
   if (lane == 0) {
     int p = 0;
@@ -128,7 +128,7 @@ __device__ int nnls_solve_passive(const double *H, int R, const NnlsScratch &q, 
   double *Gp = q.Gp, *sp = q.sp;
   for (int e = lane; e < p * p; e += 32) {
     const int a = e % p, b = e / p;
-    Gp[a + b * p] = H[q.map[a] + q.map[b] * R];
+    Gp[a + b * p] = H[q.map[a] + q.map[b] * ldh];
   }
   for (int a = lane; a < p; a += 32)
     sp[a] = q.y[q.map[a]];
@@ -193,11 +193,11 @@ __device__ __forceinline__ int nnls_count_passive(int R, const NnlsScratch &q, i
     n += !q.act[i];
   return warp_sum_int(n);
 }
-__device__ __forceinline__ void nnls_multipliers(const double *H, int R, const NnlsScratch &q, int lane) {
+__device__ __forceinline__ void nnls_multipliers(const double *H, int ldh, int R, const NnlsScratch &q, int lane) {
   for (int i = lane; i < R; i += 32) { // w = y - H d   (reference src/utils/update.cpp:49-57)
     double t = 0.0;
     for (int j = 0; j < R; j++)
-      t += H[i + j * R] * q.d[j];
+      t += H[i + j * ldh] * q.d[j];
     q.w[i] = q.y[i] - t;
   }
   __syncwarp();
@@ -206,7 +206,7 @@ __device__ __forceinline__ void nnls_multipliers(const double *H, int R, const N
 // One row: y = the row of the MTTKRP result in S (pitch `pitch`), result written back to S, active set updated in
 // `arow` (global memory).  Returns 1 when a passive-block Cholesky failed inside the main loop or an iteration cap was
 // hit (the reference has no caps; they only guard the GPU against a non-terminating corner case).
-__device__ int nnls_row(const double *H, int R, double tol, double *Srow, int pitch, unsigned char *arow,
+__device__ int nnls_row(const double *H, int ldh, int R, double tol, double *Srow, int pitch, unsigned char *arow,
                         const NnlsScratch &q, int lane) {
   int any = 0;
   for (int i = lane; i < R; i += 32) {
@@ -223,7 +223,7 @@ __device__ int nnls_row(const double *H, int R, double tol, double *Srow, int pi
   __syncwarp();
   int p = 0;
   if (any) { // warm start from the previous active set (reference :88-117)
-    p = nnls_solve_passive(H, R, q, lane);
+    p = nnls_solve_passive(H, ldh, R, q, lane);
     bool failed = p < 0;
     for (int guard = 0; !failed; guard++) {
       nnls_scatter(q.d, R, p, q, lane);
@@ -239,7 +239,7 @@ __device__ int nnls_row(const double *H, int R, double tol, double *Srow, int pi
         failed = true;
         break;
       }
-      p = nnls_solve_passive(H, R, q, lane);
+      p = nnls_solve_passive(H, ldh, R, q, lane);
       failed = p < 0;
     }
     if (failed) {
@@ -250,7 +250,7 @@ __device__ int nnls_row(const double *H, int R, double tol, double *Srow, int pi
       __syncwarp();
     }
   }
-  nnls_multipliers(H, R, q, lane);
+  nnls_multipliers(H, ldh, R, q, lane);
   int trouble = 0;
   for (int outer = 0;; outer++) { // main loop (reference :122-170)
     double best = -1.7976931348623157e308;
@@ -277,7 +277,7 @@ __device__ int nnls_row(const double *H, int R, double tol, double *Srow, int pi
     }
     if (lane == 0)
       q.act[bi] = 0;
-    p = nnls_solve_passive(H, R, q, lane);
+    p = nnls_solve_passive(H, ldh, R, q, lane);
     if (p < 0) {
       trouble = 1;
       break;
@@ -303,7 +303,7 @@ __device__ int nnls_row(const double *H, int R, double tol, double *Srow, int pi
         bad = true;
         break;
       }
-      p = nnls_solve_passive(H, R, q, lane);
+      p = nnls_solve_passive(H, ldh, R, q, lane);
       if (p < 0) {
         bad = true;
         break;
@@ -314,7 +314,7 @@ __device__ int nnls_row(const double *H, int R, double tol, double *Srow, int pi
       break;
     }
     nnls_scatter(q.d, R, p, q, lane);
-    nnls_multipliers(H, R, q, lane);
+    nnls_multipliers(H, ldh, R, q, lane);
   }
   for (int i = lane; i < R; i += 32) {
     Srow[i * pitch] = q.d[i];
@@ -335,8 +335,41 @@ __device__ int nnls_row(const double *H, int R, double tol, double *Srow, int pi
 // the diagonal s_j comes from lane 0 by shuffle, one reciprocal square root per column, L[i][j] = s_i * rinv.
 // inv[j] = 1 / L[j][j].  The strict upper triangle of Hs keeps H.  Returns 1 when a pivot is not positive (dpotrf's
 // info > 0; the reference only logs it and carries on, src/utils/update.cpp:183-185).
-__device__ __forceinline__ int cholesky_warp(double *Hs, double *inv, int R, int lane) {
+// The R x R matrices of this kernel (H / L, the diagonal-block inverses / the new Gramian) live in shared memory with
+// leading dimension LD = R rounded up to 8 and zeros in the padding, so that the tensor-core loops below need no masks.
+__device__ __forceinline__ int cholesky_warp(double *Hs, int LD, double *inv, int R, int lane) {
   int fail = 0;
+  if (R <= 32) { // one row per lane, no pass loop
+    const int i = lane;
+    const double *li = Hs + i;
+#pragma unroll 1
+    for (int j = 0; j < R; j++) {
+      const double *lj = Hs + j;
+      double a0 = 0.0, a1 = 0.0;
+      if (i >= j && i < R) {
+        a0 = li[j * LD];
+        int k = 0;
+#pragma unroll 2
+        for (; k + 2 <= j; k += 2) {
+          a0 -= li[k * LD] * lj[k * LD];
+          a1 -= li[(k + 1) * LD] * lj[(k + 1) * LD];
+        }
+        if (k < j)
+          a0 -= li[k * LD] * lj[k * LD];
+      }
+      const double si = a0 + a1;
+      const double d = __shfl_sync(0xffffffffu, si, j); // lane j holds the diagonal
+      if (!(d > 0.0))
+        fail = 1;
+      const double rinv = rsqrt(d);
+      if (i >= j && i < R)
+        Hs[i + j * LD] = si * rinv; // the diagonal becomes d * rsqrt(d) = sqrt(d)
+      if (i == j)
+        inv[j] = rinv;
+      __syncwarp();
+    }
+    return fail;
+  }
 #pragma unroll 1
   for (int j = 0; j < R; j++) {
     double rinv = 0.0;
@@ -345,16 +378,16 @@ __device__ __forceinline__ int cholesky_warp(double *Hs, double *inv, int R, int
       const int i = i0 + lane;
       double a0 = 0.0, a1 = 0.0;
       if (i < R) {
-        a0 = Hs[i + j * R];
+        a0 = Hs[i + j * LD];
         const double *li = Hs + i, *lj = Hs + j;
         int k = 0;
 #pragma unroll 2
         for (; k + 2 <= j; k += 2) {
-          a0 -= li[k * R] * lj[k * R];
-          a1 -= li[(k + 1) * R] * lj[(k + 1) * R];
+          a0 -= li[k * LD] * lj[k * LD];
+          a1 -= li[(k + 1) * LD] * lj[(k + 1) * LD];
         }
         if (k < j)
-          a0 -= li[k * R] * lj[k * R];
+          a0 -= li[k * LD] * lj[k * LD];
       }
       const double si = a0 + a1;
       if (i0 == j) { // the pass that holds the diagonal (lane 0)
@@ -366,7 +399,7 @@ __device__ __forceinline__ int cholesky_warp(double *Hs, double *inv, int R, int
           inv[j] = rinv;
       }
       if (i < R)
-        Hs[i + j * R] = si * rinv; // the diagonal becomes d * rsqrt(d) = sqrt(d)
+        Hs[i + j * LD] = si * rinv;
     }
     __syncwarp();
   }
@@ -374,15 +407,17 @@ __device__ __forceinline__ int cholesky_warp(double *Hs, double *inv, int R, int
 }
 
 // Inverses of the 8 x 8 diagonal blocks of L, D_b = (L_bb)^-1 (lower triangular), written to the same positions of Di
-// (ld = R).  Lane (blk, c) owns column c of block blk, four blocks per pass; the depth is 7 steps whatever the rank.
+// (ld = LD; everything else in Di stays zero).  Lane (blk, c) owns column c of block blk, four blocks per pass; the
+// depth is 7 steps whatever the rank.
 //   D[c][c] = inv[c],   D[i][c] = -inv[i] * sum_{k=c}^{i-1} L[i][k] D[k][c]
-__device__ __forceinline__ void diag_block_inverses_warp(const double *L, const double *inv, double *Di, int R, int lane) {
+__device__ __forceinline__ void diag_block_inverses_warp(const double *L, int LD, const double *inv, double *Di, int R,
+                                                         int lane) {
   const int NB = (R + 7) >> 3;
 #pragma unroll 1
   for (int b0 = 0; b0 < NB; b0 += 4) {
     const int b = b0 + (lane >> 3), c = 8 * b + (lane & 7);
     if (b < NB && c < R) {
-      double *x = Di + (size_t)c * R;
+      double *x = Di + (size_t)c * LD;
       x[c] = inv[c];
       const int i_end = min(8 * b + 8, R);
 #pragma unroll 1
@@ -390,7 +425,7 @@ __device__ __forceinline__ void diag_block_inverses_warp(const double *L, const 
         double acc = 0.0;
 #pragma unroll 1
         for (int k = c; k < i; k++)
-          acc += L[i + k * R] * x[k];
+          acc += L[i + k * LD] * x[k];
         x[i] = -acc * inv[i];
       }
     }
@@ -399,28 +434,28 @@ __device__ __forceinline__ void diag_block_inverses_warp(const double *L, const 
 }
 
 // F = G H^-1 = (G L^-T) L^-1 for the rows staged in S (column-major, pitch = 4 mod 16 doubles so that the A fragments
-// are bank-conflict free), in place, as a blocked triangular solve on the FP64 tensor cores (mma.sync m8n8k4): with
-// 8-column blocks,
+// are bank-conflict free; columns R .. LD-1 zeroed), in place, as a blocked triangular solve on the FP64 tensor cores
+// (mma.sync m8n8k4): with 8-column blocks,
 //   forward   Y_b = (G_b - sum_{a<b} Y_a L_ba^T) D_b^T          b = 0 .. NB-1
 //   backward  X_b = (Y_b - sum_{a>b} X_a L_ab  ) D_b            b = NB-1 .. 0
 // Per-row substitution (thread per row) moves 16 bytes of shared memory per FMA and is bound by that pipe (measured
 // 18.7 k cycles for 200 x 20); a DMMA moves 2.  Only the 8 x 8 diagonal blocks are inverted, so every product has the
 // forward error of an 8 x 8 substitution.  Warp w owns the m8 row groups w, w + nw, ..; four of them are worked on at a
-// time (independent accumulators, one B fragment for all four).
+// time (independent accumulators, one B fragment for all four).  The loops carry no masks: the matrices are zero-padded
+// to LD, rows of the last m8 group beyond nr compute garbage that nothing reads (rows of an MMA are independent).
 constexpr int SOLVE_MB = 4;
-__device__ __forceinline__ void solve_rows_dmma(double *S, int pitch, int nr, const double *L, const double *Di, int R,
+__device__ __forceinline__ void solve_rows_dmma(double *S, int pitch, int nr, const double *L, const double *Di, int LD,
                                                 int warp, int nw, int lane) {
   const int r = lane >> 2, s = lane & 3;
-  const int MG = (nr + 7) >> 3, NB = (R + 7) >> 3;
+  const int MG = (nr + 7) >> 3, NB = LD >> 3;
 #pragma unroll 1
   for (int mg0 = warp; mg0 < MG; mg0 += SOLVE_MB * nw) {
     double *Srow[SOLVE_MB];
     bool ok[SOLVE_MB];
 #pragma unroll
     for (int g = 0; g < SOLVE_MB; g++) {
-      const int row = 8 * (mg0 + g * nw) + r;
-      ok[g] = (mg0 + g * nw) < MG && row < nr;
-      Srow[g] = S + (ok[g] ? row : 0);
+      ok[g] = (mg0 + g * nw) < MG;
+      Srow[g] = S + 8 * (ok[g] ? mg0 + g * nw : mg0) + r; // a group beyond MG recomputes the first one, nothing stored
     }
 #pragma unroll 1
     for (int dir = 0; dir < 2; dir++) { // 0: forward over L^T, 1: backward over L
@@ -432,54 +467,46 @@ __device__ __forceinline__ void solve_rows_dmma(double *S, int pitch, int nr, co
         for (int g = 0; g < SOLVE_MB; g++)
           c0[g] = c1[g] = 0.0;
         // blocks already solved: a < b (forward), a > b (backward)
-        const int a_lo = dir == 0 ? 0 : b + 1, a_hi = dir == 0 ? b : NB;
+        const int k_lo = dir == 0 ? 0 : 8 * (b + 1), k_hi = dir == 0 ? 8 * b : LD;
         const int nb = 8 * b + r; // this lane's column of the B fragment
+        // forward: B[k][n] = L[8b+n][k] -> L + nb + k * LD;  backward: B[k][n] = L[k][8b+n] -> L + k + nb * LD
+        const double *bp = dir == 0 ? L + nb + (k_lo + s) * LD : L + (k_lo + s) + nb * LD;
+        const int bstep = dir == 0 ? 4 * LD : 4;
 #pragma unroll 1
-        for (int k0 = 8 * a_lo; k0 < 8 * a_hi; k0 += 4) {
-          const int k = k0 + s;
-          // forward: B[k][n] = L[8b+n][k];  backward: B[k][n] = L[k][8b+n]
-          const double bf = (k < R && nb < R) ? (dir == 0 ? L[nb + k * R] : L[k + nb * R]) : 0.0;
+        for (int k = k_lo + s; k < k_hi; k += 4, bp += bstep) {
+          const double bf = *bp;
 #pragma unroll
           for (int g = 0; g < SOLVE_MB; g++)
-            dmma_m8n8k4(c0[g], c1[g], (ok[g] && k < R) ? Srow[g][k * pitch] : 0.0, bf);
+            dmma_m8n8k4(c0[g], c1[g], Srow[g][k * pitch], bf);
         }
         // T = (G_b or Y_b) - C, written back in place (accumulator layout: row r, columns 2s, 2s + 1)
         const int col = 8 * b + 2 * s;
 #pragma unroll
         for (int g = 0; g < SOLVE_MB; g++)
           if (ok[g]) {
-            if (col < R)
-              Srow[g][col * pitch] -= c0[g];
-            if (col + 1 < R)
-              Srow[g][(col + 1) * pitch] -= c1[g];
+            Srow[g][col * pitch] -= c0[g];
+            Srow[g][(col + 1) * pitch] -= c1[g];
           }
         __syncwarp();
-        // times the inverse of the diagonal block: forward B[k][n] = D[n][k] (k <= n), backward B[k][n] = D[k][n] (k >= n)
+        // times the inverse of the diagonal block: forward B[k][n] = D[n][k], backward B[k][n] = D[k][n] (the other
+        // triangle of the block is zero)
 #pragma unroll
         for (int g = 0; g < SOLVE_MB; g++)
           c0[g] = c1[g] = 0.0;
 #pragma unroll
         for (int kk = 0; kk < 2; kk++) {
-          const int kl = 4 * kk + s, k = 8 * b + kl;
-          double bf = 0.0;
-          if (k < R && nb < R) {
-            if (dir == 0 && kl <= r)
-              bf = Di[nb + k * R];
-            if (dir == 1 && kl >= r)
-              bf = Di[k + nb * R];
-          }
+          const int k = 8 * b + 4 * kk + s;
+          const double bf = dir == 0 ? Di[nb + k * LD] : Di[k + nb * LD];
 #pragma unroll
           for (int g = 0; g < SOLVE_MB; g++)
-            dmma_m8n8k4(c0[g], c1[g], (ok[g] && k < R) ? Srow[g][k * pitch] : 0.0, bf);
+            dmma_m8n8k4(c0[g], c1[g], Srow[g][k * pitch], bf);
         }
         __syncwarp(); // every lane has read T before it is overwritten
 #pragma unroll
         for (int g = 0; g < SOLVE_MB; g++)
           if (ok[g]) {
-            if (col < R)
-              Srow[g][col * pitch] = c0[g];
-            if (col + 1 < R)
-              Srow[g][(col + 1) * pitch] = c1[g];
+            Srow[g][col * pitch] = c0[g];
+            Srow[g][(col + 1) * pitch] = c1[g];
           }
         __syncwarp();
       }
@@ -487,12 +514,13 @@ __device__ __forceinline__ void solve_rows_dmma(double *S, int pitch, int nr, co
   }
 }
 
-// Gs += F^T F for the rows staged in S, on the FP64 tensor cores: the 8 x 8 tiles of the lower block triangle
-// (ti >= tj) are dealt to the warps; a tile's k loop runs over the rows with two accumulator pairs.  The scalar version
-// (thread per entry) reads two shared-memory operands per FMA and is bound by that pipe (8.6 k cycles for 200 x 20).
-__device__ __forceinline__ void gram_dmma(const double *S, int pitch, int nr, double *Gs, int R, int warp, int nw,
+// Gs += F^T F for the rows staged in S (pad columns zero), on the FP64 tensor cores: the 8 x 8 tiles of the lower block
+// triangle (ti >= tj) are dealt to the warps; a tile's k loop runs over the rows with two accumulator pairs.  The scalar
+// version (thread per entry) reads two shared-memory operands per FMA and is bound by that pipe (8.6 k cycles for
+// 200 x 20).
+__device__ __forceinline__ void gram_dmma(const double *S, int pitch, int nr, double *Gs, int LD, int warp, int nw,
                                           int lane) {
-  const int r = lane >> 2, s = lane & 3, NT = (R + 7) >> 3;
+  const int r = lane >> 2, s = lane & 3, NT = LD >> 3;
   const int n_tiles = NT * (NT + 1) / 2;
 #pragma unroll 1
   for (int t = warp; t < n_tiles; t += nw) {
@@ -500,30 +528,22 @@ __device__ __forceinline__ void gram_dmma(const double *S, int pitch, int nr, do
     while ((ti + 1) * (ti + 2) / 2 <= t)
       ti++;
     const int tj = t - ti * (ti + 1) / 2;
-    const int ia = 8 * ti + r, jb = 8 * tj + r;
-    const bool oka = ia < R, okb = jb < R;
-    const double *pa = S + (size_t)(oka ? ia : 0) * pitch, *pb = S + (size_t)(okb ? jb : 0) * pitch;
+    const double *pa = S + (size_t)(8 * ti + r) * pitch + s, *pb = S + (size_t)(8 * tj + r) * pitch + s;
     double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
     int k0 = 0;
 #pragma unroll 2
     for (; k0 + 8 <= nr; k0 += 8) {
-      const int k = k0 + s;
-      dmma_m8n8k4(c0, c1, oka ? pa[k] : 0.0, okb ? pb[k] : 0.0);
-      dmma_m8n8k4(d0, d1, oka ? pa[k + 4] : 0.0, okb ? pb[k + 4] : 0.0);
+      dmma_m8n8k4(c0, c1, pa[k0], pb[k0]);
+      dmma_m8n8k4(d0, d1, pa[k0 + 4], pb[k0 + 4]);
     }
 #pragma unroll 1
     for (; k0 < nr; k0 += 4) {
-      const int k = k0 + s;
-      const bool okk = k < nr;
-      dmma_m8n8k4(c0, c1, (oka && okk) ? pa[k] : 0.0, (okb && okk) ? pb[k] : 0.0);
+      const bool okk = k0 + s < nr;
+      dmma_m8n8k4(c0, c1, okk ? pa[k0] : 0.0, okk ? pb[k0] : 0.0);
     }
-    const int gi = 8 * ti + r, gj = 8 * tj + 2 * s;
-    if (gi < R) {
-      if (gj < R)
-        Gs[gi + gj * R] += c0 + d0;
-      if (gj + 1 < R)
-        Gs[gi + (gj + 1) * R] += c1 + d1;
-    }
+    double *gp = Gs + (8 * ti + r) + (8 * tj + 2 * s) * LD;
+    gp[0] += c0 + d0;
+    gp[LD] += c1 + d1;
   }
 }
 
@@ -546,9 +566,10 @@ model_update_kernel(const UpdateParams p) {
 
   CALS_PROF(0);
   extern __shared__ double sm[];
-  double *Hs = sm;                 // R x R : H; the Cholesky factor takes its lower triangle, the strict upper keeps H
-  double *Gs = Hs + R * R;         // R x R : inverses of L's diagonal blocks during pass 1, then the new Gramian
-  double *cstat = Gs + R * R;      // 2R : per column reduction value / index ; then lambda, 1/lambda
+  const int LD = (R + 7) & ~7;     // leading dimension of the small matrices (zero padding beyond R)
+  double *Hs = sm;                 // LD x LD : H; the Cholesky factor takes its lower triangle, the strict upper keeps H
+  double *Gs = Hs + LD * LD;       // LD x LD : inverses of L's diagonal blocks during pass 1, then the new Gramian
+  double *cstat = Gs + LD * LD;    // 2R : per column reduction value / index ; then lambda, 1/lambda
   double *inv = cstat + 2 * R;     // R : 1 / L[j][j]
   double *hdiag = inv + R;         // R : diagonal of H (overwritten in Hs by the factorisation)
   double *red = hdiag + R;         // 64
@@ -556,7 +577,7 @@ model_update_kernel(const UpdateParams p) {
   double *S = cand + 2 * STAT_SEGS * R; // chunk_rows x R, pitch chunk_pitch
   const int pitch = p.chunk_pitch, CR = p.chunk_rows;
   // NNLS scratch (only allocated when p.nnls): per working warp 5R + R*R doubles and 2R + 1 ints, behind S
-  double *nn_base = S + (size_t)pitch * p.max_rank;
+  double *nn_base = S + (size_t)pitch * ((p.max_rank + 7) & ~7);
   // tile lookup tables of the fused partial-tile reduction: R + chunk_rows ints at the very end of the allocation
   int *cinfo = reinterpret_cast<int *>(sm + p.table_off);
   int *rinfo = cinfo + p.max_rank;
@@ -569,17 +590,20 @@ model_update_kernel(const UpdateParams p) {
 
   // ---- H = hadamard of the other Gramians ----
 #pragma unroll 1
-  for (int e = tid; e < R * R; e += nthr) {
-    double h = 1.0;
+  for (int e = tid; e < LD * LD; e += nthr) {
+    const int i = e % LD, j = e / LD;
+    double h = 0.0;
+    if (i < R && j < R) {
+      h = 1.0;
 #pragma unroll 1
-    for (int k = 0; k < N; k++)
-      if (k != n)
-        h *= grams[(size_t)k * R * R + e];
+      for (int k = 0; k < N; k++)
+        if (k != n)
+          h *= grams[(size_t)k * R * R + i + j * R];
+      if (i == j)
+        hdiag[i] = h;
+    }
     Hs[e] = h;
     Gs[e] = 0.0;
-    const int i = e % R;
-    if (i * R + i == e)
-      hdiag[i] = h;
   }
   for (int e = tid; e < 2 * R; e += nthr) // value: a sum of squares starts at 0, a max-abs at -1; then the index
     cstat[e] = (e < R) ? (iters == 1 ? 0.0 : -1.0) : 0.0;
@@ -599,7 +623,7 @@ model_update_kernel(const UpdateParams p) {
     for (int j = tid; j < R; j += nthr) {
       double cs = 0.0;
       for (int i = 0; i < R; i++)
-        cs += fabs(Hs[i + j * R]);
+        cs += fabs(Hs[i + j * LD]);
       mx = fmax(mx, cs);
     }
 #pragma unroll
@@ -637,8 +661,8 @@ model_update_kernel(const UpdateParams p) {
     // the diagonal blocks of L); the other warps stage.
     const bool overlap = r0 == 0 && !NNLS;
     if (overlap && warp == 0) {
-      chol_fail = cholesky_warp(Hs, inv, R, lane);
-      diag_block_inverses_warp(Hs, inv, Gs, R, lane);
+      chol_fail = cholesky_warp(Hs, LD, inv, R, lane);
+      diag_block_inverses_warp(Hs, LD, inv, Gs, R, lane);
       CALS_PROF(2);
     } else if (fused) {
       // Fused reduction: the result is not read from G but summed here, per (m,n) pair in segment order with four
@@ -689,6 +713,11 @@ model_update_kernel(const UpdateParams p) {
           sj[rr] = gj[rr];
       }
     }
+    if (!(overlap && warp == 0)) { // columns R .. LD-1 of the staged chunk: zero (the tensor-core loops read them)
+      const int t0 = overlap ? tid - 32 : tid, tn = overlap ? nthr - 32 : nthr;
+      for (int e = t0; e < (LD - R) * nr; e += tn)
+        S[(e % nr) + (R + e / nr) * pitch] = 0.0;
+    }
     __syncthreads();
     CALS_PROF(3);
     if (NNLS) { // warp per row, active sets warm-started from the previous iteration
@@ -707,12 +736,12 @@ model_update_kernel(const UpdateParams p) {
         unsigned char *act = p.act_pool + md.act_off + (size_t)p.rows_before * R;
         int trouble = 0;
         for (int rr = warp; rr < nr; rr += p.nnls_warps)
-          trouble += nnls_row(Hs, R, nnls_tol, S + rr, pitch, act + (size_t)(r0 + rr) * R, q, lane);
+          trouble += nnls_row(Hs, LD, R, nnls_tol, S + rr, pitch, act + (size_t)(r0 + rr) * R, q, lane);
         if (trouble && lane == 0)
           chol_fail = 1;
       }
     } else {
-      solve_rows_dmma(S, pitch, nr, Hs, Gs, R, warp, nw, lane);
+      solve_rows_dmma(S, pitch, nr, Hs, Gs, LD, warp, nw, lane);
     }
     __syncthreads();
     CALS_PROF(4);
@@ -781,7 +810,7 @@ model_update_kernel(const UpdateParams p) {
   CALS_PROF(5);
 
   // ---- lambda ----
-  for (int e = tid; e < R * R; e += nthr) // the block inverses are done with; from here on the new Gramian accumulates
+  for (int e = tid; e < LD * LD; e += nthr) // the block inverses are done with; from here on the new Gramian accumulates
     Gs[e] = 0.0;
   for (int j = tid; j < R; j += nthr) {
     double lam;
@@ -823,13 +852,13 @@ model_update_kernel(const UpdateParams p) {
     }
     __syncthreads();
     CALS_PROF(7);
-    gram_dmma(S, pitch, nr, Gs, R, warp, nw, lane);
+    gram_dmma(S, pitch, nr, Gs, LD, warp, nw, lane);
   }
   __syncthreads();
   CALS_PROF(8);
   for (int e = tid; e < R * R; e += nthr) { // mirror, then publish
     const int i = e % R, j = e / R;
-    const double v = (i >> 3) >= (j >> 3) ? Gs[i + j * R] : Gs[j + i * R]; // tiles of the lower block triangle
+    const double v = (i >> 3) >= (j >> 3) ? Gs[i + j * LD] : Gs[j + i * LD]; // tiles of the lower block triangle
     grams[(size_t)n * R * R + e] = v;
   }
   if (__syncthreads_or(chol_fail) && tid == 0)
@@ -847,9 +876,9 @@ model_update_kernel(const UpdateParams p) {
   double term2 = 0.0;
   for (int e = tid; e < R * R; e += nthr) {
     const int i = e % R, j = e / R;
-    const double gn = (i >> 3) >= (j >> 3) ? Gs[i + j * R] : Gs[j + i * R];
-    const double h = i == j ? hdiag[i] : (i < j ? Hs[i + j * R] : Hs[j + i * R]);
-    term2 += cstat[i] * cstat[j] * (NNLS ? Hs[e] : h) * gn;
+    const double gn = (i >> 3) >= (j >> 3) ? Gs[i + j * LD] : Gs[j + i * LD];
+    const double h = i == j ? hdiag[i] : (i < j ? Hs[i + j * LD] : Hs[j + i * LD]);
+    term2 += cstat[i] * cstat[j] * h * gn;
   }
   // both sums with one pass through shared memory
 #pragma unroll
