@@ -1288,10 +1288,16 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   auto t0 = std::chrono::steady_clock::now();
   CU_TRY(c, cudaEventRecord(ev_begin, s));
   long long it = 0;
+  bool capturing_timed = false;
   auto mark = [&]() -> size_t { // no-op unless timing is on
     if (!c->timing)
       return 0;
-    cudaEventRecord(get_event(c, ev_next), s);
+    // inside a stream capture only an EXTERNAL record becomes an event-record node of the graph (a plain record is
+    // an internal fork / join dependency and never fires at replay)
+    if (capturing_timed)
+      cudaEventRecordWithFlags(get_event(c, ev_next), s, cudaEventRecordExternal);
+    else
+      cudaEventRecord(get_event(c, ev_next), s);
     return ev_next++;
   };
   auto window = [&](size_t e0, size_t e1, int kind) {
@@ -1399,6 +1405,46 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   }();
   static const bool pdl_on = getenv("CALS_B200_PDL") != nullptr;
   c->pdl = use_graph && pdl_on && !c->ls_enabled;
+  // function attributes must be set outside of a capture: launch_dmma does it lazily, so trigger it here
+  auto prepare_capture = [&]() -> int {
+    for (int n = 0; n < N; n++)
+      if (c->variant == CALS_B200_MTTKRP_DMMA && ensure_dmma_attr(c, b.wm[n]))
+        return 1;
+    if (tree && b.node[0].slot < 0 && launch_pair_gemm(c, b, true))
+      return 1;
+    for (int k = 0; tree && k < b.n_nodes; k++)
+      if (b.node[k].slot >= 0 && ensure_dmma_attr(c, b.wm[b.node[k].slot]))
+        return 1;
+    return 0;
+  };
+  // Per-kernel timing inside a graph: the events between the kernels are captured as event-record nodes of a
+  // one-iteration graph, which is replayed pass by pass with a synchronisation (and a read of the windows) after each.
+  // The kernels then follow each other as closely as in the untimed replay; with plain stream launches every event and
+  // every launch adds microseconds of idle time, which inflates the windows of short kernels (a 140 us contraction of an
+  // 8-way shard was reported as 175 us).
+  const bool timed_graph = c->timing && !exchange && !graphs_off && !c->ls_enabled;
+  cudaGraphExec_t tgraph = nullptr;
+  double tsum[5] = {0, 0, 0, 0, 0};
+  if (timed_graph) {
+    if (prepare_capture())
+      return 1;
+    get_event(c, ev_next + 16 * (size_t)(N + 2)); // create the events of one iteration before the capture begins
+    cudaGraph_t graph = nullptr;
+    CU_TRY(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    capturing_timed = true;
+    const int rc = enqueue_iteration(true);
+    capturing_timed = false;
+    cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (rc < 0 || ce != cudaSuccess) {
+      if (graph)
+        cudaGraphDestroy(graph);
+      return rc < 0 ? 1 : fail(c, "cudaStreamEndCapture (timed) failed: %s", cudaGetErrorString(ce));
+    }
+    ce = cudaGraphInstantiate(&tgraph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess)
+      return fail(c, "cudaGraphInstantiate (timed) failed: %s", cudaGetErrorString(ce));
+  }
   if (use_graph) {
     std::vector<long long> key = {c->alloc_generation, (long long)c->flags, c->ls_enabled, c->ls_method, c->variant,
                                   (long long)max_live, fused_reduce ? 1 : 0, tree ? 1 : 0, c->pdl ? 1 : 0, graph_batch};
@@ -1406,15 +1452,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
                             std::equal(key.begin(), key.end(), c->iter_graph_key.begin());
     if (!same_graph) {
       drop_iteration_graph(c);
-      // function attributes must be set outside of a capture: launch_dmma does it lazily, so trigger it here
-      for (int n = 0; n < N; n++)
-        if (c->variant == CALS_B200_MTTKRP_DMMA && ensure_dmma_attr(c, b.wm[n]))
-          return 1;
-      if (tree && b.node[0].slot < 0 && launch_pair_gemm(c, b, true))
+      if (prepare_capture())
         return 1;
-      for (int k = 0; tree && k < b.n_nodes; k++)
-        if (b.node[k].slot >= 0 && ensure_dmma_attr(c, b.wm[b.node[k].slot]))
-          return 1;
       // two graphs: one CALS iteration, and GRAPH_BATCH iterations back to back (used while the number of passes still
       // to run is known to be at least that, see below)
       for (int which = 0; which < 2; which++) {
@@ -1449,6 +1488,22 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
       c->total_cols <= c->buffer_cols && !c->ls_enabled)
     known_passes = (long long)c->max_iter + 1;
   for (;; it++) {
+    if (timed_graph) {
+      CU_TRY(c, cudaGraphLaunch(tgraph, s));
+      launches += launches_per_iteration;
+      mttkrp_launches += N;
+      CU_TRY(c, cudaStreamSynchronize(s));
+      const bool drained = *(volatile int *)&c->h_flags[0] != 0; // this pass found the queue empty: no work in it
+      if (!drained)
+        for (auto &t : timed) {
+          float e = 0;
+          cudaEventElapsedTime(&e, get_event(c, t.e0), get_event(c, t.e1));
+          tsum[t.kind] += e;
+        }
+      if (drained)
+        break;
+      continue;
+    }
     if (use_graph && known_passes > 0 && it + graph_batch <= known_passes && graph_batch > 1) {
       CU_TRY(c, cudaGraphLaunch(c->batch_graph, s));
       launches += (uint64_t)launches_per_iteration * graph_batch;
@@ -1480,6 +1535,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   CU_TRY(c, cudaStreamSynchronize(s));
   CU_TRY(c, cudaGetLastError());
   auto t1 = std::chrono::steady_clock::now();
+  if (tgraph)
+    cudaGraphExecDestroy(tgraph);
 
   if (update_prof && c->d_update_prof) {
     std::vector<long long> h((size_t)N * max_live * 16);
@@ -1540,13 +1597,17 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     if (c->timing) {
       // passes launched after the queue drained (host run-ahead) are not counted
       double sum[5] = {0, 0, 0, 0, 0};
-      for (auto &t : timed) {
-        if (t.iteration >= (long long)st.global_iter)
-          continue;
-        float e = 0;
-        cudaEventElapsedTime(&e, get_event(c, t.e0), get_event(c, t.e1));
-        sum[t.kind] += e;
-      }
+      if (timed_graph) {
+        for (int k = 0; k < 5; k++)
+          sum[k] = tsum[k];
+      } else
+        for (auto &t : timed) {
+          if (t.iteration >= (long long)st.global_iter)
+            continue;
+          float e = 0;
+          cudaEventElapsedTime(&e, get_event(c, t.e0), get_event(c, t.e1));
+          sum[t.kind] += e;
+        }
       rep->mttkrp_ms = sum[T_MTTKRP] + sum[T_PAIR_GEMM] + sum[T_PAIR_LEAF];
       rep->update_ms = sum[T_UPDATE];
       rep->exchange_ms = sum[T_EXCHANGE];

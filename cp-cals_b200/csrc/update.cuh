@@ -554,9 +554,11 @@ __global__ void __launch_bounds__(UPDATE_THREADS, 2)
 model_update_kernel(const UpdateParams p) {
   pdl_enter();
   SchedState *st = p.st;
-  if ((int)blockIdx.x >= st->n_live)
+  // both loads are issued before the branch (live[] has an entry for every CTA of the grid): one round trip to L2 less
+  // on the dependent chain n_live -> live[b] -> model descriptor -> Gramians at the head of this latency-bound kernel
+  const int n_live = st->n_live, m = p.live[blockIdx.x];
+  if ((int)blockIdx.x >= n_live)
     return;
-  const int m = p.live[blockIdx.x];
   ModelDesc &md = p.models[m];
   const int R = md.rank, col = md.col, cur = st->cur;
   const int rows = p.rows, ld = p.ld, n = p.mode, N = p.n_modes;
