@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "cp-cals_b200", "libcals_b200.so")
-WATCH = ["DMMA", "UTMALDG", "UTMASTG", "SYNCS", "LDS", "STS", "LDG", "STG", "LDL", "STL", "DFMA", "DMUL", "DADD", "SHFL",
+WATCH = ["DMMA", "UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "LDS", "STS", "LDG", "STG", "LDL", "STL", "DFMA", "DMUL", "DADD", "SHFL",
          "MUFU", "BAR", "ATOM", "RED", "USETMAXREG", "HMMA", "IMMA", "UTCHMMA", "UTCIMMA"]
 
 
