@@ -175,6 +175,16 @@ struct cals_b200_ctx {
   bool pair_attr_done[16] = {};
   size_t update_attr_smem = 0;
   size_t leaf_slow_attr = 0;
+  // prefactor_kernel (update.cuh) runs on a forked branch: second stream, fork / join events per mode, scratch
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork[CALS_MAX_MODES] = {}, ev_join[CALS_MAX_MODES] = {};
+  double *d_pref = nullptr; // run allocation: max_live slots of pref_stride doubles
+  long long pref_stride = 0;
+  size_t prefactor_attr_smem = 0;
+  PrefactorParams pf[CALS_MAX_MODES];
+  size_t pf_smem = 0;
+  int pf_grid = 0;
+  int fork_mode = -1; // mode whose prefactor branch the next launch_dmma forks between its two kernels (-1: none)
 };
 
 namespace {
@@ -701,6 +711,20 @@ int ensure_dmma_attr(cals_b200_ctx *c, int wm) {
   }
 }
 
+// Fork: prefactor_kernel of mode n on the second stream, ordered after everything enqueued on the main stream so far;
+// join_prefactor makes the main stream wait for it (in a stream capture both become graph edges).
+int fork_prefactor(cals_b200_ctx *c, int n) {
+  CU_TRY(c, cudaEventRecord(c->ev_fork[n], c->stream));
+  CU_TRY(c, cudaStreamWaitEvent(c->stream2, c->ev_fork[n], 0));
+  prefactor_kernel<<<c->pf_grid, PREFACTOR_THREADS, c->pf_smem, c->stream2>>>(c->pf[n]);
+  CU_TRY(c, cudaEventRecord(c->ev_join[n], c->stream2));
+  return 0;
+}
+int join_prefactor(cals_b200_ctx *c, int n) {
+  CU_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_join[n], 0));
+  return 0;
+}
+
 template <int WM>
 int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchange, bool skip_reduce, double *out) {
   auto kern = mttkrp_dmma_kernel<WM, WN_FIXED>;
@@ -711,6 +735,12 @@ int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchan
                          (const SchedState *)c->d_st, b.fac, (const int *)b.plans.plan[n], b.ws, C_override));
   if (skip_reduce) // the update kernel sums the partial tiles itself
     return 0;
+  if (c->fork_mode >= 0) { // the prefactor branch runs next to the reduce pass, not next to the persistent DMMA kernel
+    const int fm = c->fork_mode;
+    c->fork_mode = -1;
+    if (fork_prefactor(c, fm))
+      return 1;
+  }
   const int cols = C_override > 0 ? C_override : b.cols;
   dim3 rg((cols + 31) / 32, (b.mg[n].In + REDUCE_ROWS - 1) / REDUCE_ROWS);
   CU_TRY(c, launch_chain(c, mttkrp_reduce_kernel<8 * WM, TILE_N>, rg, dim3(256), (size_t)0, b.mg[n],
@@ -790,6 +820,7 @@ void release_run(cals_b200_ctx *c) {
   c->d_models = nullptr;
   c->d_live = c->d_live_tmp = c->d_gather = c->d_evict = nullptr;
   c->d_gram = c->d_lambda = nullptr;
+  c->d_pref = nullptr;
   c->d_active = nullptr;
   for (int n = 0; n < CALS_MAX_MODES; n++)
     c->ls_prev[n] = c->ls_backup[n] = nullptr;
@@ -1030,6 +1061,12 @@ int prepare_run(cals_b200_ctx *c) {
     for (int n = 0; n < N; n++)
       if (dev_alloc(c, &c->home0[n], (size_t)geo.ldF[n] * c->total_cols, c->run_allocs))
         return 1;
+    {
+      const long long ld8 = round_up_int(max_rank, 8);
+      c->pref_stride = 2 * ld8 * ld8 + 2 * ld8 + 2;
+      if (dev_alloc(c, &c->d_pref, (size_t)std::min(M, c->buffer_cols) * (size_t)c->pref_stride, c->run_allocs))
+        return 1;
+    }
     if (c->ls_enabled) {
       for (int n = 0; n < N; n++) {
         if (dev_alloc(c, &c->ls_prev[n], (size_t)geo.ldF[n] * c->total_cols, c->run_allocs))
@@ -1202,6 +1239,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     u.rows_before = 0;
     for (int k = 0; k < n; k++)
       u.rows_before += geo.dims[k];
+    u.pref = nullptr;
+    u.pref_stride = 0;
     u.prof = c->d_update_prof ? c->d_update_prof + (size_t)n * max_live * 16 : nullptr;
     up_smem[n] = fixed + (size_t)(cr + 4) * R8 * 8 + tables(cr);
   }
@@ -1306,6 +1345,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   };
   // everything one CALS iteration launches, in stream order
   int launches_per_iteration = 0;
+  bool pref_on = false; // decided below, before the first call of enqueue_iteration
   auto enqueue_iteration = [&](bool count) -> int {
     int n_launch = 0;
     auto chain_ok = [&](cudaError_t e, const char *what) {
@@ -1342,6 +1382,11 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
           el = mark();
           window(e0, el, T_PAIR_GEMM);
         }
+        if (pref_on) { // the update's Cholesky runs on a forked branch next to the leaf that streams T
+          if (fork_prefactor(c, n))
+            return -1;
+          n_launch++;
+        }
         if (launch_pair_leaf(c, b, n, exchange))
           return -1;
         n_launch++;
@@ -1354,8 +1399,17 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
         e1 = mark();
         window(el, e1, T_PAIR_LEAF); // includes the exchange
       } else {
+        if (pref_on) { // ... or next to the partial-tile reduction (launch_dmma forks between its two kernels)
+          if (c->variant == CALS_B200_MTTKRP_NAIVE) {
+            if (fork_prefactor(c, n))
+              return -1;
+          } else
+            c->fork_mode = n;
+          n_launch++;
+        }
         if (launch_mttkrp(c, b, n, 0, c->variant, exchange, fused_reduce))
           return -1;
+        c->fork_mode = -1;
         n_launch += (c->variant == CALS_B200_MTTKRP_NAIVE || fused_reduce) ? 1 : 2;
         if (exchange) {
           const size_t x0 = mark();
@@ -1366,6 +1420,8 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
         e1 = mark();
         window(e0, e1, T_MTTKRP); // includes the exchange
       }
+      if (pref_on && join_prefactor(c, n))
+        return -1;
       if (!chain_ok(up[n].nnls ? launch_chain(c, model_update_kernel<true>, dim3(max_live), dim3(UPDATE_THREADS),
                                               up_smem[n], up[n])
                                : launch_chain(c, model_update_kernel<false>, dim3(max_live), dim3(UPDATE_THREADS),
@@ -1425,6 +1481,37 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   const bool timed_graph = c->timing && !exchange && !graphs_off && !c->ls_enabled;
   cudaGraphExec_t tgraph = nullptr;
   double tsum[5] = {0, 0, 0, 0, 0};
+  // The head of every update (H, Cholesky, block inverses) on a forked branch of the iteration graph, off the critical
+  // path (update.cuh: prefactor_kernel).  OFF unless CALS_B200_PREFACTOR=1: measured on the B200 the fork / join edges
+  // and the kernel running next to the leaf cost more than the 17 k cycles they take out of the update kernel (8-way
+  // shard of config 2: 56.7 k -> 54.0 k model-iterations/s, the leaf beside it 25 -> 31 us; config 1 +0.6 %, config 2 0).
+  static const bool pref_wanted = getenv("CALS_B200_PREFACTOR") != nullptr;
+  pref_on = (use_graph || timed_graph) && pref_wanted && !(c->flags & CALS_B200_NNLS) && !c->ls_enabled && !fused_reduce &&
+            c->d_pref != nullptr;
+  {
+    const long long ld8 = round_up_int(c->max_rank, 8);
+    c->pf_smem = (size_t)(2 * ld8 * ld8 + 2 * ld8) * 8;
+    c->pf_grid = max_live;
+    if (pref_on && c->pf_smem > 200 * 1024)
+      pref_on = false;
+    if (pref_on && c->pf_smem > c->prefactor_attr_smem) {
+      CU_TRY(c, cudaFuncSetAttribute(prefactor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->pf_smem));
+      c->prefactor_attr_smem = c->pf_smem;
+    }
+    for (int n = 0; n < N; n++) {
+      PrefactorParams &q = c->pf[n];
+      q.mode = n;
+      q.n_modes = N;
+      q.gram_pool = c->d_gram;
+      q.models = c->d_models;
+      q.live = c->d_live;
+      q.st = c->d_st;
+      q.pref = c->d_pref;
+      q.pref_stride = c->pref_stride;
+      up[n].pref = pref_on ? c->d_pref : nullptr;
+      up[n].pref_stride = c->pref_stride;
+    }
+  }
   if (timed_graph) {
     if (prepare_capture())
       return 1;
@@ -1447,7 +1534,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   }
   if (use_graph) {
     std::vector<long long> key = {c->alloc_generation, (long long)c->flags, c->ls_enabled, c->ls_method, c->variant,
-                                  (long long)max_live, fused_reduce ? 1 : 0, tree ? 1 : 0, c->pdl ? 1 : 0, graph_batch};
+                                  (long long)max_live, fused_reduce ? 1 : 0, tree ? 1 : 0, c->pdl ? 1 : 0, graph_batch, pref_on ? 1 : 0};
     const bool same_graph = c->iter_graph && c->iter_graph_key.size() == key.size() + 1 &&
                             std::equal(key.begin(), key.end(), c->iter_graph_key.begin());
     if (!same_graph) {
@@ -1703,6 +1790,15 @@ int cals_b200_create(cals_b200_ctx **out, int device) {
     return 1;
   }
   c->encode = (PFN_encodeTiled)fn;
+  bool aux_ok = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) == cudaSuccess;
+  for (int n = 0; n < CALS_MAX_MODES && aux_ok; n++)
+    aux_ok = cudaEventCreateWithFlags(&c->ev_fork[n], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_join[n], cudaEventDisableTiming) == cudaSuccess;
+  if (!aux_ok) {
+    fail(nullptr, "cannot create the auxiliary stream / events");
+    delete c;
+    return 1;
+  }
   if (cudaHostAlloc((void **)&c->h_flags, 64, cudaHostAllocMapped) != cudaSuccess ||
       cudaHostGetDevicePointer((void **)&c->d_flags, c->h_flags, 0) != cudaSuccess) {
     fail(nullptr, "cannot allocate mapped host flags");
@@ -1746,6 +1842,14 @@ int cals_b200_destroy(cals_b200_ctx *c) {
     cudaFree(c->x_stage);
   for (auto e : c->ev_pool)
     cudaEventDestroy(e);
+  for (int n = 0; n < CALS_MAX_MODES; n++) {
+    if (c->ev_fork[n])
+      cudaEventDestroy(c->ev_fork[n]);
+    if (c->ev_join[n])
+      cudaEventDestroy(c->ev_join[n]);
+  }
+  if (c->stream2)
+    cudaStreamDestroy(c->stream2);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;

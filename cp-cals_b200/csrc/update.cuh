@@ -57,6 +57,20 @@ struct UpdateParams {
   unsigned char *act_pool;  // per model: for every mode an I_n x R block, row-major, 1 = constrained to zero
   int table_off;            // doubles from the start of shared memory to the tile lookup tables of the fused reduction
   long long *prof;          // tuning aid (CALS_B200_UPDATE_PROF=1): 16 clock64() stamps per CTA, nullptr otherwise
+  // H, its Cholesky factor, the inverses of its diagonal blocks, 1 / diag(L) and diag(H) of every live model, computed
+  // by prefactor_kernel while the kernel in front of this one was running (nullptr: computed here)
+  const double *pref;
+  long long pref_stride;    // doubles per live slot
+};
+
+struct PrefactorParams {
+  int mode, n_modes;
+  const double *gram_pool;
+  const ModelDesc *models;
+  const int *live;
+  const SchedState *st;
+  double *pref;
+  long long pref_stride;
 };
 #define CALS_PROF(slot)                                                                                                \
   do {                                                                                                                 \
@@ -547,6 +561,59 @@ __device__ __forceinline__ void gram_dmma(const double *S, int pitch, int nr, do
   }
 }
 
+// The head of the update of mode n -- H = hadamard of the other modes' Gramians, its Cholesky factor, the inverses of the
+// diagonal blocks -- depends on nothing the MTTKRP of mode n produces.  prefactor_kernel computes it for every live model
+// on a forked branch of the iteration graph, next to the last light kernel in front of the update (the partial-tile
+// reduction or the leaf that streams T), and model_update_kernel picks the result up from global memory: 17 k of its
+// 34 k cycles (R = 20) leave the critical path.  Tuning knob (CALS_B200_PREFACTOR=1), off by default: on the B200 the
+// extra graph edges and the contention with the leaf kernel cost more than that (engine.cu).  One CTA per live model; layout per slot: [H / L (LD x LD) | block
+// inverses (LD x LD) | 1 / diag(L) (LD) | diag(H) (LD) | 1.0 if a pivot was not positive].
+constexpr int PREFACTOR_THREADS = 128;
+__global__ void __launch_bounds__(PREFACTOR_THREADS) prefactor_kernel(const PrefactorParams p) {
+  const int n_live = p.st->n_live, m = p.live[blockIdx.x];
+  if ((int)blockIdx.x >= n_live)
+    return;
+  const ModelDesc &md = p.models[m];
+  const int R = md.rank, n = p.mode, N = p.n_modes;
+  const int LD = (R + 7) & ~7;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  extern __shared__ double psm[];
+  double *Hs = psm, *Gs = Hs + LD * LD, *inv = Gs + LD * LD, *hdiag = inv + LD;
+  const double *grams = p.gram_pool + md.gram_off;
+#pragma unroll 1
+  for (int e = tid; e < LD * LD; e += nthr) {
+    const int i = e % LD, j = e / LD;
+    double h = 0.0;
+    if (i < R && j < R) {
+      h = 1.0;
+#pragma unroll 1
+      for (int k = 0; k < N; k++)
+        if (k != n)
+          h *= grams[(size_t)k * R * R + i + j * R];
+      if (i == j)
+        hdiag[i] = h;
+    }
+    Hs[e] = h;
+    Gs[e] = 0.0;
+  }
+  for (int e = tid; e < LD; e += nthr) {
+    inv[e] = 0.0;
+    if (e >= R)
+      hdiag[e] = 0.0;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int fail = cholesky_warp(Hs, LD, inv, R, tid);
+    diag_block_inverses_warp(Hs, LD, inv, Gs, R, tid);
+    if (tid == 0) // non-positive pivot: the update kernel counts it in chol_info
+      p.pref[(size_t)blockIdx.x * p.pref_stride + 2 * LD * LD + 2 * LD] = fail ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  double *out = p.pref + (size_t)blockIdx.x * p.pref_stride;
+  for (int e = tid; e < 2 * LD * LD + 2 * LD; e += nthr)
+    out[e] = psm[e];
+}
+
 constexpr int STAT_SEGS = 8; // row segments per column in the column statistics
 
 template <bool NNLS>
@@ -590,22 +657,35 @@ model_update_kernel(const UpdateParams p) {
   const bool fused = p.plan != nullptr;
   const PlanView pv = fused ? plan_view(p.plan, p.plan_ctas) : PlanView{};
 
-  // ---- H = hadamard of the other Gramians ----
-#pragma unroll 1
-  for (int e = tid; e < LD * LD; e += nthr) {
-    const int i = e % LD, j = e / LD;
-    double h = 0.0;
-    if (i < R && j < R) {
-      h = 1.0;
-#pragma unroll 1
-      for (int k = 0; k < N; k++)
-        if (k != n)
-          h *= grams[(size_t)k * R * R + i + j * R];
-      if (i == j)
-        hdiag[i] = h;
+  // ---- H = hadamard of the other Gramians (or everything prefactor_kernel has derived from it) ----
+  const bool prefactored = !NNLS && p.pref != nullptr;
+  int chol_fail = 0;
+  if (prefactored) {
+    const double *src = p.pref + (size_t)blockIdx.x * p.pref_stride;
+    for (int e = tid; e < 2 * LD * LD; e += nthr)
+      Hs[e] = src[e]; // Hs and Gs are adjacent
+    for (int e = tid; e < R; e += nthr) {
+      inv[e] = src[2 * LD * LD + e];
+      hdiag[e] = src[2 * LD * LD + LD + e];
     }
-    Hs[e] = h;
-    Gs[e] = 0.0;
+    chol_fail = src[2 * LD * LD + 2 * LD] != 0.0;
+  } else {
+#pragma unroll 1
+    for (int e = tid; e < LD * LD; e += nthr) {
+      const int i = e % LD, j = e / LD;
+      double h = 0.0;
+      if (i < R && j < R) {
+        h = 1.0;
+#pragma unroll 1
+        for (int k = 0; k < N; k++)
+          if (k != n)
+            h *= grams[(size_t)k * R * R + i + j * R];
+        if (i == j)
+          hdiag[i] = h;
+      }
+      Hs[e] = h;
+      Gs[e] = 0.0;
+    }
   }
   for (int e = tid; e < 2 * R; e += nthr) // value: a sum of squares starts at 0, a max-abs at -1; then the index
     cstat[e] = (e < R) ? (iters == 1 ? 0.0 : -1.0) : 0.0;
@@ -618,7 +698,6 @@ model_update_kernel(const UpdateParams p) {
   __syncthreads();
   CALS_PROF(1);
 
-  int chol_fail = 0;
   double nnls_tol = 0.0;
   if (NNLS) { // tol = 10 * eps * ||H||_1 * R   (reference src/utils/update.cpp:65-66; one_norm = max column sum)
     double mx = -1.0;
@@ -661,7 +740,7 @@ model_update_kernel(const UpdateParams p) {
     }
     // Stage rows [r0, r0 + nr) of the MTTKRP result into S.  In the first chunk warp 0 factors H meanwhile (and inverts
     // the diagonal blocks of L); the other warps stage.
-    const bool overlap = r0 == 0 && !NNLS;
+    const bool overlap = r0 == 0 && !NNLS && !prefactored;
     if (overlap && warp == 0) {
       chol_fail = cholesky_warp(Hs, LD, inv, R, lane);
       diag_block_inverses_warp(Hs, LD, inv, Gs, R, lane);
