@@ -57,6 +57,10 @@ struct SchedState {
   int ls_enabled, ls_method, ls_interval, ls_pad_;
   double ls_step; // 0: cbrt(model iteration), reference src/cals.cpp:317-318
   unsigned long long ls_performed, ls_failed;
+  // Narrow column tail (mttkrp.cuh: narrow_cols): the contraction kernels' main instances work on columns [0, C_main),
+  // their narrow instances on [C_main, C).  C_main == C unless narrow_on and the tail qualifies.
+  int C_main;
+  int narrow_on; // set by the host per run
 };
 
 // eviction predicate + iteration counter (reference src/cals.cpp:336-347); called by exactly one thread per model

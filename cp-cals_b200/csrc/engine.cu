@@ -45,6 +45,9 @@ struct Buffers {
   double *G = nullptr;
   double *ws = nullptr;
   size_t ws_tiles = 0;
+  // narrow column tail (mttkrp.cuh: narrow_cols): second, narrow instance of the contraction kernels
+  bool narrow = false;
+  double *ws_n = nullptr;
   MttkrpMaps maps[CALS_MAX_MODES];
   MttkrpGeom mg[CALS_MAX_MODES];
   int wm[CALS_MAX_MODES];
@@ -172,7 +175,7 @@ struct cals_b200_ctx {
 
   std::vector<cudaEvent_t> ev_pool;
   bool dmma_attr_done[16] = {};
-  bool pair_attr_done[16] = {};
+  bool pair_attr_done[32] = {}; // [WM]: main instance, [8 + WM]: narrow instance
   size_t update_attr_smem = 0;
   size_t leaf_slow_attr = 0;
   // prefactor_kernel (update.cuh) runs on a forked branch: second stream, fork / join events per mode, scratch
@@ -431,6 +434,10 @@ int build_mode_plans(cals_b200_ctx *c, Buffers &b) {
       cuuint32_t bw[2] = {(cuuint32_t)OC, (cuuint32_t)TILE_N};
       if (encode_map(c, &b.maps[n].W[cu], b.fac.buf[cu][q] + c->roff[q], 2, d3, s3, bw))
         return 1;
+      cuuint32_t bxn[2] = {(cuuint32_t)KT, (cuuint32_t)NARROW_COLS}, bwn[2] = {(cuuint32_t)OC, (cuuint32_t)NARROW_COLS};
+      if (encode_map(c, &b.maps[n].Bn[cu], b.fac.buf[cu][g.p_mode] + c->roff[g.p_mode], 2, d2, s2, bxn) ||
+          encode_map(c, &b.maps[n].Wn[cu], b.fac.buf[cu][q] + c->roff[q], 2, d3, s3, bwn))
+        return 1;
     }
   }
   return 0;
@@ -487,6 +494,10 @@ int build_node_slots(cals_b200_ctx *c, Buffers &b) {
       cuuint64_t s3[1] = {(cuuint64_t)geo.ldF[q] * 8};
       cuuint32_t bw[2] = {(cuuint32_t)OC, (cuuint32_t)TILE_N};
       if (encode_map(c, &b.maps[slot].W[cu], b.fac.buf[cu][q], 2, d3, s3, bw))
+        return 1;
+      cuuint32_t bxn[2] = {(cuuint32_t)KT, (cuuint32_t)NARROW_COLS}, bwn[2] = {(cuuint32_t)OC, (cuuint32_t)NARROW_COLS};
+      if (encode_map(c, &b.maps[slot].Bn[cu], b.fac.buf[cu][p], 2, d2, s2, bxn) ||
+          encode_map(c, &b.maps[slot].Wn[cu], b.fac.buf[cu][q], 2, d3, s3, bwn))
         return 1;
     }
   }
@@ -588,8 +599,9 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
         for (int cu = 0; cu < 2; cu++) {
           cuuint64_t d2[2] = {(cuuint64_t)c->xd[0], (cuuint64_t)cols};
           cuuint64_t s2[1] = {(cuuint64_t)geo.ldF[0] * 8};
-          cuuint32_t b2[2] = {(cuuint32_t)KT, (cuuint32_t)TILE_N};
-          if (encode_map(c, &b.pmaps.B[cu], b.fac.buf[cu][0], 2, d2, s2, b2))
+          cuuint32_t b2[2] = {(cuuint32_t)KT, (cuuint32_t)TILE_N}, b2n[2] = {(cuuint32_t)KT, (cuuint32_t)NARROW_COLS};
+          if (encode_map(c, &b.pmaps.B[cu], b.fac.buf[cu][0], 2, d2, s2, b2) ||
+              encode_map(c, &b.pmaps.Bn[cu], b.fac.buf[cu][0], 2, d2, s2, b2n))
             return 1;
         }
       } else if (build_node_slots(c, b))
@@ -603,14 +615,23 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
   b.plans = PlanArgs{};
   b.plans.n_modes = n_plans;
   b.plans.G = c->sm_count;
-  if (dev_alloc(c, &b.plans.built_for, (size_t)CALS_MAX_MODES, b.allocs))
+  if (dev_alloc(c, &b.plans.built_for, (size_t)2 * CALS_MAX_MODES, b.allocs))
     return 1;
-  CU_TRY(c, cudaMemsetAsync(b.plans.built_for, 0xff, CALS_MAX_MODES * sizeof(int), c->stream));
+  CU_TRY(c, cudaMemsetAsync(b.plans.built_for, 0xff, 2 * CALS_MAX_MODES * sizeof(int), c->stream));
+  // Narrow column tail (mttkrp.cuh: narrow_cols): a second, row-splitting instance of the contraction kernels for a
+  // tail of at most 32 columns.  OFF unless CALS_B200_NARROW=1: measured on the B200 the extra persistent kernel --
+  // it streams X once more, and its stages are all barrier and TMA overhead -- costs as much as the slot it saves in
+  // the main instance (8-way shard of config 2, 263 columns: 56.6 k -> 54.9 k model-iterations/s; config 1, 220 columns:
+  // 339 k -> 305 k; 8-way shard of config 3: 253 k -> 239 k).  The main instances are bit-for-bit the same code either way.
+  static const bool narrow_wanted = getenv("CALS_B200_NARROW") != nullptr;
+  b.narrow = narrow_wanted && narrow_cols(cols) > 0;
   for (int n = 0; n < n_plans; n++) {
     const int pairs_max = b.mg[n].m_tiles * n_tiles_max;
     tiles = std::max(tiles, (size_t)(c->sm_count + pairs_max + 2));
     tile_elems = std::max(tile_elems, (size_t)tile_m(b.wm[n]) * TILE_N);
     if (dev_alloc(c, &b.plans.plan[n], (size_t)plan_capacity(c->sm_count, pairs_max), b.allocs))
+      return 1;
+    if (b.narrow && dev_alloc(c, &b.plans.plan_narrow[n], (size_t)plan_capacity(c->sm_count, b.mg[n].m_tiles), b.allocs))
       return 1;
     b.plans.shape[n].In = b.mg[n].In;
     b.plans.shape[n].WM = b.wm[n];
@@ -626,6 +647,13 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
   b.ws_tiles = tiles;
   if (dev_alloc(c, &b.ws, tiles * tile_elems, b.allocs))
     return 1;
+  if (b.narrow) { // partial tiles of the narrow instance: M_TILE x NARROW_COLS, at most one per CTA and one per m-tile
+    size_t mt_max = 0;
+    for (int n = 0; n < n_plans; n++)
+      mt_max = std::max(mt_max, (size_t)b.mg[n].m_tiles);
+    if (dev_alloc(c, &b.ws_n, (size_t)(c->sm_count + mt_max + 2) * 64 * NARROW_COLS, b.allocs))
+      return 1;
+  }
   return 0;
 }
 
@@ -636,9 +664,18 @@ template <int WM> int launch_pair_gemm_wm(cals_b200_ctx *c, Buffers &b, bool att
     CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     c->pair_attr_done[WM] = true;
   }
-  if (!attr_only)
+  auto kern_n = pair_gemm_kernel<WM, WN_FIXED, true>;
+  if (b.narrow && !c->pair_attr_done[8 + WM]) {
+    CU_TRY(c, cudaFuncSetAttribute(kern_n, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    c->pair_attr_done[8 + WM] = true;
+  }
+  if (!attr_only) {
     CU_TRY(c, launch_chain(c, kern, dim3(c->sm_count), dim3(MTTKRP_THREADS), (size_t)smem, b.pmaps, b.node[0].pg,
                            (const SchedState *)c->d_st, b.node[0].T));
+    if (b.narrow)
+      CU_TRY(c, launch_chain(c, kern_n, dim3(c->sm_count), dim3(MTTKRP_THREADS), (size_t)smem, b.pmaps, b.node[0].pg,
+                             (const SchedState *)c->d_st, b.node[0].T));
+  }
   return 0;
 }
 
@@ -689,7 +726,9 @@ double *exchange_data(cals_b200_ctx *c) { return (double *)((char *)c->xblock + 
 
 template <int WM> int set_dmma_attr(cals_b200_ctx *c) {
   if (!c->dmma_attr_done[WM]) {
-    CU_TRY(c, cudaFuncSetAttribute(mttkrp_dmma_kernel<WM, WN_FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU_TRY(c, cudaFuncSetAttribute(mttkrp_dmma_kernel<WM, WN_FIXED, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   smem_bytes<WM>()));
+    CU_TRY(c, cudaFuncSetAttribute(mttkrp_dmma_kernel<WM, WN_FIXED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    smem_bytes<WM>()));
     c->dmma_attr_done[WM] = true;
   }
@@ -727,12 +766,21 @@ int join_prefactor(cals_b200_ctx *c, int n) {
 
 template <int WM>
 int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchange, bool skip_reduce, double *out) {
-  auto kern = mttkrp_dmma_kernel<WM, WN_FIXED>;
+  auto kern = mttkrp_dmma_kernel<WM, WN_FIXED, false>;
+  auto kern_n = mttkrp_dmma_kernel<WM, WN_FIXED, true>;
   if (set_dmma_attr<WM>(c))
     return 1;
   const int G = c->sm_count;
-  CU_TRY(c, launch_chain(c, kern, dim3(G), dim3(MTTKRP_THREADS), (size_t)smem_bytes<WM>(), b.maps[n], b.mg[n],
-                         (const SchedState *)c->d_st, b.fac, (const int *)b.plans.plan[n], b.ws, C_override));
+  // single-operation hook (C_override > 0): the split of the columns is made here; iteration path: by the scheduler
+  const int tail = (C_override > 0 && b.narrow) ? narrow_cols(C_override) : 0;
+  const int C_main_ov = C_override > 0 ? C_override - tail : 0;
+  if (C_override <= 0 || C_main_ov > 0)
+    CU_TRY(c, launch_chain(c, kern, dim3(G), dim3(MTTKRP_THREADS), (size_t)smem_bytes<WM>(), b.maps[n], b.mg[n],
+                           (const SchedState *)c->d_st, b.fac, (const int *)b.plans.plan[n], b.ws, C_main_ov, 0));
+  if (b.narrow && (C_override <= 0 || tail > 0))
+    CU_TRY(c, launch_chain(c, kern_n, dim3(G), dim3(MTTKRP_THREADS), (size_t)smem_bytes<WM>(), b.maps[n], b.mg[n],
+                           (const SchedState *)c->d_st, b.fac, (const int *)b.plans.plan_narrow[n], b.ws_n, C_override,
+                           C_main_ov));
   if (skip_reduce) // the update kernel sums the partial tiles itself
     return 0;
   if (c->fork_mode >= 0) { // the prefactor branch runs next to the reduce pass, not next to the persistent DMMA kernel
@@ -746,7 +794,8 @@ int launch_dmma(cals_b200_ctx *c, Buffers &b, int n, int C_override, bool exchan
   CU_TRY(c, launch_chain(c, mttkrp_reduce_kernel<8 * WM, TILE_N>, rg, dim3(256), (size_t)0, b.mg[n],
                          (const SchedState *)c->d_st, (const int *)b.plans.plan[n], (const double *)b.ws, out, G,
                          C_override, exchange ? exchange_data(c) : (double *)nullptr, (unsigned long long)c->xcap,
-                         (unsigned long long)c->seq_base, c->geo.n_modes));
+                         (unsigned long long)c->seq_base, c->geo.n_modes, (const int *)b.plans.plan_narrow[n],
+                         (const double *)b.ws_n, C_main_ov));
   return 0;
 }
 
@@ -1142,6 +1191,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   st.ls_interval = c->ls_interval;
   st.ls_step = c->ls_step;
   st.x_norm = c->x_norm_valid ? c->x_norm : 0.0;
+  st.narrow_on = (c->bufs.narrow && c->variant == CALS_B200_MTTKRP_DMMA) ? 1 : 0;
   CU_TRY(c, cudaMemcpyAsync(c->d_st, &st, sizeof st, cudaMemcpyHostToDevice, s));
   if (!c->x_norm_valid) // set_tensor has not been synchronised yet: take the norm from where the device computed it
     CU_TRY(c, cudaMemcpyAsync(&c->d_st->x_norm, c->d_norm, 8, cudaMemcpyDeviceToDevice, s));
@@ -1167,7 +1217,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
   // per element as fast as the whole chip -- so the fused form only runs when CALS_B200_FUSED_REDUCE=1 asks for it.
   static const bool fusion_forced = getenv("CALS_B200_FUSED_REDUCE") != nullptr;
   const bool fused_reduce = c->variant == CALS_B200_MTTKRP_DMMA && !(c->slice_mode >= 0 && c->comm_world > 1) &&
-                            !fusion_off && fusion_forced;
+                            !fusion_off && fusion_forced && !b.narrow;
 
   // pair nodes: two modes share one contraction of the tensor (pairnode.cuh)
   const bool tree = b.tree && c->variant == CALS_B200_MTTKRP_DMMA;
@@ -1373,11 +1423,11 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
           if (nd.slot < 0) {
             if (launch_pair_gemm(c, b))
               return -1;
-            n_launch++;
+            n_launch += b.narrow ? 2 : 1;
           } else {
             if (launch_mttkrp(c, b, nd.slot, 0, c->variant, false, false, nd.T))
               return -1;
-            n_launch += 2;
+            n_launch += b.narrow ? 3 : 2;
           }
           el = mark();
           window(e0, el, T_PAIR_GEMM);
@@ -1410,7 +1460,7 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
         if (launch_mttkrp(c, b, n, 0, c->variant, exchange, fused_reduce))
           return -1;
         c->fork_mode = -1;
-        n_launch += (c->variant == CALS_B200_MTTKRP_NAIVE || fused_reduce) ? 1 : 2;
+        n_launch += (c->variant == CALS_B200_MTTKRP_NAIVE || fused_reduce) ? 1 : (b.narrow ? 3 : 2);
         if (exchange) {
           const size_t x0 = mark();
           exchange_sum_kernel<<<c->sm_count * 2, 256, 0, s>>>(cp, c->d_st, b.G, n, N, geo.dims[n], geo.ldF[n]);
@@ -2353,7 +2403,7 @@ int cals_b200_mttkrp(cals_b200_ctx *c, int mode, uint64_t cols, const double *co
     if (c->slice_mode >= 0) // rows outside this device's slab are not produced: the hook returns them as zeros
       cudaMemsetAsync(b.G, 0, (size_t)geo.ldF[mode] * cols * 8, c->stream);
     c->pdl = false; // single launches in plain stream order
-    mttkrp_plan_kernel<<<1, 32, 0, c->stream>>>(b.plans, (int)cols);
+    mttkrp_plan_kernel<<<1, 32, 0, c->stream>>>(b.plans, (int)cols, b.narrow ? 1 : 0);
     rc = launch_mttkrp(c, b, mode, (int)cols, variant); // warm-up + result
     cudaEventRecord(e0, c->stream);
     for (int r = 1; r < repeats && !rc; r++)

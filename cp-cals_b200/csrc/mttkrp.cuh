@@ -68,7 +68,23 @@ struct MttkrpMaps {
   CUtensorMap X;     // 4-D view (P, L', M, U) of the tensor copy used for this mode
   CUtensorMap B[2];  // factor p in buffer 0 / 1: 2-D (Ip, buffer_cols)
   CUtensorMap W[2];  // factor q (fastest outer mode) in buffer 0 / 1
+  CUtensorMap Bn[2]; // the same two with a box of NARROW_COLS columns (narrow column tail)
+  CUtensorMap Wn[2];
 };
+
+// Narrow column tail.  When the live column count C leaves at most NARROW_COLS columns in its last 64-column octet (and
+// there is at least one full octet), those columns are not given a slot of the regular warp layout -- one n8 group per
+// warp and octet, so a tail of 7 columns keeps one warp of eight busy for a whole octet slot and costs the tile its
+// pipeline fill (measured: 263 columns ran 23 % slower than 255) -- but are computed by a second, NARROW instance of the
+// contraction kernels in which the eight warps split the ROWS of the tile (warp w = m8 row group w) and every warp
+// covers all of the tail's (at most four) n8 groups.  The main instances then see only full octets.
+// Tuning knob (CALS_B200_NARROW=1), off by default: the second persistent kernel costs what it saves (engine.cu).
+constexpr int NARROW_GROUPS = 4;
+constexpr int NARROW_COLS = 8 * NARROW_GROUPS;
+__host__ __device__ inline int narrow_cols(int C) {
+  const int NO = (C + 63) >> 6, tail = C - 64 * (NO - 1);
+  return (NO >= 2 && tail <= NARROW_COLS) ? tail : 0;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // PTX helpers
@@ -310,12 +326,18 @@ struct PlanArgs {
   PlanShape shape[CALS_MAX_MODES];
   int *plan[CALS_MAX_MODES];
   int G;
-  int *built_for; // [CALS_MAX_MODES] column count each plan table was last built for (-1: never); device memory
+  int *built_for; // [2 * CALS_MAX_MODES] column count each plan table was last built for (-1: never); device memory:
+                  // [n] for plan[n], [CALS_MAX_MODES + n] for plan_narrow[n]
+  int *plan_narrow[CALS_MAX_MODES]; // plan of the narrow column tail (one n-tile), nullptr when the run has none
 };
-__global__ void mttkrp_plan_kernel(const PlanArgs a, int C) {
+__global__ void mttkrp_plan_kernel(const PlanArgs a, int C, int narrow_on) {
   const int n = threadIdx.x;
-  if (n < a.n_modes && a.plan[n])
-    mttkrp_make_plan(a.plan[n], a.shape[n], C, a.G);
+  if (n < a.n_modes && a.plan[n]) {
+    const int tail = (narrow_on && a.plan_narrow[n]) ? narrow_cols(C) : 0;
+    mttkrp_make_plan(a.plan[n], a.shape[n], C - tail, a.G);
+    if (tail)
+      mttkrp_make_plan(a.plan_narrow[n], a.shape[n], tail, a.G);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -407,16 +429,45 @@ __device__ __forceinline__ void mma_stage(double (&acc)[WM][WN][2], const double
 #undef CALS_MMA_CASE
 }
 
+// One stage of the NARROW instances for one warp: the warp's own m8 row group (rows row8*8 .. +7 of the X tile) times
+// the g <= NARROW_GROUPS n8 column groups of the tail.  acc[q] belongs to column group q.
+template <bool SCALE>
+__device__ __forceinline__ void mma_narrow_stage(double (&acc)[NARROW_GROUPS][2], const double *__restrict__ Xt,
+                                                 const double *__restrict__ Bs, const double (&wv)[NARROW_GROUPS],
+                                                 int ngroups, int r, int s, int row8, int g) {
+  const double *xa = Xt + (row8 * 8 + r) * KT + 2 * s;
+  const double *xb = Bs + r * KT + 2 * s;
+#pragma unroll 1
+  for (int gk = 0; gk < ngroups; gk++) {
+    const double2 a = *reinterpret_cast<const double2 *>(xa + gk * 8);
+#pragma unroll
+    for (int q = 0; q < NARROW_GROUPS; q++)
+      if (q < g) {
+        double2 b = *reinterpret_cast<const double2 *>(xb + q * 8 * KT + gk * 8);
+        if (SCALE) {
+          b.x *= wv[q];
+          b.y *= wv[q];
+        }
+        dmma_m8n8k4(acc[q][0], acc[q][1], a.x, b.x);
+        dmma_m8n8k4(acc[q][0], acc[q][1], a.y, b.y);
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // The DMMA kernel.  384 threads: warps 0..7 consume (LDS + DMMA) with 232 registers each, warp 8 lane 0 produces (TMA);
 // warps 9..11 only exist so that the producer warpgroup can release its registers (setmaxnreg) and exit at once.
-template <int WM, int WN>
+// NARROW = false: columns [0, C_main) (C_override > 0: [0, C_override)).  NARROW = true: the narrow column tail
+// [C_main, C) (C_override > 0: [C_lo_override, C_override)) with its own plan and workspace of M_TILE x NARROW_COLS tiles.
+template <int WM, int WN, bool NARROW = false>
 __global__ void __launch_bounds__(MTTKRP_THREADS, 1)
 mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, const SchedState *__restrict__ st,
-                   const FactorPtrs fac, const int *__restrict__ plan, double *__restrict__ ws, int C_override) {
+                   const FactorPtrs fac, const int *__restrict__ plan, double *__restrict__ ws, int C_override,
+                   int C_lo_override) {
   using Cfg = TileCfg<WM, WN>;
   constexpr int M_TILE = Cfg::M_TILE, N_TILE = Cfg::N_TILE;
   static_assert(WN * NUM_MMA_WARPS == N8_TILE, "n-tile must hold N8_TILE n8 groups");
+  static_assert(WN == NARROW_GROUPS, "the narrow instance keeps its accumulators in acc[0][0 .. WN)");
 
   // 1024-byte aligned dynamic shared memory (TMA destinations need 128 B); indexing the array directly keeps the
   // pointers in the shared address space (LDS instead of generic LD)
@@ -430,9 +481,10 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
   uint64_t *full_b = empty_w + 2, *empty_b = full_b + 1;
 
   pdl_enter();
-  const int C = C_override > 0 ? C_override : st->C;
+  const int C = C_override > 0 ? C_override : (NARROW ? st->C : st->C_main);
+  const int c_lo = NARROW ? (C_override > 0 ? C_lo_override : st->C_main) : 0; // first column of the narrow tail
   const int cur = C_override > 0 ? 0 : st->cur;
-  if (C <= 0)
+  if (C - c_lo <= 0)
     return;
   const PlanView pv = plan_view(plan, gridDim.x);
   const int lo = pv.cta_lo[blockIdx.x], hi = pv.cta_lo[blockIdx.x + 1];
@@ -495,14 +547,24 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
           mbar_wait(empty_b, bph);
           bph ^= 1;
         }
-        mbar_expect_tx(full_b, Cfg::B_BYTES);
-        tma_load_2d(Bs, tmB, full_b, pt * KT, 64 * plan_oct_start(nt, pv.NO, n_tiles));
+        if (NARROW) {
+          mbar_expect_tx(full_b, NARROW_COLS * KT * 8);
+          tma_load_2d(Bs, &maps.Bn[cur], full_b, pt * KT, c_lo);
+        } else {
+          mbar_expect_tx(full_b, Cfg::B_BYTES);
+          tma_load_2d(Bs, tmB, full_b, pt * KT, 64 * plan_oct_start(nt, pv.NO, n_tiles));
+        }
         prev_key = key;
       }
       // w chunk
       mbar_wait(&empty_w[wsi], wph);
-      mbar_expect_tx(&full_w[wsi], Cfg::W_BYTES);
-      tma_load_2d(Ws + wsi * (N_TILE * OC), tmW, &full_w[wsi], qc * OC, 64 * plan_oct_start(nt, pv.NO, n_tiles));
+      if (NARROW) {
+        mbar_expect_tx(&full_w[wsi], NARROW_COLS * OC * 8);
+        tma_load_2d(Ws + wsi * (N_TILE * OC), &maps.Wn[cur], &full_w[wsi], qc * OC, c_lo);
+      } else {
+        mbar_expect_tx(&full_w[wsi], Cfg::W_BYTES);
+        tma_load_2d(Ws + wsi * (N_TILE * OC), tmW, &full_w[wsi], qc * OC, 64 * plan_oct_start(nt, pv.NO, n_tiles));
+      }
       if (++wsi == 2) {
         wsi = 0;
         wph ^= 1;
@@ -557,6 +619,17 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
   int seg = pv.cta_seg0[blockIdx.x] - 1;
 
   auto flush = [&]() {
+    if (NARROW) { // warp = m8 row group, acc[0][q] = n8 column group q of the tail; tiles are M_TILE x NARROW_COLS
+      double *tile = ws + (size_t)seg * (M_TILE * NARROW_COLS);
+#pragma unroll
+      for (int q = 0; q < NARROW_GROUPS; q++) {
+        if (warp < WM)
+          *reinterpret_cast<double2 *>(tile + (warp * 8 + r) * NARROW_COLS + q * 8 + 2 * s) =
+              make_double2(acc[0][q][0], acc[0][q][1]);
+        acc[0][q][0] = acc[0][q][1] = 0.0;
+      }
+      return;
+    }
     double *tile = ws + (size_t)seg * (M_TILE * N_TILE);
 #pragma unroll
     for (int i = 0; i < WM; i++)
@@ -567,6 +640,7 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
         acc[i][j][0] = acc[i][j][1] = 0.0;
       }
   };
+  const int g_tail = NARROW ? min(NARROW_GROUPS, (C - c_lo + 7) >> 3) : 0; // n8 groups of the narrow tail
 
   for (int u = lo; u < hi;) {
     const int pair = u / Tp;
@@ -584,7 +658,7 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
     // C would multiply TMA zero-fill for a whole octet slot: it runs one slot less instead (per-warp, the barriers do not
     // depend on it).  C = 263 then costs 9 instead of 10 slots per SM sub-partition -- what the per-GPU shards of a
     // strong-scaled model set need; full octets are untouched.
-    if (64 * (plan_oct_start(nt, pv.NO, n_tiles) + nn - 1) + 8 * warp >= C)
+    if (!NARROW && 64 * (plan_oct_start(nt, pv.NO, n_tiles) + nn - 1) + 8 * warp >= C)
       nn--;
     if (pair != prev_pair) {
       if (prev_pair >= 0)
@@ -613,7 +687,8 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
       }
 #pragma unroll
       for (int j = 0; j < WN; j++) {
-        const int c = 64 * plan_oct_start(nt, pv.NO, n_tiles) + (j * 8 + warp) * 8 + r;
+        // regular layout: n8 group (octet j, warp); narrow instance: n8 group j of the tail
+        const int c = NARROW ? c_lo + j * 8 + r : 64 * plan_oct_start(nt, pv.NO, n_tiles) + (j * 8 + warp) * 8 + r;
         double w = 1.0;
         if (c < C)
           for (int k = 1; k < g.n_outer; k++) {
@@ -627,16 +702,20 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
     prev_nt = nt;
 
     mbar_wait(&full_w[wsi], wph);
-    const double *Wc = Ws + wsi * (N_TILE * OC) + warp * 8 * OC;
+    const double *Wc = Ws + wsi * (N_TILE * OC) + (NARROW ? 0 : warp * 8 * OC);
     const int kvalid = min(KT, g.Ip - pt * KT);
     const int ngroups = (kvalid + 7) >> 3;
     for (int o = o0; o < o0 + n_here; o++) {
       double wv[WN];
 #pragma unroll
       for (int j = 0; j < WN; j++)
-        wv[j] = Wc[(j * 64 + r) * OC + o] * wslow[j];
+        wv[j] = Wc[((NARROW ? j * 8 : j * 64) + r) * OC + o] * wslow[j];
       mbar_wait(&full_x[xs], xph);
-      mma_stage<WM, WN>(acc, Xs + xs * (M_TILE * KT), Bw, wv, ngroups, r, s, nm, nn);
+      if (NARROW) {
+        if (warp < nm)
+          mma_narrow_stage<true>(acc[0], Xs + xs * (M_TILE * KT), Bs, wv, ngroups, r, s, warp, g_tail);
+      } else
+        mma_stage<WM, WN>(acc, Xs + xs * (M_TILE * KT), Bw, wv, ngroups, r, s, nm, nn);
       __syncwarp();
       if (lane == 0)
         mbar_arrive(&empty_x[xs]);
@@ -668,13 +747,17 @@ mttkrp_dmma_kernel(const __grid_constant__ MttkrpMaps maps, const MttkrpGeom g, 
 // xbuf + ((seq_base + global_iter * n_modes + mode + 1) & 1) * xcap, from where comm.cuh's exchange kernel of every
 // rank collects it.
 constexpr int REDUCE_ROWS = 8;
+// Columns [0, C_main) come from the main instance's plan / workspace, columns [C_main, C) -- the narrow tail, if any --
+// from plan_n / ws_n (tiles of M_TILE x NARROW_COLS).  C_main_override >= 0 with C_override > 0 (single-operation hook).
 template <int M_TILE, int N_TILE>
 __global__ void __launch_bounds__(256)
 mttkrp_reduce_kernel(const MttkrpGeom g, const SchedState *__restrict__ st, const int *__restrict__ plan,
                      const double *__restrict__ ws, double *__restrict__ G, int grid_ctas, int C_override, double *xbuf,
-                     unsigned long long xcap, unsigned long long seq_base, int n_modes) {
+                     unsigned long long xcap, unsigned long long seq_base, int n_modes, const int *__restrict__ plan_n,
+                     const double *__restrict__ ws_n, int C_main_override) {
   pdl_enter();
   const int C = C_override > 0 ? C_override : st->C;
+  const int C_main = C_override > 0 ? C_main_override : st->C_main;
   if (xbuf != nullptr) {
     const unsigned long long seq = seq_base + st->global_iter * (unsigned long long)n_modes + g.mode + 1;
     G = xbuf + (seq & 1ull) * xcap;
@@ -683,19 +766,22 @@ mttkrp_reduce_kernel(const MttkrpGeom g, const SchedState *__restrict__ st, cons
   if (c0 >= C)
     return;
   __shared__ double t[REDUCE_ROWS][33];
-  const PlanView pv = plan_view(plan, grid_ctas);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 256 threads: ty in 0..7
   {
     const int m = m0 + ty, c = c0 + tx;
     double sum = 0.0;
     if (m < g.In && c < C) {
+      const bool tail = c >= C_main;
+      const PlanView pv = plan_view(tail ? plan_n : plan, grid_ctas);
       const int mt = plan_tile_of(m >> 3, pv.In8, pv.m_tiles);
-      const int nt = plan_tile_of(c >> 6, pv.NO, pv.n_tiles);
+      const int nt = tail ? 0 : plan_tile_of(c >> 6, pv.NO, pv.n_tiles);
       const int pair = nt * pv.m_tiles + mt;
       const int s0 = pv.pair_seg0[pair], s1 = pv.pair_seg0[pair + 1];
-      constexpr size_t TE = (size_t)M_TILE * N_TILE;
-      const double *p = ws + (size_t)s0 * TE + (m - 8 * plan_m8_start(mt, pv.In8, pv.m_tiles)) * N_TILE +
-                        (c - 64 * plan_oct_start(nt, pv.NO, pv.n_tiles));
+      const size_t TE = tail ? (size_t)M_TILE * NARROW_COLS : (size_t)M_TILE * N_TILE;
+      const int pitch = tail ? NARROW_COLS : N_TILE;
+      const double *p = (tail ? ws_n : ws) + (size_t)s0 * TE +
+                        (size_t)(m - 8 * plan_m8_start(mt, pv.In8, pv.m_tiles)) * pitch +
+                        (tail ? c - C_main : c - 64 * plan_oct_start(nt, pv.NO, pv.n_tiles));
       double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       int k = s0;
       for (; k + 8 <= s1; k += 8, p += 8 * TE) {
@@ -703,8 +789,8 @@ mttkrp_reduce_kernel(const MttkrpGeom g, const SchedState *__restrict__ st, cons
         for (int u = 0; u < 8; u++)
           a[u] += p[u * TE];
       }
-      for (int u = 0; k < s1; k++, u++, p += TE)
-        a[u] += *p;
+      for (; k < s1; k++, p += TE) // (a static index keeps the running sums in registers)
+        a[0] += *p;
       sum = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     }
     t[ty][tx] = sum;

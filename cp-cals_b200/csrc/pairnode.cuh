@@ -32,6 +32,7 @@ template <int WM, int WN> struct PairCfg {
 struct PairMaps {
   CUtensorMap X;    // 2-D view (I0, I1*I2) of the tensor in the caller's order: box [KT x M_TILE]
   CUtensorMap B[2]; // factor of mode 0 in buffer 0 / 1: box [KT x N_TILE]
+  CUtensorMap Bn[2]; // the same with a box of NARROW_COLS columns (narrow column tail, mttkrp.cuh)
 };
 
 struct PairGeom {
@@ -51,7 +52,9 @@ struct PairGeom {
 // same time share the factor tiles in L2 and the cheap tiles of the ragged last n-tile come last.  Both operands of a
 // K tile travel together through a two-stage TMA ring; the warp layout and the inner loop are those of
 // mttkrp_dmma_kernel (mma_stage) without the outer weight.
-template <int WM, int WN>
+// NARROW = false: columns [0, C_main).  NARROW = true: the narrow column tail [C_main, C) (mttkrp.cuh: narrow_cols) -- one
+// column tile, the eight warps split the rows of the m-tile, every warp covers the tail's n8 groups.
+template <int WM, int WN, bool NARROW = false>
 __global__ void __launch_bounds__(MTTKRP_THREADS, 1)
 pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const SchedState *__restrict__ st,
                  double *__restrict__ T) {
@@ -62,13 +65,14 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
   uint64_t *full = bars, *empty = bars + PAIR_STAGES;
 
   pdl_enter();
-  const int C = st->C, cur = st->cur;
-  if (C <= 0)
+  const int C = NARROW ? st->C : st->C_main, cur = st->cur;
+  const int c_lo = NARROW ? st->C_main : 0;
+  if (C - c_lo <= 0)
     return;
   const int m_tiles = (g.R + M_TILE - 1) / M_TILE;
   // column tiles: the 64-column octets are split evenly over ceil(NO / 4) tiles, as in the MTTKRP plan (263 columns = 5
   // octets give tiles of 2 and 3 octets, not 4 and 1: a 1-octet tile keeps one column group per warp busy)
-  const int NO = (C + 63) >> 6, n_tiles = (NO + OCT_TILE - 1) / OCT_TILE;
+  const int NO = NARROW ? 1 : (C + 63) >> 6, n_tiles = (NO + OCT_TILE - 1) / OCT_TILE;
   const long long tiles = (long long)m_tiles * n_tiles;
   const int P_tiles = (g.Ip + KT - 1) / KT;
   if ((long long)blockIdx.x >= tiles)
@@ -96,9 +100,15 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
       for (int pt = 0; pt < P_tiles; pt++) {
         unsigned char *stage = smem + sidx * Cfg::STAGE_BYTES;
         mbar_wait(&empty[sidx], ph);
-        mbar_expect_tx(&full[sidx], Cfg::STAGE_BYTES);
-        tma_load_2d(stage, &maps.X, &full[sidx], pt * KT, mt * M_TILE);
-        tma_load_2d(stage + Cfg::X_BYTES, tmB, &full[sidx], pt * KT, 64 * plan_oct_start(nt, NO, n_tiles));
+        if (NARROW) {
+          mbar_expect_tx(&full[sidx], Cfg::X_BYTES + NARROW_COLS * KT * 8);
+          tma_load_2d(stage, &maps.X, &full[sidx], pt * KT, mt * M_TILE);
+          tma_load_2d(stage + Cfg::X_BYTES, &maps.Bn[cur], &full[sidx], pt * KT, c_lo);
+        } else {
+          mbar_expect_tx(&full[sidx], Cfg::STAGE_BYTES);
+          tma_load_2d(stage, &maps.X, &full[sidx], pt * KT, mt * M_TILE);
+          tma_load_2d(stage + Cfg::X_BYTES, tmB, &full[sidx], pt * KT, 64 * plan_oct_start(nt, NO, n_tiles));
+        }
         if (++sidx == PAIR_STAGES) {
           sidx = 0;
           ph ^= 1;
@@ -120,8 +130,9 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
     const int nm = min(WM, (g.R - m0 + 7) >> 3);
     const int nn_tile = plan_nn(nt, NO, n_tiles); // octets of this tile: only their columns are this CTA's to write
     int nn = nn_tile;
-    if (c0 + 64 * (nn - 1) + 8 * warp >= C) // this warp's n8 group of the last octet starts beyond C (see mttkrp.cuh)
+    if (!NARROW && c0 + 64 * (nn - 1) + 8 * warp >= C) // this warp's n8 group of the last octet starts beyond C
       nn--;
+    const int g_tail = NARROW ? min(NARROW_GROUPS, (C - c_lo + 7) >> 3) : 0;
 #pragma unroll
     for (int i = 0; i < WM; i++)
 #pragma unroll
@@ -132,7 +143,11 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
       const double *Bw = (const double *)(smem + sidx * Cfg::STAGE_BYTES + Cfg::X_BYTES) + warp * 8 * KT;
       const int kvalid = min(KT, g.Ip - pt * KT);
       mbar_wait(&full[sidx], ph);
-      mma_stage<WM, WN, false>(acc, Xs, Bw, ones, (kvalid + 7) >> 3, r, s, nm, nn);
+      if (NARROW) {
+        if (warp < nm)
+          mma_narrow_stage<false>(acc[0], Xs, Bw - warp * 8 * KT, ones, (kvalid + 7) >> 3, r, s, warp, g_tail);
+      } else
+        mma_stage<WM, WN, false>(acc, Xs, Bw, ones, (kvalid + 7) >> 3, r, s, nm, nn);
       __syncwarp();
       if (lane == 0)
         mbar_arrive(&empty[sidx]);
@@ -140,6 +155,20 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
         sidx = 0;
         ph ^= 1;
       }
+    }
+    if (NARROW) { // warp = m8 row group, acc[0][q] = n8 group q of the tail
+      const int row = m0 + warp * 8 + r;
+      if (warp < nm && row < g.R) {
+#pragma unroll
+        for (int q = 0; q < NARROW_GROUPS; q++) {
+          const int col = c_lo + q * 8 + 2 * s;
+          if (col < C)
+            T[(size_t)col * g.ldT + row] = acc[0][q][0];
+          if (col + 1 < C)
+            T[(size_t)(col + 1) * g.ldT + row] = acc[0][q][1];
+        }
+      }
+      continue;
     }
     // rows m0 + 8i + r, columns c0 + 64j + 8*warp + 2s (+1): for one register the 8 lanes of equal s write 8 consecutive
     // rows of one column (64 B runs)

@@ -168,9 +168,18 @@ __global__ void __launch_bounds__(32) sched_kernel(const SchedParams p) {
   // benchmark step, every call of a parameter sweep) finds its tables in place instead of spending ~0.1 ms of a single
   // thread per mode on rebuilding them.
   const int C_now = sh_col;
-  if (C_now > 0 && lane < p.plans.n_modes && p.plans.built_for[lane] != C_now) {
-    mttkrp_make_plan(p.plans.plan[lane], p.plans.shape[lane], C_now, p.plans.G);
-    p.plans.built_for[lane] = C_now;
+  const int tail = st->narrow_on ? narrow_cols(C_now) : 0; // columns left to the narrow instances (mttkrp.cuh)
+  if (lane == 0)
+    st->C_main = C_now - tail;
+  if (C_now > 0 && lane < p.plans.n_modes) {
+    if (p.plans.built_for[lane] != C_now - tail) {
+      mttkrp_make_plan(p.plans.plan[lane], p.plans.shape[lane], C_now - tail, p.plans.G);
+      p.plans.built_for[lane] = C_now - tail;
+    }
+    if (tail > 0 && p.plans.plan_narrow[lane] != nullptr && p.plans.built_for[CALS_MAX_MODES + lane] != tail) {
+      mttkrp_make_plan(p.plans.plan_narrow[lane], p.plans.shape[lane], tail, p.plans.G);
+      p.plans.built_for[CALS_MAX_MODES + lane] = tail;
+    }
   }
 }
 
