@@ -84,7 +84,8 @@ def launch_list(path, out):
     for r in rows:
         name, val, unit = short_name(r[4]), float(r[-1].replace(",", "")), r[-2]
         ns = val * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1)
-        a = agg.setdefault(name, {"launches": 0, "ns": 0.0, "min_ns": 1e30, "max_ns": 0.0})
+        a = agg.setdefault(name, {"launches": 0, "ns": 0.0, "min_ns": 1e30, "max_ns": 0.0, "all": []})
+        a["all"].append(ns)
         if a["launches"] == 0:
             order.append(name)
         a["launches"] += 1
@@ -92,16 +93,21 @@ def launch_list(path, out):
         a["min_ns"] = min(a["min_ns"], ns)
         a["max_ns"] = max(a["max_ns"], ns)
         total += ns
-    kernels = [{"kernel": n, "launches": agg[n]["launches"], "total_ms": agg[n]["ns"] / 1e6,
-                "avg_us": agg[n]["ns"] / agg[n]["launches"] / 1e3, "min_us": agg[n]["min_ns"] / 1e3,
-                "max_us": agg[n]["max_ns"] / 1e3, "share": agg[n]["ns"] / total} for n in order]
+    def busy(a):  # launches that did work: the host runs a few passes ahead of the `done` flag, and the kernels of a
+        v = [x for x in a["all"] if x >= 0.2 * a["max_ns"]]  # pass that finds the queue drained exit at once
+        return {"busy_launches": len(v), "busy_avg_us": sum(v) / len(v) / 1e3}
+    kernels = [dict({"kernel": n, "launches": agg[n]["launches"], "total_ms": agg[n]["ns"] / 1e6,
+                     "avg_us": agg[n]["ns"] / agg[n]["launches"] / 1e3, "min_us": agg[n]["min_ns"] / 1e3,
+                     "max_us": agg[n]["max_ns"] / 1e3, "share": agg[n]["ns"] / total}, **busy(agg[n])) for n in order]
     kernels.sort(key=lambda k: -k["total_ms"])
     json.dump({"source": path, "note": "ncu --metrics gpu__time_duration.sum --clock-control none: per-launch times "
-               "are cold-cache and serialised -- read the SHARES", "launches": len(rows), "total_ms": total / 1e6,
+               "are cold-cache and serialised -- read the SHARES; avg_us includes the passes the host launches after the "
+               "queue has drained (kernels exit at once), busy_avg_us does not", "launches": len(rows), "total_ms": total / 1e6,
                "kernels": kernels}, open(out, "w"), indent=1)
     print("wrote", out)
     for k in kernels:
-        print("%-40s %6d launches %10.3f ms  %5.1f%%" % (k["kernel"], k["launches"], k["total_ms"], 100 * k["share"]))
+        print("%-40s %6d launches %10.3f ms  %5.1f%%  busy avg %8.1f us x %d" % (k["kernel"], k["launches"], k["total_ms"],
+                                                                             100 * k["share"], k["busy_avg_us"], k["busy_launches"]))
 
 
 def traffic(report, fingerprint_file, out):
