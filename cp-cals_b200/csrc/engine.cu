@@ -284,22 +284,29 @@ cudaError_t launch_chain(cals_b200_ctx *c, void (*kern)(KArgs...), dim3 grid, di
 constexpr int WN_FIXED = 4;
 constexpr int LS_CHUNKS = 48; // CTAs per trial model in the explicit-error kernel
 
-int wm_max() {
-  static int v = 0;
-  if (!v) {
-    const char *e = getenv("CALS_B200_WM_MAX"); // tuning knob: tallest CTA tile in m8 row groups (4..8)
-    v = e ? atoi(e) : 6;
-    if (v < 4 || v > 8)
-      v = 6;
+// Tallest CTA tile in m8 row groups.  6 for wide buffers (config 2, 2100 columns: 85.8 k model-iterations/s with 6,
+// 84.6 k with 8).  A narrow buffer -- the per-GPU shard of a strong-scaled model set -- has n-tiles of 2 or 3 octets, whose
+// stages are short against their fixed cost (barriers, weight fragments), and gains from taller tiles when the mode is
+// long enough to still fill the grid: 7 measured +1.1 % on the 8-way shard of config 2 (263 columns), +1.8 % on that of
+// config 4 (291), +1.4 % on the 4-way shard of config 2 (525); 100-row modes (config 1) lose 0.8 %.
+// CALS_B200_WM_MAX=4..8 overrides both.
+int wm_max(int In, int cols) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("CALS_B200_WM_MAX");
+    forced = e ? atoi(e) : 0;
+    if (forced < 4 || forced > 8)
+      forced = 0;
   }
-  return v;
+  if (forced)
+    return forced;
+  return (cols <= 640 && In >= 200) ? 7 : 6;
 }
 
-int pick_wm(int In, int tallest = 0) {
+int pick_wm(int In, int cols) {
   // m8 row groups are split evenly over ceil(In8 / tallest) m-tiles; the tile is then only as tall as that split needs,
   // so that most tiles are full and run the fully unrolled path.
-  if (tallest <= 0)
-    tallest = wm_max();
+  const int tallest = wm_max(In, cols);
   const int In8 = (In + 7) / 8;
   const int m_tiles = (In8 + tallest - 1) / tallest;
   const int wm = (In8 + m_tiles - 1) / m_tiles;
@@ -390,7 +397,7 @@ int build_mode_plans(cals_b200_ctx *c, Buffers &b) {
     if (S > 0x7fffffff / std::max(1, g.outer_dim[0] * g.P_tiles))
       return fail(c, "tensor too large for 32-bit chunk indices");
     g.S = (int)S;
-    const int wm = pick_wm(g.In);
+    const int wm = pick_wm(g.In, (int)b.cols);
     b.wm[n] = wm;
     g.m_tiles = (g.In + tile_m(wm) - 1) / tile_m(wm);
     b.mg[n] = g;
@@ -475,7 +482,7 @@ int build_node_slots(cals_b200_ctx *c, Buffers &b) {
     g.P_tiles = (g.Ip + KT - 1) / KT;
     g.QC = (g.outer_dim[0] + OC - 1) / OC;
     g.S = 1;
-    const int wm = pick_wm(R);
+    const int wm = pick_wm(R, (int)b.cols);
     b.wm[slot] = wm;
     g.m_tiles = (R + tile_m(wm) - 1) / tile_m(wm);
     b.mg[slot] = g;

@@ -20,10 +20,16 @@ MTTKRP_SHAPES = [
     ((20, 6, 5, 4, 3), 33),  # 5 modes
     ((64, 24, 50), 300),     # two n-tiles
     ((130, 17, 90), 513),    # several m-tiles, 3 n-tiles, K tail
-    # ragged last octet (csrc/mttkrp.cuh RaggedOctet): the units of a partly filled octet are dealt to all warps
-    ((200, 30, 20), 263),    # an 8-way shard of config 2: 5 octets, one valid n8 group in the last, 5 m8 groups per tile
+    # ragged last octet: warps whose n8 group of the last octet starts beyond C run one slot less (csrc/mttkrp.cuh)
+    ((200, 30, 20), 263),    # an 8-way shard of config 2: 5 octets in tiles of 2 and 3, one valid n8 group in the last
     ((56, 24, 10), 71),      # second octet of the only n-tile holds 7 columns; 7 m8 groups
-    ((24, 9, 5, 4), 137),    # 4 modes (slow outer weights of the units), third octet holds 9 columns
+    ((24, 9, 5, 4), 137),    # 4 modes (slow outer weights), third octet holds 9 columns
+    ((48, 20, 12), 289),     # 4 octets + 33 columns: five valid groups in the fifth octet
+    ((48, 20, 12), 296),     # ... exactly five groups
+    ((48, 20, 12), 297),     # ... and one column into the sixth group
+    ((33, 14, 9), 327),      # 6 octets in tiles of 3 and 3, the last holds 7 columns
+    ((30, 10, 6, 5), 537),   # 4 modes, 9 octets in three n-tiles, 25 columns in the last octet
+    ((72, 16, 11), 257),     # one column in the fifth octet; m-tiles of unequal height
     ((17, 16, 15), 1),       # a single column
 ]
 
@@ -211,6 +217,9 @@ def test_cp_cals_per_iteration_vs_oracle(pkg, modes, ranks, K, buffer):
     ((20, 44, 9, 31), list(range(1, 10)) * 8, 3, None),          # 4 modes, 360 columns, odd pitches in both layouts
     ((40, 56, 24), [20] * 13 + [3], 3, None),                    # 263 columns: ragged last octet in MTTKRP and pair GEMM
     ((30, 12, 9, 16), [7] * 10 + [1], 3, None),                  # 4 modes, 71 columns: ragged octet with slow outer modes
+    ((40, 52, 20), [20] * 14 + [9], 2, None),                    # 289 columns: five groups in the fifth octet, last m-tile of T ragged
+    ((24, 20, 12), [16] * 20 + [7], 2, None),                    # 327 columns: two n-tiles of 3 octets, 7 columns in the last
+    ((40, 41, 9), [20, 20, 20, 11, 20, 3, 20], 4, 71),           # queueing at 71 buffer columns: the ragged octet comes and goes
 ])
 def test_pair_node_equals_per_mode_mttkrp(pkg, modes, ranks, K, buffer):
     """Pair nodes (csrc/pairnode.cuh): 3-mode tensors take the MTTKRPs of modes 1 and 2 from T = X_(0)^T A_0, 4-mode
