@@ -465,8 +465,10 @@ def run_sharded(args, cfg_id, rank, world, local_rank, D, steps, warmup, main_li
     # ---------------- roofline of the dominant kernel (extra passes with per-kernel CUDA events) ----------------
     eng.set_timing(1)
     mt_ms, mt_launches, up_ms, gemm_ms, leaf_ms, tensor_flops, tree = 0.0, 0, 0.0, 0.0, 0.0, 0.0, False
+    fused_blocks = 0
     for _ in range(2):
         rep = eng.rerun()
+        fused_blocks = int(rep.fused_leaf_blocks)
         mt_ms += rep.mttkrp_ms
         up_ms += rep.update_ms
         mt_launches += rep.mttkrp_launches
@@ -514,11 +516,20 @@ def run_sharded(args, cfg_id, rank, world, local_rank, D, steps, warmup, main_li
         node_rows = [modes[1] * modes[2]] if len(modes) == 3 else [modes[0] * modes[1], modes[2] * modes[3]]
         full_modes = len(modes) - 2 * len(node_rows)
         leaf_launches = 2 * len(node_rows) * iters
-        leaf_bytes = sum(2 * 8.0 * r * C for r in node_rows) * iters  # every leaf streams its node's T once
+        if fused_blocks:
+            # 3 modes, first leaf in the contraction's epilogue: its pass reads fused_blocks partial results per element
+            # of G_1 (I1 x C) instead of T; the second leaf streams T once
+            leaf_bytes = (8.0 * node_rows[0] * C + 8.0 * fused_blocks * modes[1] * C) * iters
+        else:
+            leaf_bytes = sum(2 * 8.0 * r * C for r in node_rows) * iters  # every leaf streams its node's T once
         pn = {
             "what": "two modes take their MTTKRP from one shared contraction T (csrc/pairnode.cuh): %d tensor-sized "
                     "contractions per ALS iteration instead of %d; the leaf kernels stream T from HBM"
-                    % (full_modes + len(node_rows), len(modes)),
+                    % (full_modes + len(node_rows), len(modes)) +
+                    ("; the first leaf rides in the contraction's epilogue (its launch sums %d per-tile partial results "
+                     "per element), so T is read once per iteration and pair_contraction_tflops includes that work"
+                     % fused_blocks if fused_blocks else ""),
+            "first_leaf_fused": bool(fused_blocks),
             "mttkrp_dmma_ms_per_launch": (tensor_ms - gemm_ms) / (iters * full_modes) if full_modes else None,
             "pair_contraction_ms_per_launch": gemm_ms / (iters * len(node_rows)),
             "pair_contraction_tflops": flops_per_launch / (gemm_ms / (iters * len(node_rows)) * 1e-3) / 1e12,

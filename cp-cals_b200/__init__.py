@@ -53,7 +53,7 @@ class Report(C.Structure):
                 ("mttkrp_ms", C.c_double), ("update_ms", C.c_double), ("mttkrp_launches", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("mttkrp_flops", C.c_double), ("exchange_ms", C.c_double),
                 ("pair_gemm_ms", C.c_double), ("pair_leaf_ms", C.c_double), ("tensor_flops", C.c_double),
-                ("tree", C.c_int32), ("reserved_", C.c_int32)]
+                ("tree", C.c_int32), ("fused_leaf_blocks", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

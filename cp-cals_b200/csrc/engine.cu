@@ -58,6 +58,7 @@ struct Buffers {
   struct PairNode {
     PairGeom pg{};
     double *T = nullptr; // (E1 * E2) x cols
+    double *Gp = nullptr; // fused first leaf: partial results [ceil(E2 / pair_wm)][cols][ldF[mode_fast]]
     int slot = -1;       // -1: pair_gemm_kernel
   };
   bool tree = false;
@@ -316,15 +317,16 @@ int pick_wm(int In, int cols) {
 // Tile height of pair_gemm_kernel.  Both operands stream through the ring, so a taller tile has the better flop-per-byte
 // ratio (measured at 200^3 x 2100 columns: 31.6 / 33.6 / 34.6 TFLOP/s for 40 / 48 / 64 rows); small problems want enough
 // tiles to fill the last wave of the persistent grid.  Score = speed of the tile shape x fill of the waves.
-int pick_pair_wm(int R, int cols, int sms) {
+int pick_pair_wm(int E1, int E2, int cols, int sms) {
   static const double shape_speed[9] = {0, 0, 0, 0, 0.88, 0.915, 0.97, 0.985, 1.0};
-  const long long R8 = (R + 7) / 8, n_tiles = (cols + TileCfg<4, WN_FIXED>::N_TILE - 1) / TileCfg<4, WN_FIXED>::N_TILE;
+  const long long E1b = (E1 + 7) / 8, n_tiles = (cols + TileCfg<4, WN_FIXED>::N_TILE - 1) / TileCfg<4, WN_FIXED>::N_TILE;
   int best = 8;
   double best_score = -1.0;
-  for (int wm = 8; wm >= 4; wm--) {
-    const long long tiles = ((R8 + wm - 1) / wm) * n_tiles;
+  for (int wm = 8; wm >= 4; wm--) { // an m-tile is 8 values of i1 x wm values of i2
+    const long long E2b = (E2 + wm - 1) / wm;
+    const long long tiles = E1b * E2b * n_tiles;
     const long long waves = (tiles + sms - 1) / sms;
-    const double rows_used = (double)R8 / (double)(((R8 + wm - 1) / wm) * wm);
+    const double rows_used = ((double)E1 / (double)(8 * E1b)) * ((double)E2 / (double)(E2b * wm));
     const double score = shape_speed[wm] * rows_used * (double)tiles / (double)(waves * sms);
     if (score > best_score) {
       best_score = score;
@@ -511,6 +513,13 @@ int build_node_slots(cals_b200_ctx *c, Buffers &b) {
   return 0;
 }
 
+// CALS_B200_FUSED_LEAF: -1 unset (the buffer shape decides), 0 / 1 forced.  Read per run -- it is part of the allocation
+// signature -- so that one process can measure and test both forms of the first leaf.
+int fused_leaf_knob() {
+  const char *e = getenv("CALS_B200_FUSED_LEAF");
+  return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+}
+
 // Pair nodes need a 3- or 4-mode tensor that is whole on this device (or, 3 modes, sliced along mode 1 or 2) and factor
 // columns that fit the leaf kernels' shared memory (the run loop uses them with the tensor-core MTTKRP variant only); CALS_B200_NO_PAIR_NODE=1 keeps the three per-mode MTTKRPs (A/B measurements).
 bool pair_node_wanted(cals_b200_ctx *c) {
@@ -597,12 +606,38 @@ int alloc_buffers(cals_b200_ctx *c, Buffers &b, int cols, bool with_home_cols, i
       if (N == 3) {
         PairGeom &pg = b.node[0].pg;
         pg.Ip = c->xd[0];
-        b.pair_wm = pick_pair_wm(pg.R, cols, c->sm_count);
-        cuuint64_t dx[2] = {(cuuint64_t)c->xd[0], (cuuint64_t)pg.R};
-        cuuint64_t sx[1] = {(cuuint64_t)c->ldX0 * 8};
-        cuuint32_t bx[2] = {(cuuint32_t)KT, (cuuint32_t)tile_m(b.pair_wm)};
-        if (encode_map(c, &b.pmaps.X, c->Xp, 2, dx, sx, bx))
+        b.pair_wm = pick_pair_wm(pg.E1, pg.E2, cols, c->sm_count);
+        // m-tile = 8 values of i1 x pair_wm values of i2 (pairnode.cuh): one box of the 3-D view
+        cuuint64_t dx[3] = {(cuuint64_t)c->xd[0], (cuuint64_t)pg.E1, (cuuint64_t)pg.E2};
+        cuuint64_t sx[2] = {(cuuint64_t)c->ldX0 * 8, (cuuint64_t)c->ldX0 * pg.E1 * 8};
+        cuuint32_t bx[3] = {(cuuint32_t)KT, 8, (cuuint32_t)b.pair_wm};
+        if (encode_map(c, &b.pmaps.X, c->Xp, 3, dx, sx, bx))
           return 1;
+        // The first leaf rides in the contraction's epilogue (pairnode.cuh) unless its result is a partial sum that goes
+        // to the exchange buffer (sliced tensor over several GPUs).  Measured (gpurun_out/exp31, fused against separate
+        // pass): config 2 86.5 k against 84.8 k model-iterations/s, config 1 365 k against 341 k; the 8-way shard of
+        // config 2 -- 263 columns, where the TMA-fed slow leaf already streams T at HBM speed and the epilogue is a larger
+        // share of the short tiles -- 57.6 k against 58.0 k, so a narrow buffer over a large T keeps the separate pass.
+        // CALS_B200_FUSED_LEAF=0 / 1 forces either.
+        const int fl = fused_leaf_knob();
+        static const bool narrow_instance = getenv("CALS_B200_NARROW") != nullptr; // (its tiles carry no partials)
+        const bool narrow_big = cols <= LEAF_TMA_MAX_COLS && (size_t)pg.R * cols * 8 > ((size_t)32 << 20);
+        const bool want_fused = fl >= 0 ? fl != 0 : !narrow_big;
+        pg.fuse_slow = (want_fused && !narrow_instance && !(c->slice_mode >= 0 && c->comm_world > 1)) ? 1 : 0;
+        pg.ld_fast = geo.ldF[pg.mode_fast];
+        pg.gp_stride = (long long)cols * geo.ldF[pg.mode_fast];
+        if (pg.fuse_slow) {
+          const size_t E2b = (size_t)(pg.E2 + b.pair_wm - 1) / b.pair_wm;
+          if (dev_alloc(c, &b.node[0].Gp, E2b * (size_t)pg.gp_stride, b.allocs))
+            return 1;
+          for (int cu = 0; cu < 2; cu++) { // the slow factor's rows of a tile: [pair_wm rounded up to even] x TILE_N
+            cuuint64_t da[2] = {(cuuint64_t)pg.E2, (cuuint64_t)cols};
+            cuuint64_t sa[1] = {(cuuint64_t)geo.ldF[pg.mode_slow] * 8};
+            cuuint32_t ba[2] = {(cuuint32_t)((b.pair_wm + 1) & ~1), (cuuint32_t)TILE_N};
+            if (encode_map(c, &b.pmaps.A[cu], b.fac.buf[cu][pg.mode_slow] + pg.off_slow, 2, da, sa, ba))
+              return 1;
+          }
+        }
         for (int cu = 0; cu < 2; cu++) {
           cuuint64_t d2[2] = {(cuuint64_t)c->xd[0], (cuuint64_t)cols};
           cuuint64_t s2[1] = {(cuuint64_t)geo.ldF[0] * 8};
@@ -678,10 +713,10 @@ template <int WM> int launch_pair_gemm_wm(cals_b200_ctx *c, Buffers &b, bool att
   }
   if (!attr_only) {
     CU_TRY(c, launch_chain(c, kern, dim3(c->sm_count), dim3(MTTKRP_THREADS), (size_t)smem, b.pmaps, b.node[0].pg,
-                           (const SchedState *)c->d_st, b.node[0].T));
+                           (const SchedState *)c->d_st, b.node[0].T, b.node[0].Gp));
     if (b.narrow)
       CU_TRY(c, launch_chain(c, kern_n, dim3(c->sm_count), dim3(MTTKRP_THREADS), (size_t)smem, b.pmaps, b.node[0].pg,
-                             (const SchedState *)c->d_st, b.node[0].T));
+                             (const SchedState *)c->d_st, b.node[0].T, b.node[0].Gp));
   }
   return 0;
 }
@@ -713,7 +748,12 @@ int launch_pair_leaf(cals_b200_ctx *c, Buffers &b, int n, bool exchange) {
   x.xcap = (unsigned long long)c->xcap;
   x.seq_base = c->seq_base;
   x.n_modes = c->geo.n_modes;
-  if (n == pg.mode_fast) {
+  if (n == pg.mode_fast && pg.fuse_slow && nd.slot < 0 && !exchange) {
+    // the contraction's epilogue has left ceil(E2 / pair_wm) partial results per element
+    dim3 grid((unsigned)((pg.E1 + 255) / 256), (unsigned)b.cols);
+    CU_TRY(c, launch_chain(c, pair_partial_reduce_kernel, grid, dim3(256), (size_t)0, pg, (const SchedState *)c->d_st,
+                           (const double *)nd.Gp, (pg.E2 + b.pair_wm - 1) / b.pair_wm, b.G));
+  } else if (n == pg.mode_fast) {
     dim3 grid((unsigned)b.cols, (unsigned)((pg.E1 + 255) / 256));
     if (b.cols <= LEAF_TMA_MAX_COLS) // narrow grid: one TMA-fed stream per column
       CU_TRY(c, launch_chain(c, pair_leaf_slow_tma_kernel, grid, dim3(LEAF_THREADS), leaf_slow_smem(pg.E2), pg,
@@ -1064,6 +1104,7 @@ int prepare_run(cals_b200_ctx *c) {
   sig.push_back(c->buffer_cols);
   sig.push_back(c->ls_enabled ? 1 + c->ls_method : 0);
   sig.push_back(c->pair_node);
+  sig.push_back(fused_leaf_knob());
   for (int m = 0; m < M; m++)
     sig.push_back(c->hmodels[m].rank);
   const bool reuse = !c->run_sig.empty() && sig == c->run_sig && c->d_models && c->bufs.cols == c->buffer_cols;
@@ -1733,6 +1774,9 @@ int run_loop(cals_b200_ctx *c, cals_b200_report *rep, bool restore_home) {
     rep->mttkrp_flops = 2.0 * (double)c->nX * (double)N * (double)st.col_iter_sum;
     // flop that actually ran on the tensor cores: with the pair node two contractions per iteration instead of N
     rep->tree = tree ? 1 : 0;
+    rep->fused_leaf_blocks = (tree && N == 3 && b.node[0].pg.fuse_slow && !exchange)
+                                 ? (b.node[0].pg.E2 + b.pair_wm - 1) / b.pair_wm
+                                 : 0;
     int contractions = 0;
     for (int n = 0; n < N; n++)
       contractions += node_of(n) < 0 ? 1 : 0;

@@ -7,6 +7,10 @@
 //   leaves, for a pair (f, s) with T rows (i_f, i_s), i_f fastest:
 //                                  G_f[i_f, c] = sum_{i_s} T[(i_f,i_s), c] * A_s[i_s, c]        pair_leaf_slow_kernel (HBM-bound)
 //                                  G_s[i_s, c] = sum_{i_f} T[(i_f,i_s), c] * A_f[i_f, c]        pair_leaf_fast_kernel (HBM-bound)
+//   3 modes: the first leaf rides in the epilogue of pair_gemm_kernel (A_s is not touched between the contraction and
+//   the leaf): a tile of T covers 8 values of i_f x WM values of i_s, every thread multiplies its accumulators by A_s
+//   and sums them over the tile's i_s, and pair_partial_reduce_kernel adds the ceil(E2 / WM) partial results per
+//   element in fixed order -- T is then read once per iteration instead of twice.
 //
 // ALS updates mode f, then mode s, and T holds neither factor, so both leaves see exactly the factors the reference's
 // per-mode MTTKRPs see (src/cals.cpp:214-222 calls mttkrp::mttkrp once per mode): the sums are the same, only their
@@ -26,13 +30,20 @@ template <int WM, int WN> struct PairCfg {
   static constexpr int X_BYTES = M_TILE * KT * 8;
   static constexpr int B_BYTES = N_TILE * KT * 8;
   static constexpr int STAGE_BYTES = X_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = PAIR_STAGES * STAGE_BYTES + 256;
+  static constexpr int BAR_BYTES = 256;
+  // fused first leaf: the tile's WM rows of the slow factor, [N_TILE][WMP]; WMP = WM rounded up to even: TMA boxes are
+  // multiples of 16 bytes along the contiguous dimension and start at 16-byte granules (an odd first row makes the copy
+  // fault with "illegal instruction"), so for odd WM the box starts at the even row at or below the tile's first
+  static constexpr int WMP = (WM + 1) & ~1;
+  static constexpr int A_BYTES = N_TILE * WMP * 8;
+  static constexpr int SMEM_BYTES = PAIR_STAGES * STAGE_BYTES + BAR_BYTES + A_BYTES;
 };
 
 struct PairMaps {
-  CUtensorMap X;    // 2-D view (I0, I1*I2) of the tensor in the caller's order: box [KT x M_TILE]
+  CUtensorMap X;    // 3-D view (I0, I1, I2) of the tensor in the caller's order: box [KT x 8 x WM]
   CUtensorMap B[2]; // factor of mode 0 in buffer 0 / 1: box [KT x N_TILE]
   CUtensorMap Bn[2]; // the same with a box of NARROW_COLS columns (narrow column tail, mttkrp.cuh)
+  CUtensorMap A[2];  // factor of the slow mode of the pair in buffer 0 / 1: box [WMP x N_TILE] (fused first leaf)
 };
 
 struct PairGeom {
@@ -46,30 +57,42 @@ struct PairGeom {
   int off_fast, off_slow;
   long long ldT;
   int ldF[CALS_MAX_MODES]; // leading dimensions of the factor buffers == those of G for the same mode
+  // fused first leaf (3 modes, no exchange): partial results Gp[b2][c][i1], b2 = block of WM values of i2
+  int fuse_slow;
+  int ld_fast;         // ldF[mode_fast] (a plain field: the kernels index no parameter array at run time)
+  long long gp_stride; // doubles between the partial results of consecutive b2 (= buffer columns * ldF[mode_fast])
 };
 
 // T = X_(0)^T A_0.  Persistent CTAs over the (m-tile, n-tile) grid, m-tile fastest, so that the CTAs running at the
-// same time share the factor tiles in L2 and the cheap tiles of the ragged last n-tile come last.  Both operands of a
-// K tile travel together through a two-stage TMA ring; the warp layout and the inner loop are those of
-// mttkrp_dmma_kernel (mma_stage) without the outer weight.
+// same time share the factor tiles in L2 and the cheap tiles of the ragged last n-tile come last.  An m-tile is a patch
+// of 8 values of i1 x WM values of i2 (one TMA box of the 3-D tensor view): m8 row group i of the tile is i2 = i2_0 + i,
+// fragment row r is i1 = i1_0 + r.  Both operands of a K tile travel together through a two-stage TMA ring; the warp
+// layout and the inner loop are those of mttkrp_dmma_kernel (mma_stage) without the outer weight.
+// Epilogue: T, and -- g.fuse_slow -- the tile's share of the first leaf, Gp[b2][c][i1] = sum_i T[(i1, i2_0 + i), c] *
+// A_slow[i2_0 + i, c], which a thread forms from its own accumulators (no shuffles: a thread's WM accumulators of one
+// column are the WM values of i2 of one i1).
 // NARROW = false: columns [0, C_main).  NARROW = true: the narrow column tail [C_main, C) (mttkrp.cuh: narrow_cols) -- one
 // column tile, the eight warps split the rows of the m-tile, every warp covers the tail's n8 groups.
 template <int WM, int WN, bool NARROW = false>
 __global__ void __launch_bounds__(MTTKRP_THREADS, 1)
 pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const SchedState *__restrict__ st,
-                 double *__restrict__ T) {
+                 double *__restrict__ T, double *__restrict__ Gp) {
   using Cfg = PairCfg<WM, WN>;
-  constexpr int M_TILE = Cfg::M_TILE, N_TILE = Cfg::N_TILE;
+  constexpr int N_TILE = Cfg::N_TILE, WMP = Cfg::WMP;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t *bars = (uint64_t *)(smem + PAIR_STAGES * Cfg::STAGE_BYTES);
   uint64_t *full = bars, *empty = bars + PAIR_STAGES;
+  uint64_t *full_a = bars + 2 * PAIR_STAGES, *empty_a = full_a + 1;
+  double *As = (double *)(smem + PAIR_STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES); // [N_TILE][WMP]
+  const bool fuse = !NARROW && g.fuse_slow;
 
   pdl_enter();
   const int C = NARROW ? st->C : st->C_main, cur = st->cur;
   const int c_lo = NARROW ? st->C_main : 0;
   if (C - c_lo <= 0)
     return;
-  const int m_tiles = (g.R + M_TILE - 1) / M_TILE;
+  const int E1b = (g.E1 + 7) >> 3, E2b = (g.E2 + WM - 1) / WM;
+  const int m_tiles = E1b * E2b;
   // column tiles: the 64-column octets are split evenly over ceil(NO / 4) tiles, as in the MTTKRP plan (263 columns = 5
   // octets give tiles of 2 and 3 octets, not 4 and 1: a 1-octet tile keeps one column group per warp busy)
   const int NO = NARROW ? 1 : (C + 63) >> 6, n_tiles = (NO + OCT_TILE - 1) / OCT_TILE;
@@ -84,6 +107,8 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], NUM_MMA_WARPS);
     }
+    mbar_init(full_a, 1);
+    mbar_init(empty_a, NUM_MMA_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -94,24 +119,34 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
       return;
     const CUtensorMap *tmB = &maps.B[cur];
     int sidx = 0;
-    uint32_t ph = 1;
+    uint32_t ph = 1, aph = 1;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
       const int nt = (int)(t / m_tiles), mt = (int)(t - (long long)nt * m_tiles);
+      const int b2 = mt / E1b, b1 = mt - b2 * E1b;
       for (int pt = 0; pt < P_tiles; pt++) {
         unsigned char *stage = smem + sidx * Cfg::STAGE_BYTES;
         mbar_wait(&empty[sidx], ph);
         if (NARROW) {
           mbar_expect_tx(&full[sidx], Cfg::X_BYTES + NARROW_COLS * KT * 8);
-          tma_load_2d(stage, &maps.X, &full[sidx], pt * KT, mt * M_TILE);
+          tma_load_3d(stage, &maps.X, &full[sidx], pt * KT, 8 * b1, WM * b2);
           tma_load_2d(stage + Cfg::X_BYTES, &maps.Bn[cur], &full[sidx], pt * KT, c_lo);
         } else {
           mbar_expect_tx(&full[sidx], Cfg::STAGE_BYTES);
-          tma_load_2d(stage, &maps.X, &full[sidx], pt * KT, mt * M_TILE);
+          tma_load_3d(stage, &maps.X, &full[sidx], pt * KT, 8 * b1, WM * b2);
           tma_load_2d(stage + Cfg::X_BYTES, tmB, &full[sidx], pt * KT, 64 * plan_oct_start(nt, NO, n_tiles));
         }
         if (++sidx == PAIR_STAGES) {
           sidx = 0;
           ph ^= 1;
+        }
+        // The slow factor's rows of this tile are needed by the epilogue only and their buffer is free once the previous
+        // tile's epilogue is over: the copy is issued behind the tile's first PAIR_STAGES stage loads, which fill the ring
+        // while that epilogue still runs (ahead of them, the wait would hold back the ring at every tile boundary).
+        if (fuse && pt == min(PAIR_STAGES, P_tiles) - 1) {
+          mbar_wait(empty_a, aph);
+          aph ^= 1;
+          mbar_expect_tx(full_a, Cfg::A_BYTES);
+          tma_load_2d(As, &maps.A[cur], full_a, (WM * b2) & ~1, 64 * plan_oct_start(nt, NO, n_tiles));
         }
       }
     }
@@ -123,11 +158,13 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
   double acc[WM][WN][2];
   const double ones[WN] = {1.0, 1.0, 1.0, 1.0};
   int sidx = 0;
-  uint32_t ph = 0;
+  uint32_t ph = 0, aph = 0;
   for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int nt = (int)(t / m_tiles), mt = (int)(t - (long long)nt * m_tiles);
-    const int m0 = mt * M_TILE, c0 = 64 * plan_oct_start(nt, NO, n_tiles);
-    const int nm = min(WM, (g.R - m0 + 7) >> 3);
+    const int b2 = mt / E1b, b1 = mt - b2 * E1b;
+    const int i1 = 8 * b1 + r, i2_0 = WM * b2; // this thread's i1; row group i of the tile is i2 = i2_0 + i
+    const int c0 = 64 * plan_oct_start(nt, NO, n_tiles);
+    const int nm = min(WM, g.E2 - i2_0);
     const int nn_tile = plan_nn(nt, NO, n_tiles); // octets of this tile: only their columns are this CTA's to write
     int nn = nn_tile;
     if (!NARROW && c0 + 64 * (nn - 1) + 8 * warp >= C) // this warp's n8 group of the last octet starts beyond C
@@ -156,9 +193,9 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
         ph ^= 1;
       }
     }
-    if (NARROW) { // warp = m8 row group, acc[0][q] = n8 group q of the tail
-      const int row = m0 + warp * 8 + r;
-      if (warp < nm && row < g.R) {
+    if (NARROW) { // warp = m8 row group (= i2_0 + warp), acc[0][q] = n8 group q of the tail
+      const size_t row = (size_t)i1 + (size_t)g.E1 * (i2_0 + warp);
+      if (warp < nm && i1 < g.E1) {
 #pragma unroll
         for (int q = 0; q < NARROW_GROUPS; q++) {
           const int col = c_lo + q * 8 + 2 * s;
@@ -168,25 +205,81 @@ pair_gemm_kernel(const __grid_constant__ PairMaps maps, const PairGeom g, const 
             T[(size_t)(col + 1) * g.ldT + row] = acc[0][q][1];
         }
       }
-      continue;
+      continue; // (the narrow instance never runs together with the fused leaf: engine.cu)
     }
-    // rows m0 + 8i + r, columns c0 + 64j + 8*warp + 2s (+1): for one register the 8 lanes of equal s write 8 consecutive
-    // rows of one column (64 B runs)
+    // rows (i1_0 + r) + E1 * (i2_0 + i), columns c0 + 64j + 8*warp + 2s (+1): for one register the 8 lanes of equal s
+    // write 8 consecutive rows of one column (64 B runs).  One pointer per column, stepped by E1 from row group to row group.
+    if (fuse)
+      mbar_wait(full_a, aph);
+    if (i1 < g.E1) {
+      double *gp = Gp + (size_t)b2 * g.gp_stride + i1;
+      const int ldG = g.ld_fast;
 #pragma unroll
-    for (int i = 0; i < WM; i++) {
-      const int row = m0 + i * 8 + r;
-      if (row < g.R) {
+      for (int j = 0; j < WN; j++) {
 #pragma unroll
-        for (int j = 0; j < WN; j++) {
-          const int col = c0 + j * 64 + warp * 8 + 2 * s;
-          if (j < nn_tile && col < C)
-            T[(size_t)col * g.ldT + row] = acc[i][j][0];
-          if (j < nn_tile && col + 1 < C)
-            T[(size_t)(col + 1) * g.ldT + row] = acc[i][j][1];
+        for (int e = 0; e < 2; e++) {
+          const int cl = j * 64 + warp * 8 + 2 * s + e, col = c0 + cl; // column inside the tile / of the buffer
+          if (j < nn_tile && col < C) {
+            double *tp = T + (size_t)col * g.ldT + ((size_t)i1 + (size_t)g.E1 * i2_0);
+#pragma unroll
+            for (int i = 0; i < WM; i++) {
+              if (i < nm)
+                *tp = acc[i][j][e];
+              tp += g.E1;
+            }
+            if (fuse) { // accumulators of row groups beyond nm are zero, so the sum may run over all WM
+              double p = 0.0;
+              if (WM & 1) { // the box starts at an even row: the tile's first row is its row (WM * b2) & 1
+                const double *w = As + cl * WMP + ((WM * b2) & 1);
+#pragma unroll
+                for (int i = 0; i < WM; i++)
+                  p = fma(acc[i][j][e], w[i], p);
+              } else {
+                const double2 *w = reinterpret_cast<const double2 *>(As + cl * WMP);
+#pragma unroll
+                for (int i = 0; i < WM / 2; i++) {
+                  const double2 v = w[i];
+                  p = fma(acc[2 * i][j][e], v.x, p);
+                  p = fma(acc[2 * i + 1][j][e], v.y, p);
+                }
+              }
+              gp[(size_t)col * ldG] = p;
+            }
+          }
         }
       }
     }
+    if (fuse) {
+      aph ^= 1;
+      __syncwarp();
+      if (lane == 0)
+        mbar_arrive(empty_a);
+    }
   }
+}
+
+// First leaf from the partial results of pair_gemm_kernel's epilogue: G_fast[i1, c] = sum_{b2} Gp[b2][c][i1], b2 in
+// ascending order (deterministic).  One thread per element, i1 fastest; the E2b partial slices are L2-resident right
+// after the contraction when they fit (config 2: 25 x 3.4 MB).
+__global__ void __launch_bounds__(256)
+pair_partial_reduce_kernel(const PairGeom g, const SchedState *__restrict__ st, const double *__restrict__ Gp, int E2b,
+                           double *__restrict__ G) {
+  pdl_enter();
+  const int C = st->C;
+  const int c = blockIdx.y, i1 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C || i1 >= g.E1)
+    return;
+  const double *p = Gp + (size_t)c * g.ld_fast + i1;
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  int k = 0;
+  for (; k + 4 <= E2b; k += 4, p += 4 * g.gp_stride) {
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      a[u] += p[u * g.gp_stride];
+  }
+  for (; k < E2b; k++, p += g.gp_stride)
+    a[0] += *p;
+  G[(size_t)c * g.ld_fast + i1 + g.off_fast] = (a[0] + a[1]) + (a[2] + a[3]);
 }
 
 // Slab mode over several GPUs: a leaf's result is this device's PARTIAL sum (or its own row block) and goes to the exchange

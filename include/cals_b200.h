@@ -57,7 +57,8 @@ typedef struct cals_b200_report {
   double pair_leaf_ms;       /* timing: CUDA-event time summed over the leaf kernels that read T (part of mttkrp_ms) */
   double tensor_flops;       /* flop that actually ran on the FP64 tensor cores (== mttkrp_flops without the pair node) */
   int32_t tree;              /* 1 when the pair node was used by this run */
-  int32_t reserved_;
+  int32_t fused_leaf_blocks; /* > 0: the first leaf of the 3-mode pair node rode in the contraction's epilogue; the number
+                                of partial results per element that pair_partial_reduce_kernel summed (ceil(I2 / tile)) */
 } cals_b200_report;
 
 typedef struct cals_b200_model_stats {

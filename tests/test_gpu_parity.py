@@ -245,6 +245,28 @@ def test_pair_node_equals_per_mode_mttkrp(pkg, modes, ranks, K, buffer):
         assert abs(a.fit - b.fit) <= 1e-12
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("modes,ranks,K", [
+    ((37, 45, 23), [4, 9, 1, 12, 7], 4),       # i1 not a multiple of 8, i2 not a multiple of any tile height
+    ((40, 56, 24), [20] * 13 + [3], 3),        # 263 columns: two n-tiles
+    ((16, 8, 100), [5, 6], 3),                 # one i1 block, many i2 blocks: many partial results per element
+    ((16, 203, 3), [5, 6, 2], 3),              # many i1 blocks, a single short i2 block
+])
+def test_first_leaf_fused_and_separate(pkg, monkeypatch, fused, modes, ranks, K):
+    """The first leaf of a 3-mode pair node either rides in the epilogue of the contraction (per-tile partial results,
+    summed in fixed order by pair_partial_reduce_kernel) or runs as its own pass over T (csrc/pairnode.cuh;
+    CALS_B200_FUSED_LEAF=0/1 forces either, the default depends on the buffer shape).  Both against the oracle."""
+    monkeypatch.setenv("CALS_B200_FUSED_LEAF", fused)
+    rng = np.random.default_rng(hash((modes, K, 11)) % 2 ** 32)
+    X = rng.uniform(-1, 1, size=modes)
+    ms = caseio.random_models(rng, modes, ranks)
+    want = oracle.cp_cals(X, ms, max_iter=K, force_max_iter=True, buffer_size=sum(ranks))
+    kts = to_ktensors(pkg, ms)
+    rep = pkg.cp_cals(X, kts, pkg.CalsParams(max_iterations=K, buffer_size=sum(ranks), force_max_iter=True))
+    assert rep.pair_node
+    assert_models_close(kts, want.models, want.x_norm, what="fused leaf " + fused)
+
+
 def test_pair_node_with_jackknife_nnls_and_line_search(pkg):
     """The pair node only replaces where G comes from: flagged (jackknife) models, the NNLS update and line search
     give the same results with and without it."""

@@ -16,9 +16,9 @@ for t in "2 1 5 c2" "2 8 5 c2s8" "1 1 10 c1" "4 8 2 c4s8"; do
   rm -f $O/launches_$4.csv
 done
 # full captures: small kernels at config 2, all kernels of the 8-way shard of config 2, the contraction of config 4's shard
-ncu --set full --clock-control none -k 'regex:model_update|pair_leaf|mttkrp_reduce|sched_kernel|move_kernel' -s 12 -c 9 -f -o $O/small_c2 python tools/ncu_target_cfg.py 2 1 4 > $O/small_c2.log 2>&1
+ncu --set full --clock-control none -k 'regex:model_update|pair_leaf|pair_partial_reduce|mttkrp_reduce|sched_kernel|move_kernel' -s 12 -c 9 -f -o $O/small_c2 python tools/ncu_target_cfg.py 2 1 4 > $O/small_c2.log 2>&1
 python tools/ncu_summary.py full $O/small_c2.ncu-rep $O/small_kernels_c2_full.json; rm -f $O/small_c2.ncu-rep
-ncu --set full --clock-control none -k 'regex:mttkrp_dmma|pair_gemm|model_update|pair_leaf|mttkrp_reduce' -s 9 -c 9 -f -o $O/shard_c2s8 python tools/ncu_target_cfg.py 2 8 4 > $O/shard_c2s8.log 2>&1
+ncu --set full --clock-control none -k 'regex:mttkrp_dmma|pair_gemm|model_update|pair_leaf|pair_partial_reduce|mttkrp_reduce' -s 9 -c 9 -f -o $O/shard_c2s8 python tools/ncu_target_cfg.py 2 8 4 > $O/shard_c2s8.log 2>&1
 python tools/ncu_summary.py full $O/shard_c2s8.ncu-rep $O/shard_c2s8_full.json; rm -f $O/shard_c2s8.ncu-rep
 ncu --set full --clock-control none -k 'regex:mttkrp_dmma' -s 2 -c 2 -f -o $O/shard_c4s8 python tools/ncu_target_cfg.py 4 8 2 > $O/shard_c4s8.log 2>&1
 python tools/ncu_summary.py full $O/shard_c4s8.ncu-rep $O/shard_c4s8_full.json; rm -f $O/shard_c4s8.ncu-rep
